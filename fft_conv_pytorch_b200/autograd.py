@@ -1,0 +1,111 @@
+"""Backward pass of the FFT convolution, built from the same forward kernels.
+
+The reference has no custom autograd: torch differentiates through rfftn / einsum / irfftn
+(reference tests pin ``weight.grad`` and ``bias.grad``: tests/test_functional.py:72-117,
+tests/test_functional_transpose.py:73-124). Here the op is opaque to autograd, so the adjoints are written out;
+every one of them is again a (transposed) convolution and runs on the same sm_100a kernels:
+
+  y = conv(x, w)                      grad_x = conv_transpose(grad_y, w)        grad_w = corr(x_pad, grad_y) sampled on the dilation lattice
+  y = conv_transpose(x, w)            grad_x = conv(grad_y, w)                  grad_w = corr(grad_y_pad, x) sampled on the dilation lattice
+  grad_bias = sum of grad_y over batch and space
+
+The weight gradients are evaluated as convolutions with batch and channel roles swapped (stride <-> dilation).
+Non-zero padding modes are differentiated by padding explicitly with ``F.pad`` first.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+
+def _raw_conv(transposed: bool, x: Tensor, w: Tensor, b: Optional[Tensor], stride, padding, opad, dilation, groups: int) -> Tensor:
+    """The non-differentiable op (zero padding mode). Tests substitute an oracle-backed implementation."""
+    from . import functional as Fn
+
+    with torch.no_grad():
+        return Fn._run(transposed, x, w, b, stride, padding, opad, dilation, groups, "constant")
+
+
+def _swap(t: Tensor) -> Tensor:
+    """(A, B, *sp) -> (B, A, *sp), contiguous."""
+    return t.transpose(0, 1).contiguous()
+
+
+def _crop(t: Tensor, sizes: Tuple[int, ...]) -> Tensor:
+    idx = (slice(None), slice(None)) + tuple(slice(0, s) for s in sizes)
+    return t[idx]
+
+
+def _grad_weight_fwd(x: Tensor, gy: Tensor, ksize, stride, padding, dilation, groups: int) -> Tensor:
+    """grad_w[o, i, m] = sum_{b, j} gy[b, o, j] * xpad[b, i, j*s + m*d]  -> (Cout, Cin/g, *K)."""
+    B, cin = x.shape[:2]
+    cout = gy.shape[1]
+    ig, og = cin // groups, cout // groups
+    outs = []
+    for g in range(groups):
+        xs = _swap(x[:, g * ig:(g + 1) * ig])       # (ig, B, *L)      "batch" = input channel, "channels" = batch
+        gs = _swap(gy[:, g * og:(g + 1) * og])      # (og, B, *Lout)   kernel: out = output channel, in = batch
+        r = _raw_conv(False, xs, gs, None, dilation, padding, 0, stride, 1)  # (ig, og, *K')
+        outs.append(_swap(_crop(r, ksize)))         # (og, ig, *K)
+    return torch.cat(outs, 0)
+
+
+def _grad_weight_tr(x: Tensor, gy: Tensor, ksize, stride, padding, dilation, groups: int) -> Tensor:
+    """grad_w[i, o, m] = sum_{b, q} x[b, i, q] * gypad[b, o, q*t + m*d]  -> (Cin, Cout/g, *K)."""
+    B, cin = x.shape[:2]
+    cout = gy.shape[1]
+    ig, og = cin // groups, cout // groups
+    outs = []
+    for g in range(groups):
+        gs = _swap(gy[:, g * og:(g + 1) * og])      # (og, B, *Lout)  signal
+        xs = _swap(x[:, g * ig:(g + 1) * ig])       # (ig, B, *L)     kernel
+        r = _raw_conv(False, gs, xs, None, dilation, padding, 0, stride, 1)  # (og, ig, *K')
+        outs.append(_swap(_crop(r, ksize)))         # (ig, og, *K)
+    return torch.cat(outs, 0)
+
+
+class _FFTConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, transposed, stride, padding, opad, dilation, groups):
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (transposed, stride, padding, opad, dilation, groups, b is not None)
+        return _raw_conv(transposed, x, w, b, stride, padding, opad, dilation, groups)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        transposed, stride, padding, opad, dilation, groups, has_bias = ctx.cfg
+        gy = gy.contiguous()
+        n = x.ndim - 2
+        ksize = tuple(w.shape[2:])
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            if not transposed:
+                # adjoint of a strided conv is a transposed conv; output_padding restores the rows the stride dropped
+                op = tuple(
+                    x.shape[2 + i] - ((gy.shape[2 + i] - 1) * stride[i] - 2 * padding[i] + dilation[i] * (ksize[i] - 1) + 1)
+                    for i in range(n)
+                )
+                gx = _raw_conv(True, gy, w, None, stride, padding, op, dilation, groups)
+            else:
+                gx = _crop(_raw_conv(False, gy, w, None, stride, padding, 0, dilation, groups), tuple(x.shape[2:]))
+        if ctx.needs_input_grad[1]:
+            if not transposed:
+                gw = _grad_weight_fwd(x, gy, ksize, stride, padding, dilation, groups)
+            else:
+                gw = _grad_weight_tr(x, gy, ksize, stride, padding, dilation, groups)
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(dim=(0,) + tuple(range(2, gy.ndim)))
+        return gx, gw, gb, None, None, None, None, None, None
+
+
+def conv_with_grad(transposed: bool, signal: Tensor, kernel: Tensor, bias: Optional[Tensor], stride, padding, opad, dilation,
+                   groups: int, padding_mode: str) -> Tensor:
+    if not transposed and padding_mode != "constant" and any(p != 0 for p in padding):
+        pads = [p for p in padding[::-1] for _ in range(2)]
+        signal = F.pad(signal, pads, mode=padding_mode)  # differentiable; the conv itself then runs unpadded
+        padding = (0,) * len(padding)
+    return _FFTConvFn.apply(signal, kernel, bias, transposed, tuple(stride), tuple(padding), tuple(opad), tuple(dilation), groups)

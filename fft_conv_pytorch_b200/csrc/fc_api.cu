@@ -1,0 +1,282 @@
+// fc_api.cu — the C ABI of include/fftconv_b200.h: plan management and kernel launches.
+// Compiled by nvcc for sm_100a into libfftconv_b200.so. (tests/cpu_emul compiles the same file with
+// -DFC_CPU_EMUL as host C++ to exercise the kernel logic without a GPU; that build is test-only.)
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "fc_kernels.cuh"
+#include "fc_plan.h"
+#ifndef FC_CPU_EMUL
+#include "fc_fused.cuh"
+#endif
+
+#ifdef FC_CPU_EMUL
+#define FC_LAUNCH(kfn, grid, block, smem, stream, arg) fc_emul_launch(grid, block, smem, [=]() { kfn(arg); })
+#else
+#define FC_LAUNCH(kfn, grid, block, smem, stream, arg) kfn<<<grid, block, smem, stream>>>(arg)
+#endif
+
+namespace {
+
+thread_local std::string g_err;
+
+int set_err(int code, const std::string& m) {
+  g_err = m;
+  return code;
+}
+
+int check_cuda(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err((int)e, std::string(what) + ": " + cudaGetErrorString(e));
+  return FC_OK;
+}
+
+const int kMaxSmem = 200 * 1024;
+int g_num_sms = 148;
+
+void init_once() {
+  static std::once_flag flag;
+  std::call_once(flag, []() {
+#ifndef FC_CPU_EMUL
+    cudaFuncSetAttribute(fc_pass_kernel<FC_R2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(fc_pass_kernel<FC_C2C_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(fc_pass_kernel<FC_C2C_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(fc_pass_kernel<FC_C2R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      g_num_sms = sms;
+    fc_fused_init();
+    cudaGetLastError();
+#endif
+  });
+}
+
+int launch_pass(const fc_plan* pl, const fc_pass& p, const void* in, void* out, const float2* tw, const float* bias, cudaStream_t st) {
+  fc_pass_args a;
+  a.p = p;
+  a.in = in;
+  a.out = out;
+  a.tw = tw;
+  a.bias = bias;
+  if (p.kind == FC_C2R) a.p.has_bias = bias ? 1 : 0;
+  const size_t smem = (size_t)2 * p.T * p.pitch * sizeof(float2);
+  if (smem > (size_t)kMaxSmem) return set_err(FC_EUNSUPPORTED, "pass tile does not fit shared memory");
+  // Persistent CTAs: enough to fill every SM at the occupancy the tile allows, never more than there are tiles.
+  int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(smem + 1024);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int64_t grid = (int64_t)g_num_sms * per_sm;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  if (grid < 1) return FC_OK;
+  dim3 g((unsigned)grid), b((unsigned)pl->threads);
+  switch (p.kind) {
+    case FC_R2C: {
+      auto k = fc_pass_kernel<FC_R2C>;
+      FC_LAUNCH(k, g, b, smem, st, a);
+    } break;
+    case FC_C2C_FWD: {
+      auto k = fc_pass_kernel<FC_C2C_FWD>;
+      FC_LAUNCH(k, g, b, smem, st, a);
+    } break;
+    case FC_C2C_INV: {
+      auto k = fc_pass_kernel<FC_C2C_INV>;
+      FC_LAUNCH(k, g, b, smem, st, a);
+    } break;
+    default: {
+      auto k = fc_pass_kernel<FC_C2R>;
+      FC_LAUNCH(k, g, b, smem, st, a);
+    } break;
+  }
+  return check_cuda("axis pass launch");
+}
+
+int launch_contract(const float2* X, const float2* K, float2* Y, int64_t bins, int batch, int cin, int cout, int groups, cudaStream_t st) {
+  fc_contract_args a;
+  a.X = X;
+  a.K = K;
+  a.Y = Y;
+  a.bins = bins;
+  a.batch = batch;
+  a.cin = cin;
+  a.cout = cout;
+  a.groups = groups;
+  const int Og = cout / groups;
+  const int threads = 128;
+  const unsigned gx = (unsigned)((bins + threads - 1) / threads);
+  if (batch >= 5 && Og >= 5) {
+    a.btiles = (batch + 7) / 8;
+    a.otiles = (Og + 7) / 8;
+    dim3 g(gx, (unsigned)(a.btiles * a.otiles), (unsigned)groups), b(threads);
+    auto k = fc_contract_kernel<8, 8>;
+    FC_LAUNCH(k, g, b, 0, st, a);
+  } else if (batch >= 3 || Og >= 3) {
+    a.btiles = (batch + 3) / 4;
+    a.otiles = (Og + 3) / 4;
+    dim3 g(gx, (unsigned)(a.btiles * a.otiles), (unsigned)groups), b(threads);
+    auto k = fc_contract_kernel<4, 4>;
+    FC_LAUNCH(k, g, b, 0, st, a);
+  } else {
+    a.btiles = (batch + 1) / 2;
+    a.otiles = (Og + 1) / 2;
+    dim3 g(gx, (unsigned)(a.btiles * a.otiles), (unsigned)groups), b(threads);
+    auto k = fc_contract_kernel<2, 2>;
+    FC_LAUNCH(k, g, b, 0, st, a);
+  }
+  return check_cuda("contraction launch");
+}
+
+// Resolve a buffer id of a step to a pointer.
+struct Bufs {
+  const void* user_in;
+  void* spec;
+  void* sA;
+  void* sB;
+  void* user_out;
+};
+void* buf_ptr(const Bufs& b, int id) {
+  switch (id) {
+    case FC_BUF_USER_IN: return const_cast<void*>(b.user_in);
+    case FC_BUF_SPEC: return b.spec;
+    case FC_BUF_SA: return b.sA;
+    case FC_BUF_SB: return b.sB;
+    default: return b.user_out;
+  }
+}
+
+int run_steps(const fc_plan* pl, const std::vector<fc_step>& steps, const Bufs& b, const float2* tw, const float* bias, cudaStream_t st) {
+  for (const fc_step& s : steps) {
+    int rc = launch_pass(pl, s.pass, buf_ptr(b, s.src), buf_ptr(b, s.dst), tw, bias, st);
+    if (rc) return rc;
+  }
+  return FC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fc_last_error(void) { return g_err.c_str(); }
+const char* fc_version(void) { return "fftconv_b200 0.1 (sm_100a)"; }
+
+int fc_plan_create(fc_plan** out, const fc_problem* problem) {
+  if (!out || !problem) return set_err(FC_ENULL, "fc_plan_create: NULL argument");
+  *out = nullptr;
+  fc_plan* pl = new fc_plan();
+  std::string msg;
+  int rc = fc_plan_build(pl, problem, &msg);
+  if (rc) {
+    delete pl;
+    return set_err(rc, msg);
+  }
+#ifndef FC_CPU_EMUL
+  fc_fused_plan(pl);
+#endif
+  *out = pl;
+  return FC_OK;
+}
+
+void fc_plan_destroy(fc_plan* plan) { delete plan; }
+
+int fc_plan_get_info(const fc_plan* plan, fc_plan_info* info) {
+  if (!plan || !info) return set_err(FC_ENULL, "fc_plan_get_info: NULL argument");
+  *info = plan->info;
+  return FC_OK;
+}
+
+int fc_plan_describe(const fc_plan* plan, char* buf, size_t buflen) {
+  if (!plan || !buf || !buflen) return set_err(FC_ENULL, "fc_plan_describe: NULL argument");
+  std::string s = fc_plan_to_string(plan);
+  size_t n = s.size() < buflen - 1 ? s.size() : buflen - 1;
+  std::memcpy(buf, s.data(), n);
+  buf[n] = 0;
+  return (int)n;
+}
+
+int fc_plan_init_const(const fc_plan* plan, void* d_const, void* stream) {
+  if (!plan || !d_const) return set_err(FC_ENULL, "fc_plan_init_const: NULL argument");
+  init_once();
+  dim3 g((unsigned)((plan->tw_len + 255) / 256)), b(256);
+  if (g.x > 64) g.x = 64;
+  float2* tw = reinterpret_cast<float2*>(d_const);
+  const int len = plan->tw_len;
+#ifdef FC_CPU_EMUL
+  fc_emul_launch(g, b, 0, [=]() { fc_twiddle_kernel(tw, len); });
+#else
+  fc_twiddle_kernel<<<g, b, 0, (cudaStream_t)stream>>>(tw, len);
+#endif
+  return check_cuda("twiddle table launch");
+}
+
+int fc_signal_spectrum(const fc_plan* plan, const void* d_const, const float* d_x, float* d_xspec, void* d_ws, void* stream) {
+  if (!plan || !d_const || !d_x || !d_xspec || !d_ws) return set_err(FC_ENULL, "fc_signal_spectrum: NULL argument");
+  init_once();
+  Bufs b{d_x, d_xspec, (char*)d_ws + plan->off_sA, (char*)d_ws + plan->off_sB, nullptr};
+  return run_steps(plan, plan->sig_fwd, b, (const float2*)d_const, nullptr, (cudaStream_t)stream);
+}
+
+int fc_kernel_spectrum(const fc_plan* plan, const void* d_const, const float* d_w, float* d_kspec, void* d_ws, void* stream) {
+  if (!plan || !d_const || !d_w || !d_kspec || !d_ws) return set_err(FC_ENULL, "fc_kernel_spectrum: NULL argument");
+  init_once();
+  Bufs b{d_w, d_kspec, (char*)d_ws + plan->off_sA, (char*)d_ws + plan->off_sB, nullptr};
+  return run_steps(plan, plan->ker_fwd, b, (const float2*)d_const, nullptr, (cudaStream_t)stream);
+}
+
+int fc_contract(const fc_plan* plan, const float* d_xspec, const float* d_kspec, float* d_yspec, void* stream) {
+  if (!plan || !d_xspec || !d_kspec || !d_yspec) return set_err(FC_ENULL, "fc_contract: NULL argument");
+  init_once();
+  const fc_contract_desc& c = plan->contract;
+  return launch_contract((const float2*)d_xspec, (const float2*)d_kspec, (float2*)d_yspec, c.bins, c.batch, c.cin, c.cout, c.groups,
+                         (cudaStream_t)stream);
+}
+
+int fc_inverse(const fc_plan* plan, const void* d_const, const float* d_yspec, const float* d_bias, float* d_y, void* d_ws, void* stream) {
+  if (!plan || !d_const || !d_yspec || !d_y || !d_ws) return set_err(FC_ENULL, "fc_inverse: NULL argument");
+  init_once();
+  Bufs b{nullptr, const_cast<float*>(d_yspec), (char*)d_ws + plan->off_sA, (char*)d_ws + plan->off_sB, d_y};
+  return run_steps(plan, plan->inv, b, (const float2*)d_const, d_bias, (cudaStream_t)stream);
+}
+
+int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const float* d_kspec, const float* d_bias, float* d_y, void* d_ws,
+            void* stream) {
+  if (!plan || !d_const || !d_x || !d_kspec || !d_y || !d_ws) return set_err(FC_ENULL, "fc_conv: NULL argument");
+  init_once();
+#ifndef FC_CPU_EMUL
+  if (plan->fused.enabled) return fc_fused_conv(plan, (const float2*)d_const, d_x, (const float2*)d_kspec, d_bias, d_y, d_ws, (cudaStream_t)stream);
+#endif
+  float* xspec = (float*)((char*)d_ws + plan->off_xspec);
+  float* yspec = (float*)((char*)d_ws + plan->off_yspec);
+  int rc = fc_signal_spectrum(plan, d_const, d_x, xspec, d_ws, stream);
+  if (rc) return rc;
+  rc = fc_contract(plan, xspec, d_kspec, yspec, stream);
+  if (rc) return rc;
+  return fc_inverse(plan, d_const, yspec, d_bias, d_y, d_ws, stream);
+}
+
+int fc_conv_host(const fc_plan* plan, const void* d_const, const float* h_x, float* d_x_stage, const float* d_kspec, const float* d_bias,
+                 float* d_y_stage, float* h_y, void* d_ws, void* stream) {
+  if (!plan || !h_x || !d_x_stage || !d_y_stage || !h_y) return set_err(FC_ENULL, "fc_conv_host: NULL argument");
+  const fc_problem& P = plan->prob;
+  int64_t in_elems = (int64_t)P.batch * P.cin;
+  for (int i = 0; i < P.ndim; ++i) in_elems *= P.in_size[i];
+  cudaError_t e = cudaMemcpyAsync(d_x_stage, h_x, (size_t)in_elems * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return set_err((int)e, std::string("H2D copy: ") + cudaGetErrorString(e));
+  int rc = fc_conv(plan, d_const, d_x_stage, d_kspec, d_bias, d_y_stage, d_ws, stream);
+  if (rc) return rc;
+  e = cudaMemcpyAsync(h_y, d_y_stage, (size_t)plan->info.out_elems * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e != cudaSuccess) return set_err((int)e, std::string("D2H copy: ") + cudaGetErrorString(e));
+  return FC_OK;
+}
+
+int fc_complex_matmul(const float* d_a, const float* d_b, float* d_y, int64_t batch, int64_t cin, int64_t cout, int64_t groups, int64_t bins,
+                      void* stream) {
+  if (!d_a || !d_b || !d_y) return set_err(FC_ENULL, "fc_complex_matmul: NULL argument");
+  if (batch < 1 || cin < 1 || cout < 1 || groups < 1 || bins < 1 || cin % groups || cout % groups)
+    return set_err(FC_EINVAL, "fc_complex_matmul: bad shape");
+  init_once();
+  return launch_contract((const float2*)d_a, (const float2*)d_b, (float2*)d_y, bins, (int)batch, (int)cin, (int)cout, (int)groups,
+                         (cudaStream_t)stream);
+}
+
+}  // extern "C"

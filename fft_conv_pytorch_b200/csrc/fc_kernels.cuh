@@ -1,0 +1,527 @@
+// fc_kernels.cuh — generic axis-pass and contraction kernels (any power-of-two extent, any channel count).
+//
+// These are the "always correct" kernels of the pipeline; the fused / specialised kernels for the
+// benchmark shapes live in fc_fused.cuh and are checked against these. The code is plain CUDA C++ with no
+// warp intrinsics so that tests/cpu_emul can run the very same source on host threads (test infrastructure
+// only; the shipped library contains device code only).
+#pragma once
+#include "fc_types.h"
+
+#ifdef FC_CPU_EMUL
+#include "cuda_shim.h"
+#else
+#include <cuda_runtime.h>
+#define FC_DYN_SMEM(name)                      \
+  extern __shared__ float4 fc_dyn_smem_raw[];  \
+  float2* name = reinterpret_cast<float2*>(fc_dyn_smem_raw)
+#endif
+
+#define FC_DEV __device__ __forceinline__
+
+// ------------------------------------------------------------------------------------------------ complex helpers
+FC_DEV float2 fc_c(float x, float y) { return make_float2(x, y); }
+FC_DEV float2 fc_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+FC_DEV float2 fc_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+FC_DEV float2 fc_mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+FC_DEV float2 fc_conj(float2 a) { return make_float2(a.x, -a.y); }
+FC_DEV float2 fc_mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+FC_DEV float2 fc_scale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+
+// XOR swizzle of the element index inside a line: makes both the unit-stride reads and the stride-R /
+// stride-Ns writes of a Stockham stage hit 16 distinct 8-byte bank pairs per half warp.
+FC_DEV int fc_swz(int i) { return i ^ ((i >> 4) & 15); }
+
+// ------------------------------------------------------------------------------------------------ maps
+// Dense position u -> source index, or -1 for a structural zero. (fc_types.h: fc_imap)
+FC_DEV int fc_imap_src(const fc_imap& m, int u) {
+  if (u >= m.ext) return -1;
+  int w = u;
+  if (m.up > 1) {
+    if (u % m.up) return -1;
+    w = u / m.up;
+  }
+  int v = w * m.sub - m.pad;
+  if (v < 0 || v >= m.L) {
+    if (m.mode == FC_PAD_CONSTANT) return -1;
+    if (m.mode == FC_PAD_REFLECT)
+      v = (v < 0) ? -v : 2 * (m.L - 1) - v;
+    else if (m.mode == FC_PAD_REPLICATE)
+      v = (v < 0) ? 0 : m.L - 1;
+    else
+      v = (v < 0) ? v + m.L : v - m.L;  // circular
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ radix butterflies
+// Forward DFT (sign -1) of R points held in registers; results in natural order.
+template <int R>
+FC_DEV void fc_butterfly(float2* v);
+
+template <>
+FC_DEV void fc_butterfly<2>(float2* v) {
+  float2 a = v[0], b = v[1];
+  v[0] = fc_add(a, b);
+  v[1] = fc_sub(a, b);
+}
+
+template <>
+FC_DEV void fc_butterfly<4>(float2* v) {
+  float2 b0 = fc_add(v[0], v[2]), b2 = fc_sub(v[0], v[2]);
+  float2 b1 = fc_add(v[1], v[3]), b3 = fc_mul_mi(fc_sub(v[1], v[3]));
+  v[0] = fc_add(b0, b1);
+  v[2] = fc_sub(b0, b1);
+  v[1] = fc_add(b2, b3);
+  v[3] = fc_sub(b2, b3);
+}
+
+template <>
+FC_DEV void fc_butterfly<8>(float2* v) {
+  const float h = 0.70710678118654752440f;
+  float2 a0 = fc_add(v[0], v[4]), a4 = fc_sub(v[0], v[4]);
+  float2 a1 = fc_add(v[1], v[5]), a5 = fc_sub(v[1], v[5]);
+  float2 a2 = fc_add(v[2], v[6]), a6 = fc_sub(v[2], v[6]);
+  float2 a3 = fc_add(v[3], v[7]), a7 = fc_sub(v[3], v[7]);
+  a5 = make_float2(h * (a5.x + a5.y), h * (a5.y - a5.x));   // * (1 - i)/sqrt2
+  a6 = fc_mul_mi(a6);                                       // * (-i)
+  a7 = make_float2(h * (a7.y - a7.x), -h * (a7.x + a7.y));  // * (-1 - i)/sqrt2
+  float2 b0 = fc_add(a0, a2), b2 = fc_sub(a0, a2);
+  float2 b1 = fc_add(a1, a3), b3 = fc_mul_mi(fc_sub(a1, a3));
+  float2 b4 = fc_add(a4, a6), b6 = fc_sub(a4, a6);
+  float2 b5 = fc_add(a5, a7), b7 = fc_mul_mi(fc_sub(a5, a7));
+  v[0] = fc_add(b0, b1);
+  v[4] = fc_sub(b0, b1);
+  v[2] = fc_add(b2, b3);
+  v[6] = fc_sub(b2, b3);
+  v[1] = fc_add(b4, b5);
+  v[5] = fc_sub(b4, b5);
+  v[3] = fc_add(b6, b7);
+  v[7] = fc_sub(b6, b7);
+}
+
+// One Stockham stage of radix R over T lines of M points: in -> out (both swizzled, same pitch).
+// Ns = product of the radices already applied. tw is the table exp(-2*pi*i*j/tw_len).
+template <int R>
+FC_DEV void fc_fft_stage(const float2* in, float2* out, int M, int Ns, int T, int pitch, const float2* tw, int tw_len) {
+  const int per = M / R;  // butterflies per line
+  const int total = T * per;
+  const int tw_step = tw_len / (Ns * R);
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int line = idx / per;
+    const int j = idx - line * per;
+    const int k = j & (Ns - 1);
+    const float2* src = in + line * pitch;
+    float2* dst = out + line * pitch;
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = src[fc_swz(j + r * per)];
+    if (Ns > 1) {
+      const float2 w1 = __ldg(tw + k * tw_step);
+      float2 w = w1;
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        v[r] = fc_mul(v[r], w);
+        if (r + 1 < R) w = fc_mul(w, w1);
+      }
+    }
+    fc_butterfly<R>(v);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) dst[fc_swz(j0 + r * Ns)] = v[r];
+  }
+}
+
+// Forward complex FFT of T lines of M points (M power of two), unnormalised, Stockham autosort with
+// radix 8/4/2 stages ping-ponging between a and b. Data must be visible (barrier) on entry; a barrier
+// follows every stage. Returns the buffer holding the result (swizzled, natural order).
+FC_DEV float2* fc_fft_forward(float2* a, float2* b, int M, int T, int pitch, const float2* tw, int tw_len) {
+  int Ns = 1;
+  float2* in = a;
+  float2* out = b;
+  while (Ns < M) {
+    const int rem = M / Ns;
+    int R;
+    if (rem >= 8 && rem != 16)
+      R = 8;
+    else if (rem >= 4)
+      R = 4;
+    else
+      R = 2;
+    if (R == 8)
+      fc_fft_stage<8>(in, out, M, Ns, T, pitch, tw, tw_len);
+    else if (R == 4)
+      fc_fft_stage<4>(in, out, M, Ns, T, pitch, tw, tw_len);
+    else
+      fc_fft_stage<2>(in, out, M, Ns, T, pitch, tw, tw_len);
+    __syncthreads();
+    Ns *= R;
+    float2* t = in;
+    in = out;
+    out = t;
+  }
+  return in;
+}
+
+// W_twN^(e) for the four-step twiddle, e already reduced mod twN.
+FC_DEV float2 fc_big_twiddle(int64_t e, int64_t twN) {
+  float s, c;
+  sincospif(-2.0f * (float)((double)e / (double)twN), &s, &c);
+  return make_float2(c, s);
+}
+
+// ------------------------------------------------------------------------------------------------ the axis pass
+struct fc_pass_args {
+  fc_pass p;
+  const void* in;
+  void* out;
+  const float2* tw;   // twiddle table, p.tw_len entries
+  const float* bias;  // C2R only, may be null
+};
+
+// Per-line bookkeeping kept in shared memory for the current tile.
+struct fc_line_info {
+  int64_t in_base;
+  int64_t out_base;
+  int64_t r;  // line index inside the outer item (twiddle / composite position)
+  int32_t valid;
+  int32_t bias_idx;
+};
+
+#define FC_MAX_T 128
+
+template <int KIND>
+__global__ void fc_pass_kernel(fc_pass_args a) {
+  const fc_pass& p = a.p;
+  FC_DYN_SMEM(smem);
+  float2* bufA = smem;
+  float2* bufB = smem + (size_t)p.T * p.pitch;
+  __shared__ fc_line_info lines[FC_MAX_T];
+
+  const int T = p.T, M = p.M, N = p.N, pitch = p.pitch;
+  const int tid = threadIdx.x, nth = blockDim.x;
+
+  for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    // ---- line bookkeeping
+    for (int lt = tid; lt < T; lt += nth) {
+      int64_t o, r;
+      int valid;
+      if (p.flat) {
+        const int64_t g = tile * T + lt;
+        valid = g < p.n_outer * p.R;
+        o = valid ? g / p.R : 0;
+        r = valid ? g - o * p.R : 0;
+      } else {
+        o = tile / p.tiles_per_outer;
+        r = (tile - o * p.tiles_per_outer) * T + lt;
+        valid = r < p.R;
+        if (!valid) r = 0;
+      }
+      fc_line_info li;
+      if (KIND == FC_R2C) {
+        const int64_t o1 = o / p.o_c2, o2 = o - o1 * p.o_c2;
+        li.in_base = (o1 / p.o_q) * p.o_sA + (o1 % p.o_q) * p.o_sB + o2 * p.o_sC + r * p.in_rs;
+      } else {
+        li.in_base = o * p.in_os + r * p.in_rs;
+      }
+      li.out_base = o * p.out_os + r * p.out_rs;
+      li.r = r;
+      li.valid = valid;
+      li.bias_idx = (int)(o % (p.cout > 0 ? p.cout : 1));
+      lines[lt] = li;
+    }
+    __syncthreads();
+
+    // ---- load tile into bufA
+    if (KIND == FC_R2C) {
+      const float* x = reinterpret_cast<const float*>(a.in);
+      float* dst = reinterpret_cast<float*>(bufA);
+      const int total = T * N;
+      for (int idx = tid; idx < total; idx += nth) {
+        int l, n;
+        if (p.in_rfast) {
+          l = idx & (T - 1);
+          n = idx >> p.log2T;
+        } else {
+          l = idx / N;
+          n = idx - l * N;
+        }
+        const fc_line_info li = lines[l];
+        float val = 0.f;
+        if (li.valid) {
+          const int64_t u = (int64_t)n * p.pos_n + li.r * p.pos_r;
+          const int s = (u < p.imap.ext) ? fc_imap_src(p.imap, (int)u) : -1;
+          if (s >= 0) val = __ldg(x + li.in_base + (int64_t)s * p.in_es);
+        }
+        dst[2 * (l * pitch + fc_swz(n >> 1)) + (n & 1)] = val;
+      }
+    } else if (KIND == FC_C2C_FWD) {
+      const float2* x = reinterpret_cast<const float2*>(a.in);
+      const int total = T * N;
+      for (int idx = tid; idx < total; idx += nth) {
+        int l, n;
+        if (p.in_rfast) {
+          l = idx & (T - 1);
+          n = idx >> p.log2T;
+        } else {
+          l = idx / N;
+          n = idx - l * N;
+        }
+        const fc_line_info li = lines[l];
+        float2 val = make_float2(0.f, 0.f);
+        if (li.valid) {
+          const int s = fc_imap_src(p.imap, n);
+          if (s >= 0) val = __ldg(x + li.in_base + (int64_t)s * p.in_es);
+        }
+        bufA[l * pitch + fc_swz(n)] = val;
+      }
+    } else if (KIND == FC_C2C_INV) {
+      const float2* x = reinterpret_cast<const float2*>(a.in);
+      const int total = T * N;
+      for (int idx = tid; idx < total; idx += nth) {
+        int l, n;
+        if (p.in_rfast) {
+          l = idx & (T - 1);
+          n = idx >> p.log2T;
+        } else {
+          l = idx / N;
+          n = idx - l * N;
+        }
+        const fc_line_info li = lines[l];
+        float2 val = make_float2(0.f, 0.f);
+        if (li.valid) val = fc_conj(__ldg(x + li.in_base + (int64_t)n * p.in_es));
+        bufA[l * pitch + fc_swz(n)] = val;
+      }
+    } else {  // FC_C2R: bins 0..M, plain layout
+      const float2* x = reinterpret_cast<const float2*>(a.in);
+      const int W = M + 1;
+      const int total = T * W;
+      for (int idx = tid; idx < total; idx += nth) {
+        int l, k;
+        if (p.in_rfast) {
+          l = idx & (T - 1);
+          k = idx >> p.log2T;
+        } else {
+          l = idx / W;
+          k = idx - l * W;
+        }
+        const fc_line_info li = lines[l];
+        float2 val = make_float2(0.f, 0.f);
+        if (li.valid) {
+          val = __ldg(x + li.in_base + (int64_t)k * p.in_es);
+          if (p.twiddle) {
+            const int64_t e = ((int64_t)k * li.r) % p.twN;
+            val = fc_mul(val, fc_conj(fc_big_twiddle(e, p.twN)));
+          }
+        }
+        bufA[l * pitch + k] = val;
+      }
+    }
+    __syncthreads();
+
+    // ---- transform
+    float2* res;
+    if (KIND == FC_C2R) {
+      // Hermitian half spectrum Y[0..M] (plain, bufA) -> conj(Z) (swizzled, bufB); then forward FFT gives conj(z).
+      const int total = T * M;
+      const int tstep = p.tw_len / N;
+      for (int idx = tid; idx < total; idx += nth) {
+        const int l = idx / M;
+        const int k = idx - l * M;
+        const float2 yk = bufA[l * pitch + k];
+        const float2 ym = fc_conj(bufA[l * pitch + (M - k)]);
+        const float2 s = fc_add(yk, ym);
+        const float2 d = fc_mul(fc_sub(yk, ym), fc_conj(__ldg(a.tw + k * tstep)));
+        // Z = s + i*d ; store conj(Z)
+        bufB[l * pitch + fc_swz(k)] = make_float2(s.x - d.y, -(s.y + d.x));
+      }
+      __syncthreads();
+      res = fc_fft_forward(bufB, bufA, M, T, pitch, a.tw, p.tw_len);
+    } else {
+      res = fc_fft_forward(bufA, bufB, M, T, pitch, a.tw, p.tw_len);
+    }
+
+    // ---- store
+    if (KIND == FC_R2C) {
+      float2* other = (res == bufA) ? bufB : bufA;
+      // untangle the packed real transform: Z (swizzled, res) -> X[0..M] (plain, other)
+      const int W = M + 1;
+      const int total = T * W;
+      const int tstep = p.tw_len / N;
+      for (int idx = tid; idx < total; idx += nth) {
+        const int l = idx / W;
+        const int k = idx - l * W;
+        const float2 zk = res[l * pitch + fc_swz(k & (M - 1))];
+        const float2 zc = fc_conj(res[l * pitch + fc_swz((M - k) & (M - 1))]);
+        const float2 e = fc_scale(fc_add(zk, zc), 0.5f);
+        const float2 o = fc_scale(fc_mul_mi(fc_sub(zk, zc)), 0.5f);
+        other[l * pitch + k] = fc_add(e, fc_mul(__ldg(a.tw + k * tstep), o));
+      }
+      __syncthreads();
+      float2* y = reinterpret_cast<float2*>(a.out);
+      for (int idx = tid; idx < total; idx += nth) {
+        int l, k;
+        if (p.out_rfast) {
+          l = idx & (T - 1);
+          k = idx >> p.log2T;
+        } else {
+          l = idx / W;
+          k = idx - l * W;
+        }
+        const fc_line_info li = lines[l];
+        if (!li.valid) continue;
+        float2 val = other[l * pitch + k];
+        if (p.twiddle) {
+          const int64_t e = ((int64_t)k * li.r) % p.twN;
+          val = fc_mul(val, fc_big_twiddle(e, p.twN));
+        }
+        val = fc_scale(val, p.scale);
+        if (p.conj_out) val = fc_conj(val);
+        y[li.out_base + (int64_t)k * p.out_es] = val;
+      }
+    } else if (KIND == FC_C2C_FWD) {
+      float2* y = reinterpret_cast<float2*>(a.out);
+      const int total = T * N;
+      for (int idx = tid; idx < total; idx += nth) {
+        int l, k;
+        if (p.out_rfast) {
+          l = idx & (T - 1);
+          k = idx >> p.log2T;
+        } else {
+          l = idx / N;
+          k = idx - l * N;
+        }
+        const fc_line_info li = lines[l];
+        if (!li.valid) continue;
+        float2 val = fc_scale(res[l * pitch + fc_swz(k)], p.scale);
+        if (p.conj_out) val = fc_conj(val);
+        y[li.out_base + (int64_t)k * p.out_es] = val;
+      }
+    } else if (KIND == FC_C2C_INV) {
+      float2* y = reinterpret_cast<float2*>(a.out);
+      const fc_omap om = p.omap;
+      const int total = T * N;
+      for (int idx = tid; idx < total; idx += nth) {
+        int l, n;
+        if (p.out_rfast) {
+          l = idx & (T - 1);
+          n = idx >> p.log2T;
+        } else {
+          l = idx / N;
+          n = idx - l * N;
+        }
+        const fc_line_info li = lines[l];
+        if (!li.valid) continue;
+        const float2 val = fc_conj(res[l * pitch + fc_swz(n)]);
+        // dense index n owns the outputs j with (j*os + ob) / og == n
+        for (int e = 0; e < om.og; ++e) {
+          const int t = n * om.og + e - om.ob;
+          if (t < 0 || (t % om.os)) continue;
+          const int j = t / om.os;
+          if (j >= om.Lout) continue;
+          const bool live = (e == 0) && (n < om.lim);
+          y[li.out_base + (int64_t)j * p.out_es] = live ? val : make_float2(0.f, 0.f);
+        }
+      }
+    } else {  // FC_C2R
+      float* y = reinterpret_cast<float*>(a.out);
+      const fc_omap om = p.omap;
+      const int total = T * N;
+      for (int idx = tid; idx < total; idx += nth) {
+        int l, n;
+        if (p.out_rfast) {
+          l = idx & (T - 1);
+          n = idx >> p.log2T;
+        } else {
+          l = idx / N;
+          n = idx - l * N;
+        }
+        const fc_line_info li = lines[l];
+        if (!li.valid) continue;
+        const float2 z = res[l * pitch + fc_swz(n >> 1)];
+        const float val = (n & 1) ? -z.y : z.x;
+        const float b = p.has_bias ? __ldg(a.bias + li.bias_idx) : 0.f;
+        const int64_t u = (int64_t)n * p.pos_n + li.r * p.pos_r;
+        for (int e = 0; e < om.og; ++e) {
+          const int64_t t = u * om.og + e - om.ob;
+          if (t < 0 || (t % om.os)) continue;
+          const int64_t j = t / om.os;
+          if (j >= om.Lout) continue;
+          const bool live = (e == 0) && (u < om.lim);
+          y[li.out_base + j * p.out_es] = (live ? val : 0.f) + b;
+        }
+      }
+    }
+    __syncthreads();  // smem (lines, buffers) is reused by the next tile
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ contraction
+// Y[b, g*Og + o, f] = sum_i X[b, g*Ig + i, f] * K[g*Og + o, i, f]      (reference complex_matmul, functional.py:11-16)
+// One thread per frequency bin (coalesced 8-byte accesses), a TB x TO register tile of outputs per thread.
+struct fc_contract_args {
+  const float2* X;
+  const float2* K;
+  float2* Y;
+  int64_t bins;
+  int32_t batch, cin, cout, groups;
+  int32_t btiles, otiles;
+};
+
+template <int TB, int TO>
+__global__ void fc_contract_kernel(fc_contract_args a) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= a.bins) return;
+  const int Ig = a.cin / a.groups, Og = a.cout / a.groups;
+  const int g = blockIdx.z;
+  const int bt = blockIdx.y / a.otiles, ot = blockIdx.y - bt * a.otiles;
+  const int b0 = bt * TB, o0 = ot * TO;
+  float2 acc[TB][TO];
+#pragma unroll
+  for (int i = 0; i < TB; ++i)
+#pragma unroll
+    for (int j = 0; j < TO; ++j) acc[i][j] = make_float2(0.f, 0.f);
+  const float2* xp[TB];
+  const float2* kp[TO];
+#pragma unroll
+  for (int i = 0; i < TB; ++i) {
+    const int b = (b0 + i < a.batch) ? b0 + i : a.batch - 1;
+    xp[i] = a.X + ((int64_t)b * a.cin + (int64_t)g * Ig) * a.bins + f;
+  }
+#pragma unroll
+  for (int j = 0; j < TO; ++j) {
+    const int o = (o0 + j < Og) ? o0 + j : Og - 1;
+    kp[j] = a.K + ((int64_t)(g * Og + o) * Ig) * a.bins + f;
+  }
+  for (int c = 0; c < Ig; ++c) {
+    float2 xv[TB], kv[TO];
+#pragma unroll
+    for (int i = 0; i < TB; ++i) xv[i] = __ldg(xp[i] + (int64_t)c * a.bins);
+#pragma unroll
+    for (int j = 0; j < TO; ++j) kv[j] = __ldg(kp[j] + (int64_t)c * a.bins);
+#pragma unroll
+    for (int i = 0; i < TB; ++i)
+#pragma unroll
+      for (int j = 0; j < TO; ++j) {
+        acc[i][j].x += xv[i].x * kv[j].x - xv[i].y * kv[j].y;
+        acc[i][j].y += xv[i].x * kv[j].y + xv[i].y * kv[j].x;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < TB; ++i) {
+    if (b0 + i >= a.batch) continue;
+#pragma unroll
+    for (int j = 0; j < TO; ++j) {
+      if (o0 + j >= Og) continue;
+      a.Y[((int64_t)(b0 + i) * a.cout + (int64_t)g * Og + o0 + j) * a.bins + f] = acc[i][j];
+    }
+  }
+}
+
+// Twiddle table: tw[j] = exp(-2*pi*i*j/len), evaluated in double precision.
+__global__ void fc_twiddle_kernel(float2* tw, int len) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) {
+    double s, c;
+    sincospi(-2.0 * (double)j / (double)len, &s, &c);
+    tw[j] = make_float2((float)c, (float)s);
+  }
+}

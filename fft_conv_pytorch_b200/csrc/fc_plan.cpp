@@ -1,0 +1,657 @@
+// fc_plan.cpp — shape algebra of fft_conv / fft_conv_transpose and the axis-pass program.
+//
+// Mirrors (does not copy) the reference's argument handling:
+//   forward     functional.py:44-66 (tuples, dilation, padding, transform extent) and :76-82 (crop + stride)
+//   transposed  functional.py:103-154 (kernel regroup, dilation, zero-stuffing, extents) and :163-169 (crop)
+// Differences, all result-preserving:
+//   * the transform extent per axis is the next power of two >= the no-wrap minimum instead of "rounded to even";
+//   * the transposed path runs a true (un-flipped, un-conjugated) circular convolution of the zero-stuffed
+//     signal with the dilated kernel, which equals the reference's flip + left-pad + correlation;
+//   * stride/dilation lattices with a common factor g are reduced by g (polyphase): only the populated
+//     lattice is transformed, the remaining outputs are bias only.
+#include "fc_plan.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+namespace {
+
+int ilog2(int64_t v) {
+  int l = 0;
+  while ((int64_t(1) << l) < v) ++l;
+  return l;
+}
+int64_t next_pow2(int64_t v) { return int64_t(1) << ilog2(v); }
+int gcd_i(int a, int b) {
+  while (b) {
+    int t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+const int kMaxComplexLine = 4096;  // longest complex FFT done inside one CTA
+const int kMaxRealLine = 8192;
+
+fc_imap identity_imap(int n) {
+  fc_imap m;
+  m.L = n;
+  m.mode = FC_PAD_CONSTANT;
+  m.pad = 0;
+  m.up = 1;
+  m.sub = 1;
+  m.ext = n;
+  return m;
+}
+fc_omap identity_omap(int n) {
+  fc_omap m;
+  m.Lout = n;
+  m.os = 1;
+  m.ob = 0;
+  m.og = 1;
+  m.lim = n;
+  return m;
+}
+
+// Fill the tile geometry of a pass once kind / N / R / n_outer / flags are set.
+void finish_pass(fc_pass& p) {
+  p.M = (p.kind == FC_R2C || p.kind == FC_C2R) ? p.N / 2 : p.N;
+  if (p.M < 1) p.M = 1;
+  const bool rfast = p.in_rfast || p.out_rfast;
+  int budget = (rfast && p.M >= 512) ? 8192 : 4096;
+  int T = 1;
+  while (T * 2 * p.M <= budget && T * 2 <= 64) T *= 2;
+  const int64_t lines_avail = p.flat ? p.n_outer * p.R : p.R;
+  while (T > 1 && T / 2 >= lines_avail) T /= 2;
+  p.T = T;
+  p.log2T = ilog2(T);
+  p.pitch = p.M + 1;
+  if (p.flat) {
+    p.tiles_per_outer = 0;
+    p.n_tiles = (p.n_outer * p.R + T - 1) / T;
+  } else {
+    p.tiles_per_outer = (p.R + T - 1) / T;
+    p.n_tiles = p.tiles_per_outer * p.n_outer;
+  }
+}
+
+fc_pass blank_pass(int kind, int N, int tw_len) {
+  fc_pass p;
+  std::memset(&p, 0, sizeof(p));
+  p.kind = kind;
+  p.N = N;
+  p.tw_len = tw_len;
+  p.scale = 1.f;
+  p.pos_n = 1;
+  p.pos_r = 0;
+  p.o_c2 = 1;
+  p.o_q = 1;
+  p.twN = 1;
+  p.imap = identity_imap(N);
+  p.omap = identity_omap(N);
+  return p;
+}
+
+// Description of the real tensor feeding a forward program (signal or weight).
+struct SrcDesc {
+  int64_t n_outer;                   // B*Cin or Cout*(Cin/g)
+  int64_t o_c2, o_q, o_sA, o_sB, o_sC;
+  fc_imap imap[FC_MAX_ND];
+  int L[FC_MAX_ND];
+  bool conj;
+  float scale;
+};
+
+void build_forward(const fc_plan& pl, const SrcDesc& s, std::vector<fc_step>& out) {
+  const int tw = pl.tw_len;
+  auto set_src = [&](fc_pass& p) {
+    p.o_c2 = s.o_c2;
+    p.o_q = s.o_q;
+    p.o_sA = s.o_sA;
+    p.o_sB = s.o_sB;
+    p.o_sC = s.o_sC;
+  };
+  if (pl.structure == FC_S_1D) {
+    const fc_axis& a = pl.ax[0];
+    fc_pass p = blank_pass(FC_R2C, a.N, tw);
+    p.n_outer = s.n_outer;
+    p.R = 1;
+    p.flat = 1;
+    set_src(p);
+    p.in_rs = 0;
+    p.in_es = 1;
+    p.imap = s.imap[0];
+    p.n_in = s.L[0];
+    p.n_out = a.Nk;
+    p.out_os = a.Nk;
+    p.out_rs = 0;
+    p.out_es = 1;
+    p.conj_out = s.conj;
+    p.scale = s.scale;
+    finish_pass(p);
+    out.push_back({p, FC_BUF_USER_IN, FC_BUF_SPEC});
+  } else if (pl.structure == FC_S_1D_SPLIT) {
+    const int N1 = pl.N1, N2 = pl.N2, Nk1 = N1 / 2 + 1;
+    fc_pass p = blank_pass(FC_R2C, N1, tw);
+    p.n_outer = s.n_outer;
+    p.R = N2;
+    set_src(p);
+    p.in_rs = 0;
+    p.in_es = 1;
+    p.in_rfast = 1;
+    p.pos_n = N2;
+    p.pos_r = 1;
+    p.imap = s.imap[0];
+    p.n_in = N1;
+    p.n_out = Nk1;
+    p.out_os = (int64_t)Nk1 * N2;
+    p.out_es = N2;
+    p.out_rs = 1;
+    p.out_rfast = 1;
+    p.twiddle = 1;
+    p.twN = (int64_t)N1 * N2;
+    finish_pass(p);
+    out.push_back({p, FC_BUF_USER_IN, FC_BUF_SA});
+    fc_pass q = blank_pass(FC_C2C_FWD, N2, tw);
+    q.n_outer = s.n_outer;
+    q.R = Nk1;
+    q.flat = 1;
+    q.in_os = (int64_t)Nk1 * N2;
+    q.in_rs = N2;
+    q.in_es = 1;
+    q.n_in = N2;
+    q.n_out = N2;
+    q.out_os = (int64_t)Nk1 * N2;
+    q.out_rs = N2;
+    q.out_es = 1;
+    q.conj_out = s.conj;
+    q.scale = s.scale;
+    finish_pass(q);
+    out.push_back({q, FC_BUF_SA, FC_BUF_SPEC});
+  } else if (pl.structure == FC_S_2D) {
+    const fc_axis &ay = pl.ax[0], &ax = pl.ax[1];
+    const int Ly = s.L[0], Lx = s.L[1];
+    fc_pass p = blank_pass(FC_R2C, ax.N, tw);
+    p.n_outer = s.n_outer;
+    p.R = Ly;
+    set_src(p);
+    p.in_rs = Lx;
+    p.in_es = 1;
+    p.imap = s.imap[1];
+    p.n_in = Lx;
+    p.n_out = ax.Nk;
+    p.out_os = (int64_t)ax.Nk * Ly;  // [o][kx][y]
+    p.out_es = Ly;
+    p.out_rs = 1;
+    p.out_rfast = 1;
+    finish_pass(p);
+    out.push_back({p, FC_BUF_USER_IN, FC_BUF_SA});
+    fc_pass q = blank_pass(FC_C2C_FWD, ay.N, tw);
+    q.n_outer = s.n_outer;
+    q.R = ax.Nk;
+    q.flat = 1;
+    q.in_os = (int64_t)ax.Nk * Ly;
+    q.in_rs = Ly;
+    q.in_es = 1;
+    q.imap = s.imap[0];
+    q.n_in = Ly;
+    q.n_out = ay.N;
+    q.out_os = (int64_t)ax.Nk * ay.N;  // [o][kx][ky]
+    q.out_rs = ay.N;
+    q.out_es = 1;
+    q.conj_out = s.conj;
+    q.scale = s.scale;
+    finish_pass(q);
+    out.push_back({q, FC_BUF_SA, FC_BUF_SPEC});
+  } else {  // FC_S_3D
+    const fc_axis &az = pl.ax[0], &ay = pl.ax[1], &ax = pl.ax[2];
+    const int Lz = s.L[0], Ly = s.L[1], Lx = s.L[2];
+    fc_pass p = blank_pass(FC_R2C, ax.N, tw);
+    p.n_outer = s.n_outer;
+    p.R = (int64_t)Lz * Ly;
+    set_src(p);
+    p.in_rs = Lx;
+    p.in_es = 1;
+    p.imap = s.imap[2];
+    p.n_in = Lx;
+    p.n_out = ax.Nk;
+    p.out_os = (int64_t)ax.Nk * Lz * Ly;  // [o][kx][z][y]
+    p.out_es = (int64_t)Lz * Ly;
+    p.out_rs = 1;
+    p.out_rfast = 1;
+    finish_pass(p);
+    out.push_back({p, FC_BUF_USER_IN, FC_BUF_SA});
+    fc_pass q = blank_pass(FC_C2C_FWD, ay.N, tw);
+    q.n_outer = s.n_outer;
+    q.R = (int64_t)ax.Nk * Lz;  // lines (kx, z)
+    q.in_os = (int64_t)ax.Nk * Lz * Ly;
+    q.in_rs = Ly;
+    q.in_es = 1;
+    q.imap = s.imap[1];
+    q.n_in = Ly;
+    q.n_out = ay.N;
+    q.out_os = (int64_t)ay.N * ax.Nk * Lz;  // [o][ky][kx][z]
+    q.out_es = (int64_t)ax.Nk * Lz;
+    q.out_rs = 1;
+    q.out_rfast = 1;
+    finish_pass(q);
+    out.push_back({q, FC_BUF_SA, FC_BUF_SB});
+    fc_pass r = blank_pass(FC_C2C_FWD, az.N, tw);
+    r.n_outer = s.n_outer;
+    r.R = (int64_t)ay.N * ax.Nk;  // lines (ky, kx)
+    r.flat = 1;
+    r.in_os = (int64_t)ay.N * ax.Nk * Lz;
+    r.in_rs = Lz;
+    r.in_es = 1;
+    r.imap = s.imap[0];
+    r.n_in = Lz;
+    r.n_out = az.N;
+    r.out_os = (int64_t)ay.N * ax.Nk * az.N;  // [o][ky][kx][kz]
+    r.out_rs = az.N;
+    r.out_es = 1;
+    r.conj_out = s.conj;
+    r.scale = s.scale;
+    finish_pass(r);
+    out.push_back({r, FC_BUF_SB, FC_BUF_SPEC});
+  }
+}
+
+void build_inverse(const fc_plan& pl, std::vector<fc_step>& out) {
+  const int tw = pl.tw_len;
+  const int64_t n_outer = (int64_t)pl.prob.batch * pl.prob.cout;
+  const int has_bias = 1;  // resolved at launch time (null bias pointer => 0)
+  if (pl.structure == FC_S_1D) {
+    const fc_axis& a = pl.ax[0];
+    fc_pass p = blank_pass(FC_C2R, a.N, tw);
+    p.n_outer = n_outer;
+    p.R = 1;
+    p.flat = 1;
+    p.in_os = a.Nk;
+    p.in_rs = 0;
+    p.in_es = 1;
+    p.n_in = a.Nk;
+    p.n_out = a.Lout;
+    p.out_os = a.Lout;
+    p.out_rs = 0;
+    p.out_es = 1;
+    p.omap = a.omap;
+    p.cout = pl.prob.cout;
+    p.has_bias = has_bias;
+    finish_pass(p);
+    out.push_back({p, FC_BUF_SPEC, FC_BUF_USER_OUT});
+  } else if (pl.structure == FC_S_1D_SPLIT) {
+    const fc_axis& a = pl.ax[0];
+    const int N1 = pl.N1, N2 = pl.N2, Nk1 = N1 / 2 + 1;
+    fc_pass q = blank_pass(FC_C2C_INV, N2, tw);
+    q.n_outer = n_outer;
+    q.R = Nk1;
+    q.flat = 1;
+    q.in_os = (int64_t)Nk1 * N2;
+    q.in_rs = N2;
+    q.in_es = 1;
+    q.n_in = N2;
+    q.n_out = N2;
+    q.out_os = (int64_t)Nk1 * N2;
+    q.out_rs = N2;
+    q.out_es = 1;
+    finish_pass(q);
+    out.push_back({q, FC_BUF_SPEC, FC_BUF_SA});
+    fc_pass p = blank_pass(FC_C2R, N1, tw);
+    p.n_outer = n_outer;
+    p.R = N2;
+    p.in_os = (int64_t)Nk1 * N2;
+    p.in_es = N2;
+    p.in_rs = 1;
+    p.in_rfast = 1;
+    p.n_in = Nk1;
+    p.twiddle = 1;
+    p.twN = (int64_t)N1 * N2;
+    p.pos_n = N2;
+    p.pos_r = 1;
+    p.out_os = a.Lout;
+    p.out_rs = 0;
+    p.out_es = 1;
+    p.out_rfast = 1;
+    p.n_out = a.Lout;
+    p.omap = a.omap;
+    p.cout = pl.prob.cout;
+    p.has_bias = has_bias;
+    finish_pass(p);
+    out.push_back({p, FC_BUF_SA, FC_BUF_USER_OUT});
+  } else if (pl.structure == FC_S_2D) {
+    const fc_axis &ay = pl.ax[0], &ax = pl.ax[1];
+    fc_pass q = blank_pass(FC_C2C_INV, ay.N, tw);
+    q.n_outer = n_outer;
+    q.R = ax.Nk;
+    q.flat = 1;
+    q.in_os = (int64_t)ax.Nk * ay.N;
+    q.in_rs = ay.N;
+    q.in_es = 1;
+    q.n_in = ay.N;
+    q.n_out = ay.Lout;
+    q.out_os = (int64_t)ax.Nk * ay.Lout;  // [o][kx][jy]
+    q.out_rs = ay.Lout;
+    q.out_es = 1;
+    q.omap = ay.omap;
+    finish_pass(q);
+    out.push_back({q, FC_BUF_SPEC, FC_BUF_SA});
+    fc_pass p = blank_pass(FC_C2R, ax.N, tw);
+    p.n_outer = n_outer;
+    p.R = ay.Lout;
+    p.in_os = (int64_t)ax.Nk * ay.Lout;
+    p.in_es = ay.Lout;
+    p.in_rs = 1;
+    p.in_rfast = 1;
+    p.n_in = ax.Nk;
+    p.n_out = ax.Lout;
+    p.out_os = (int64_t)ay.Lout * ax.Lout;
+    p.out_rs = ax.Lout;
+    p.out_es = 1;
+    p.omap = ax.omap;
+    p.cout = pl.prob.cout;
+    p.has_bias = has_bias;
+    finish_pass(p);
+    out.push_back({p, FC_BUF_SA, FC_BUF_USER_OUT});
+  } else {
+    const fc_axis &az = pl.ax[0], &ay = pl.ax[1], &ax = pl.ax[2];
+    fc_pass r = blank_pass(FC_C2C_INV, az.N, tw);
+    r.n_outer = n_outer;
+    r.R = (int64_t)ay.N * ax.Nk;
+    r.flat = 1;
+    r.in_os = (int64_t)ay.N * ax.Nk * az.N;
+    r.in_rs = az.N;
+    r.in_es = 1;
+    r.n_in = az.N;
+    r.n_out = az.Lout;
+    r.out_os = (int64_t)ay.N * ax.Nk * az.Lout;  // [o][ky][kx][jz]
+    r.out_rs = az.Lout;
+    r.out_es = 1;
+    r.omap = az.omap;
+    finish_pass(r);
+    out.push_back({r, FC_BUF_SPEC, FC_BUF_SA});
+    fc_pass q = blank_pass(FC_C2C_INV, ay.N, tw);
+    q.n_outer = n_outer;
+    q.R = (int64_t)ax.Nk * az.Lout;  // lines (kx, jz)
+    q.in_os = (int64_t)ay.N * ax.Nk * az.Lout;
+    q.in_es = (int64_t)ax.Nk * az.Lout;
+    q.in_rs = 1;
+    q.in_rfast = 1;
+    q.n_in = ay.N;
+    q.n_out = ay.Lout;
+    q.out_os = (int64_t)ax.Nk * az.Lout * ay.Lout;  // [o][kx][jz][jy]
+    q.out_rs = ay.Lout;
+    q.out_es = 1;
+    q.omap = ay.omap;
+    finish_pass(q);
+    out.push_back({q, FC_BUF_SA, FC_BUF_SB});
+    fc_pass p = blank_pass(FC_C2R, ax.N, tw);
+    p.n_outer = n_outer;
+    p.R = (int64_t)az.Lout * ay.Lout;  // lines (jz, jy)
+    p.in_os = (int64_t)ax.Nk * az.Lout * ay.Lout;
+    p.in_es = (int64_t)az.Lout * ay.Lout;
+    p.in_rs = 1;
+    p.in_rfast = 1;
+    p.n_in = ax.Nk;
+    p.n_out = ax.Lout;
+    p.out_os = (int64_t)az.Lout * ay.Lout * ax.Lout;
+    p.out_rs = ax.Lout;
+    p.out_es = 1;
+    p.omap = ax.omap;
+    p.cout = pl.prob.cout;
+    p.has_bias = has_bias;
+    finish_pass(p);
+    out.push_back({p, FC_BUF_SB, FC_BUF_USER_OUT});
+  }
+}
+
+int64_t step_out_bytes(const fc_step& s) { return s.pass.n_outer * s.pass.out_os * 8; }
+
+}  // namespace
+
+int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
+  auto fail = [&](int code, const std::string& m) {
+    if (msg) *msg = m;
+    return code;
+  };
+  if (!prob) return fail(FC_ENULL, "problem is NULL");
+  const fc_problem& P = *prob;
+  pl->prob = P;
+  std::memset(&pl->info, 0, sizeof(pl->info));
+  std::memset(&pl->fused, 0, sizeof(pl->fused));
+  const int nd = P.ndim;
+  if (nd < 1 || nd > FC_MAX_ND) return fail(FC_EUNSUPPORTED, "ndim must be 1, 2 or 3 (got " + std::to_string(nd) + ")");
+  if (P.batch < 1 || P.cin < 1 || P.cout < 1 || P.groups < 1) return fail(FC_EINVAL, "batch, channels and groups must be positive");
+  if (P.cin % P.groups || P.cout % P.groups)
+    return fail(FC_EINVAL, "in_channels (" + std::to_string(P.cin) + ") and out_channels (" + std::to_string(P.cout) +
+                               ") must be divisible by groups (" + std::to_string(P.groups) + ")");
+  if (P.padding_mode < 0 || P.padding_mode > 3) return fail(FC_EINVAL, "unknown padding_mode");
+  if (P.transposed && P.padding_mode != FC_PAD_CONSTANT) return fail(FC_EINVAL, "fft_conv_transpose has no padding_mode");
+  pl->nd = nd;
+  pl->threads = P.threads > 0 ? P.threads : 256;
+  if (pl->threads % 32 || pl->threads > 1024) return fail(FC_EINVAL, "threads must be a multiple of 32, <= 1024");
+  const bool poly = !(P.flags & FC_FLAG_NO_POLYPHASE);
+
+  int64_t bins = 1, out_vol = 1, in_vol = 1, k_vol = 1;
+  double inv_scale = 1.0;
+  for (int i = 0; i < nd; ++i) {
+    fc_axis& a = pl->ax[i];
+    a.L = P.in_size[i];
+    a.K = P.kernel_size[i];
+    a.stride = P.stride[i];
+    a.pad = P.padding[i];
+    a.dil = P.dilation[i];
+    a.opad = P.transposed ? P.output_padding[i] : 0;
+    const std::string ax_s = "axis " + std::to_string(i) + ": ";
+    if (a.L < 1 || a.K < 1) return fail(FC_EINVAL, ax_s + "signal and kernel extents must be positive");
+    if (a.stride < 1 || a.dil < 1) return fail(FC_EINVAL, ax_s + "stride and dilation must be >= 1");
+    if (a.pad < 0 || a.opad < 0) return fail(FC_EINVAL, ax_s + "padding and output_padding must be >= 0");
+    a.g = poly ? gcd_i(a.stride, a.dil) : 1;
+    const int s2 = a.stride / a.g, d2 = a.dil / a.g;
+    const int64_t Kd = (int64_t)(a.K - 1) * a.dil + 1;
+    int64_t need;
+    if (!P.transposed) {
+      const int64_t Lp = (int64_t)a.L + 2 * a.pad;
+      if (Lp < Kd)
+        return fail(FC_EINVAL, ax_s + "dilated kernel extent (" + std::to_string(Kd) + ") exceeds the padded signal extent (" +
+                                   std::to_string(Lp) + ")");
+      if (P.padding_mode == FC_PAD_REFLECT && a.pad > a.L - 1) return fail(FC_EINVAL, ax_s + "reflect padding must be < signal extent");
+      if (P.padding_mode == FC_PAD_CIRCULAR && a.pad > a.L) return fail(FC_EINVAL, ax_s + "circular padding must be <= signal extent");
+      a.Lout = (int)((Lp - Kd) / a.stride + 1);
+      a.imap_sig.L = a.L;
+      a.imap_sig.mode = P.padding_mode;
+      a.imap_sig.pad = a.pad;
+      a.imap_sig.up = 1;
+      a.imap_sig.sub = a.g;
+      a.imap_sig.ext = (int)((Lp + a.g - 1) / a.g);
+      a.omap.Lout = a.Lout;
+      a.omap.os = s2;
+      a.omap.ob = 0;
+      a.omap.og = 1;
+      need = a.imap_sig.ext;
+    } else {
+      const int64_t ext = (int64_t)(a.L - 1) * s2 + 1;
+      const int64_t Kd2 = (int64_t)(a.K - 1) * d2 + 1;
+      const int64_t dense = ext + Kd2 - 1;
+      const int64_t Lout = (int64_t)(a.L - 1) * a.stride - 2 * (int64_t)a.pad + (int64_t)a.dil * (a.K - 1) + a.opad + 1;
+      if (Lout < 1) return fail(FC_EINVAL, ax_s + "transposed convolution output extent would be " + std::to_string(Lout));
+      a.Lout = (int)Lout;
+      a.imap_sig.L = a.L;
+      a.imap_sig.mode = FC_PAD_CONSTANT;
+      a.imap_sig.pad = 0;
+      a.imap_sig.up = s2;
+      a.imap_sig.sub = 1;
+      a.imap_sig.ext = (int)ext;
+      a.omap.Lout = a.Lout;
+      a.omap.os = 1;
+      a.omap.ob = a.pad;
+      a.omap.og = a.g;
+      a.omap.lim = (int)dense;
+      need = std::max<int64_t>(dense, (Lout - 1 + a.pad) / a.g + 1);
+    }
+    a.imap_ker.L = a.K;
+    a.imap_ker.mode = FC_PAD_CONSTANT;
+    a.imap_ker.pad = 0;
+    a.imap_ker.up = d2;
+    a.imap_ker.sub = 1;
+    a.imap_ker.ext = (a.K - 1) * d2 + 1;
+    const int64_t N = next_pow2(std::max<int64_t>(need, 2));
+    const bool last = (i == nd - 1);
+    if (nd > 1 && N > (last ? kMaxRealLine : kMaxComplexLine))
+      return fail(FC_EUNSUPPORTED, ax_s + "transform extent " + std::to_string(N) + " exceeds the per-axis limit");
+    if (nd == 1 && N > (int64_t)kMaxRealLine * kMaxComplexLine)
+      return fail(FC_EUNSUPPORTED, ax_s + "transform extent " + std::to_string(N) + " exceeds the 1-d limit");
+    a.N = (int)N;
+    if (!P.transposed) a.omap.lim = a.N;
+    a.Nk = last ? a.N / 2 + 1 : a.N;
+    out_vol *= a.Lout;
+    in_vol *= a.L;
+    k_vol *= a.K;
+    inv_scale *= (double)a.N;
+  }
+
+  // ---- structure
+  pl->N1 = pl->N2 = 0;
+  if (nd == 1) {
+    if (pl->ax[0].N <= kMaxRealLine) {
+      pl->structure = FC_S_1D;
+    } else {
+      pl->structure = FC_S_1D_SPLIT;
+      const int l2 = ilog2(pl->ax[0].N);
+      pl->N1 = 1 << ((l2 + 1) / 2);
+      pl->N2 = pl->ax[0].N / pl->N1;
+      pl->ax[0].Nk = 0;  // bins are (N1/2+1) x N2 for the split layout
+    }
+  } else {
+    pl->structure = (nd == 2) ? FC_S_2D : FC_S_3D;
+  }
+  if (pl->structure == FC_S_1D_SPLIT)
+    bins = (int64_t)(pl->N1 / 2 + 1) * pl->N2;
+  else {
+    bins = 1;
+    for (int i = 0; i < nd; ++i) bins *= pl->ax[i].Nk;
+  }
+  int tw_len = 2;
+  for (int i = 0; i < nd; ++i) tw_len = std::max(tw_len, pl->ax[i].N);
+  if (pl->structure == FC_S_1D_SPLIT) tw_len = std::max(pl->N1, pl->N2);
+  pl->tw_len = tw_len;
+
+  // ---- forward programs
+  const int Ig = P.cin / P.groups, Og = P.cout / P.groups;
+  SrcDesc sig;
+  sig.n_outer = (int64_t)P.batch * P.cin;
+  sig.o_c2 = 1;
+  sig.o_q = 1;
+  sig.o_sA = in_vol;
+  sig.o_sB = 0;
+  sig.o_sC = 0;
+  sig.conj = false;
+  sig.scale = 1.f;
+  SrcDesc ker;
+  ker.n_outer = (int64_t)P.cout * Ig;
+  ker.o_c2 = Ig;
+  if (!P.transposed) {  // weight (Cout, Cin/g, K...)
+    ker.o_q = 1;
+    ker.o_sA = (int64_t)Ig * k_vol;
+    ker.o_sB = 0;
+    ker.o_sC = k_vol;
+  } else {  // weight (Cin, Cout/g, K...): (co, ci_local) -> w[grp*Ig + ci_local][co_local]  (functional.py:109-114)
+    ker.o_q = Og;
+    ker.o_sA = (int64_t)Ig * Og * k_vol;
+    ker.o_sB = k_vol;
+    ker.o_sC = (int64_t)Og * k_vol;
+  }
+  ker.conj = !P.transposed;
+  ker.scale = (float)(1.0 / inv_scale);
+  for (int i = 0; i < nd; ++i) {
+    sig.imap[i] = pl->ax[i].imap_sig;
+    sig.L[i] = pl->ax[i].L;
+    ker.imap[i] = pl->ax[i].imap_ker;
+    ker.L[i] = pl->ax[i].K;
+  }
+  pl->sig_fwd.clear();
+  pl->ker_fwd.clear();
+  pl->inv.clear();
+  build_forward(*pl, sig, pl->sig_fwd);
+  build_forward(*pl, ker, pl->ker_fwd);
+  build_inverse(*pl, pl->inv);
+
+  pl->contract.bins = bins;
+  pl->contract.batch = P.batch;
+  pl->contract.cin = P.cin;
+  pl->contract.cout = P.cout;
+  pl->contract.groups = P.groups;
+
+  // ---- sizes
+  fc_plan_info& I = pl->info;
+  I.ndim = nd;
+  for (int i = 0; i < nd; ++i) {
+    I.out_size[i] = pl->ax[i].Lout;
+    I.fft_size[i] = pl->ax[i].N;
+  }
+  I.bins = bins;
+  I.out_elems = (int64_t)P.batch * P.cout * out_vol;
+  I.xspec_bytes = (int64_t)P.batch * P.cin * bins * 8;
+  I.kspec_bytes = (int64_t)P.cout * Ig * bins * 8;
+  I.yspec_bytes = (int64_t)P.batch * P.cout * bins * 8;
+  int64_t sA = 0, sB = 0;
+  auto scan = [&](const std::vector<fc_step>& v) {
+    for (const fc_step& s : v) {
+      if (s.dst == FC_BUF_SA) sA = std::max(sA, step_out_bytes(s));
+      if (s.dst == FC_BUF_SB) sB = std::max(sB, step_out_bytes(s));
+    }
+  };
+  scan(pl->sig_fwd);
+  scan(pl->ker_fwd);
+  scan(pl->inv);
+  pl->off_xspec = 0;
+  pl->off_yspec = align_up(pl->off_xspec + I.xspec_bytes, 256);
+  pl->off_sA = align_up(pl->off_yspec + I.yspec_bytes, 256);
+  pl->off_sB = align_up(pl->off_sA + sA, 256);
+  pl->scratch_bytes = sA + sB;
+  I.workspace_bytes = align_up(pl->off_sB + sB, 256) + 256;
+  I.const_bytes = (int64_t)tw_len * 8;
+  I.n_launches = (int)(pl->sig_fwd.size() + 1 + pl->inv.size());
+  I.n_launches_kspec = (int)pl->ker_fwd.size();
+  I.fused = 0;
+  I.algo_bytes_s1 = 4 * (int64_t)P.batch * P.cin * in_vol + I.xspec_bytes;
+  I.algo_bytes_s2 = 4 * (int64_t)P.cout * Ig * k_vol + I.kspec_bytes;
+  I.algo_bytes_s3 = I.xspec_bytes + I.kspec_bytes + I.yspec_bytes;
+  I.algo_bytes_s4 = I.yspec_bytes + 4 * I.out_elems + 4 * (int64_t)P.cout;
+  return FC_OK;
+}
+
+std::string fc_plan_to_string(const fc_plan* pl) {
+  std::ostringstream os;
+  const fc_problem& P = pl->prob;
+  os << "fft_conv" << (P.transposed ? "_transpose" : "") << " nd=" << pl->nd << " B=" << P.batch << " Cin=" << P.cin
+     << " Cout=" << P.cout << " groups=" << P.groups << " structure=" << pl->structure;
+  if (pl->structure == FC_S_1D_SPLIT) os << " N1=" << pl->N1 << " N2=" << pl->N2;
+  os << " bins=" << pl->info.bins << " tw_len=" << pl->tw_len << "\n";
+  for (int i = 0; i < pl->nd; ++i) {
+    const fc_axis& a = pl->ax[i];
+    os << "  axis" << i << ": L=" << a.L << " K=" << a.K << " s=" << a.stride << " p=" << a.pad << " d=" << a.dil
+       << " op=" << a.opad << " g=" << a.g << " N=" << a.N << " Nk=" << a.Nk << " Lout=" << a.Lout << " imap(ext=" << a.imap_sig.ext
+       << ",up=" << a.imap_sig.up << ",sub=" << a.imap_sig.sub << ",pad=" << a.imap_sig.pad << ") omap(os=" << a.omap.os
+       << ",ob=" << a.omap.ob << ",og=" << a.omap.og << ",lim=" << a.omap.lim << ")\n";
+  }
+  auto dump = [&](const char* name, const std::vector<fc_step>& v) {
+    for (size_t i = 0; i < v.size(); ++i) {
+      const fc_pass& p = v[i].pass;
+      static const char* kn[] = {"R2C", "C2C_FWD", "C2C_INV", "C2R"};
+      os << "  " << name << "[" << i << "] " << kn[p.kind] << " N=" << p.N << " M=" << p.M << " T=" << p.T << " outer=" << p.n_outer
+         << " R=" << p.R << " tiles=" << p.n_tiles << " flat=" << p.flat << " in(os=" << p.in_os << ",rs=" << p.in_rs
+         << ",es=" << p.in_es << ",rfast=" << p.in_rfast << ") out(os=" << p.out_os << ",rs=" << p.out_rs << ",es=" << p.out_es
+         << ",rfast=" << p.out_rfast << ") tw=" << p.twiddle << " conj=" << p.conj_out << " scale=" << p.scale << " buf " << v[i].src
+         << "->" << v[i].dst << "\n";
+    }
+  };
+  dump("sig", pl->sig_fwd);
+  dump("ker", pl->ker_fwd);
+  dump("inv", pl->inv);
+  os << "  fused=" << pl->fused.enabled << " workspace=" << pl->info.workspace_bytes << " launches=" << pl->info.n_launches << "\n";
+  return os.str();
+}

@@ -1,0 +1,64 @@
+// fc_plan.h — host-side plan object: shape algebra + the program of axis passes for one convolution call.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "fc_types.h"
+
+enum { FC_BUF_USER_IN = 0, FC_BUF_SPEC = 1, FC_BUF_SA = 2, FC_BUF_SB = 3, FC_BUF_USER_OUT = 4 };
+
+// Layout family of the transform program.
+enum {
+  FC_S_1D = 1,       // one real pass along the only axis
+  FC_S_1D_SPLIT = 2, // four-step: N = N1*N2, real pass over the strided index, complex pass over the contiguous one
+  FC_S_2D = 3,
+  FC_S_3D = 4
+};
+
+struct fc_step {
+  fc_pass pass;
+  int src;  // FC_BUF_*
+  int dst;
+};
+
+// Geometry of the fused "last forward axis -> contraction -> first inverse axis" kernel (fc_fused.cuh).
+struct fc_fused_desc {
+  int32_t enabled;
+  int32_t N;        // transform length of the fused axis
+  int32_t n_in;     // stored input elements per line
+  int32_t n_out;    // stored output elements per line
+  int32_t nb;       // batches per CTA
+  int32_t lines;    // lines (bins of the other axes) per (batch, channel)
+  fc_imap imap;
+  fc_omap omap;
+};
+
+struct fc_axis {
+  int L, K, stride, pad, dil, opad;
+  int g;        // polyphase reduction factor gcd(stride, dilation)
+  int N;        // transform extent
+  int Nk;       // stored bins on this axis
+  int Lout;     // output extent
+  fc_imap imap_sig, imap_ker;
+  fc_omap omap;
+};
+
+struct fc_plan {
+  fc_problem prob;
+  fc_plan_info info;
+  int structure;
+  int nd;
+  int threads;
+  int tw_len;
+  int N1, N2;  // FC_S_1D_SPLIT factors
+  fc_axis ax[FC_MAX_ND];
+  std::vector<fc_step> sig_fwd, ker_fwd, inv;
+  fc_contract_desc contract;
+  fc_fused_desc fused;
+  int64_t off_xspec, off_yspec, off_sA, off_sB;
+  int64_t scratch_bytes;
+};
+
+// Returns FC_OK or a negative code; msg receives the reason.
+int fc_plan_build(fc_plan* plan, const fc_problem* prob, std::string* msg);
+std::string fc_plan_to_string(const fc_plan* plan);

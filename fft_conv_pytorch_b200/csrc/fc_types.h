@@ -1,0 +1,79 @@
+// fc_types.h — POD descriptors shared by the host planner (fc_plan.cpp) and the device kernels (fc_kernels.cuh).
+//
+// A convolution call is executed as a short program of "axis passes" over spectra kept in HBM:
+//   R2C      real lines  -> half spectrum along one axis   (fused pad / zero-stuffing gather on load)
+//   C2C_FWD  complex lines, forward transform of one more axis (gather map on load)
+//   [contraction over channels, per frequency bin]
+//   C2C_INV  inverse transform of one axis (crop / stride / lattice map on store)
+//   C2R      half spectrum -> real lines (crop / stride / lattice map + bias on store)
+// Each pass moves a tile of T lines through shared memory; on each side of a pass either the line
+// elements are contiguous in HBM ("n-fast") or the T lines of a tile are adjacent ("r-fast", a transposing
+// access), so every HBM access is made of >= T*8-byte contiguous segments.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/fftconv_b200.h"
+
+enum { FC_R2C = 0, FC_C2C_FWD = 1, FC_C2C_INV = 2, FC_C2R = 3 };
+
+// Gather map of a forward pass: dense transform position u in [0, N) -> source index, or "zero".
+// Covers F.pad (reference functional.py:60-62; all four modes), the zero-stuffing of the transposed conv
+// (functional.py:126-139, `up`), kernel dilation (functional.py:49-57, `up`) and the polyphase subsample `sub`.
+struct fc_imap {
+  int32_t L;     // source extent
+  int32_t mode;  // FC_PAD_*
+  int32_t pad;   // left padding
+  int32_t up;    // zero-stuffing factor (>=1): only u % up == 0 carries data
+  int32_t sub;   // subsample factor (>=1): dense position w reads padded position w*sub
+  int32_t ext;   // dense extent; u >= ext is zero
+};
+
+// Scatter map of an inverse pass: output index j in [0, Lout) takes dense index q/og, q = j*os + ob, when
+// q % og == 0 and q/og < lim, else 0 (+ bias in the last pass). Covers the crop+stride slice of
+// functional.py:76-82 and the crop of functional.py:163-169.
+struct fc_omap {
+  int32_t Lout;
+  int32_t os;
+  int32_t ob;
+  int32_t og;
+  int32_t lim;
+};
+
+struct fc_pass {
+  int32_t kind;       // FC_R2C .. FC_C2R
+  int32_t N;          // transform length on this axis (real length for R2C / C2R)
+  int32_t M;          // complex FFT length run in shared memory (N/2 for R2C / C2R, else N)
+  int32_t T;          // lines per tile (power of two)
+  int32_t log2T;
+  int32_t pitch;      // shared-memory line pitch in complex elements
+  int32_t n_in;       // stored input elements per line
+  int32_t n_out;      // stored output elements per line
+  int32_t flat;       // 1: tiles run over the flattened (outer, line) index (both sides n-fast)
+  int32_t in_rfast;   // 1: input side is r-fast (lines of a tile adjacent in HBM)
+  int32_t out_rfast;  // 1: output side is r-fast
+  int32_t twiddle;    // 1: four-step twiddle W_twN^(k*r) on R2C store / conj on C2R load
+  int32_t conj_out;   // forward passes: conjugate on store (kernel spectrum of the correlation)
+  int32_t pos_n;      // dense position on the mapped axis: u = n*pos_n + r*pos_r
+  int32_t pos_r;
+  int32_t tw_len;     // length of the twiddle table (power of two >= every N of the plan)
+  int32_t cout;       // C2R: bias index = outer % cout
+  int32_t has_bias;
+  float scale;        // forward passes: multiply on store (1/prod(N) folded into the kernel spectrum)
+  int64_t twN;        // four-step twiddle modulus
+  int64_t n_outer;
+  int64_t R;          // lines per outer item
+  int64_t tiles_per_outer;
+  int64_t n_tiles;
+  // element (outer o, line r, index n) lives at o*os + r*rs + n*es (complex elements, or floats on the real side)
+  int64_t in_os, in_rs, in_es;
+  int64_t out_os, out_rs, out_es;
+  // R2C input base: base(o) = ((o/o_c2)/o_q)*o_sA + ((o/o_c2)%o_q)*o_sB + (o%o_c2)*o_sC   (replaces in_os)
+  int64_t o_c2, o_q, o_sA, o_sB, o_sC;
+  fc_imap imap;
+  fc_omap omap;
+};
+
+struct fc_contract_desc {
+  int64_t bins;  // F
+  int32_t batch, cin, cout, groups;
+};

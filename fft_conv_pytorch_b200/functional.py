@@ -1,0 +1,301 @@
+"""Functional API: ``fft_conv``, ``fft_conv_transpose``, ``complex_matmul`` with the reference's signatures.
+
+Mirrors fft_conv_pytorch/functional.py of the reference (``fft_conv`` :19-28, ``fft_conv_transpose`` :92-101,
+``complex_matmul`` :11-16): same argument names, meaning and defaults. The work is done by the sm_100a kernels of
+``libfftconv_b200.so`` through the C ABI of include/fftconv_b200.h; torch only supplies device memory and the
+current stream. There is no CPU implementation: CPU tensors are staged to the GPU and back (the "host buffer"
+path, ``fc_conv_host``), and without a CUDA device or without the library every call raises.
+
+Differences from the reference, all documented in DESIGN.md:
+  * the result is a contiguous tensor (the reference returns a strided view of its irfftn buffer);
+  * float32 only (the reference also runs float64 on CPU);
+  * malformed problems that the reference silently mis-computes (kernel larger than the padded signal,
+    ``Cin % groups != 0`` ...) raise ``ValueError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+import weakref
+from collections import OrderedDict
+from typing import Iterable, Optional, Tuple, Union
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+from .utils import to_ntuple
+
+IntOrSeq = Union[int, Iterable[int]]
+
+_lock = threading.RLock()
+_plans: "OrderedDict[tuple, _PlanEntry]" = OrderedDict()
+_PLAN_CACHE_MAX = 64
+_kspec_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+_KSPEC_CACHE_MAX_BYTES = 64 << 30
+_kspec_cache_bytes = 0
+_launch_counter = 0  # kernels queued by this module (bench.py reports it)
+
+
+def launches() -> int:
+    return _launch_counter
+
+
+class _PlanEntry:
+    """A host plan plus its per-device constant table."""
+
+    def __init__(self, plan: L.Plan):
+        self.plan = plan
+        self.const = {}  # device index -> uint8 tensor
+
+    def const_for(self, device: torch.device) -> Tensor:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        t = self.const.get(idx)
+        if t is None:
+            lib = self.plan.lib
+            t = torch.empty(int(self.plan.info.const_bytes), dtype=torch.uint8, device=device)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            L.check(lib, lib.fc_plan_init_const(self.plan.handle, ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(stream)), "fc_plan_init_const")
+            self.const[idx] = t
+        return t
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("fft_conv_pytorch_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
+
+
+def get_plan(
+    transposed: bool,
+    batch: int,
+    cin: int,
+    cout: int,
+    groups: int,
+    in_size: Tuple[int, ...],
+    kernel_size: Tuple[int, ...],
+    stride: Tuple[int, ...],
+    padding: Tuple[int, ...],
+    dilation: Tuple[int, ...],
+    output_padding: Tuple[int, ...],
+    padding_mode: str,
+    flags: int = 0,
+    threads: int = 0,
+) -> _PlanEntry:
+    key = (transposed, batch, cin, cout, groups, in_size, kernel_size, stride, padding, dilation, output_padding, padding_mode, flags, threads)
+    with _lock:
+        e = _plans.get(key)
+        if e is not None:
+            _plans.move_to_end(key)
+            return e
+        prob = L.make_problem(transposed, batch, cin, cout, groups, in_size, kernel_size, stride, padding, dilation, output_padding,
+                              padding_mode, threads, flags)
+        e = _PlanEntry(L.Plan(L.load(), prob))
+        _plans[key] = e
+        while len(_plans) > _PLAN_CACHE_MAX:
+            _plans.popitem(last=False)
+        return e
+
+
+def clear_caches() -> None:
+    global _kspec_cache_bytes
+    with _lock:
+        _plans.clear()
+        _kspec_cache.clear()
+        _kspec_cache_bytes = 0
+
+
+def _ptr(t: Optional[Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _check_tensor(name: str, t: Tensor) -> None:
+    if not isinstance(t, Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {t.dtype}); fft_conv_pytorch_b200 computes in fp32 only")
+
+
+def kernel_spectrum(entry: _PlanEntry, kernel: Tensor, device: torch.device, use_cache: bool = True) -> Tensor:
+    """Cached spectrum of the weight tensor (stage 2): dilation scatter / transposed regroup + transform +
+    conjugate + 1/N scale, in the layout the contraction reads.
+
+    The cache entry is tied to the weight *object* (weak reference) and to its storage pointer and version
+    counter, so an optimizer step, an in-place edit or a re-used allocation can never serve a stale spectrum.
+    It is a derived, non-persistent object: never part of a ``state_dict``."""
+    global _kspec_cache_bytes, _launch_counter
+    plan = entry.plan
+    dev_idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (id(plan), id(kernel), dev_idx)
+    if use_cache:
+        with _lock:
+            hit = _kspec_cache.get(key)
+            if hit is not None:
+                ref, ver, ptr, spec = hit
+                if ref() is kernel and ver == kernel._version and ptr == kernel.data_ptr():
+                    _kspec_cache.move_to_end(key)
+                    return spec
+                _drop_kspec(key)
+    lib = plan.lib
+    const = entry.const_for(device)
+    kspec = torch.empty(int(plan.info.kspec_bytes) // 4, dtype=torch.float32, device=device)
+    ws = torch.empty(int(plan.info.workspace_bytes), dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    w = kernel.detach().to(device=device).contiguous()
+    L.check(lib, lib.fc_kernel_spectrum(plan.handle, _ptr(const), _ptr(w), _ptr(kspec), _ptr(ws), ctypes.c_void_p(stream)), "fc_kernel_spectrum")
+    _launch_counter += int(plan.info.n_launches_kspec)
+    if use_cache:
+        with _lock:
+            try:
+                ref = weakref.ref(kernel, lambda _r, k=key: _drop_kspec(k))
+            except TypeError:
+                return kspec
+            _kspec_cache[key] = (ref, kernel._version, kernel.data_ptr(), kspec)
+            _kspec_cache_bytes += kspec.numel() * 4
+            while _kspec_cache_bytes > _KSPEC_CACHE_MAX_BYTES and len(_kspec_cache) > 1:
+                _drop_kspec(next(iter(_kspec_cache)))
+    return kspec
+
+
+def _drop_kspec(key) -> None:
+    global _kspec_cache_bytes
+    with _lock:
+        old = _kspec_cache.pop(key, None)
+        if old is not None:
+            _kspec_cache_bytes -= old[3].numel() * 4
+
+
+def _run(transposed: bool, signal: Tensor, kernel: Tensor, bias: Optional[Tensor], stride, padding, output_padding, dilation,
+         groups: int, padding_mode: str, flags: int = 0) -> Tensor:
+    global _launch_counter
+    _check_tensor("signal", signal)
+    _check_tensor("kernel", kernel)
+    if bias is not None:
+        _check_tensor("bias", bias)
+    n = signal.ndim - 2
+    if n < 1:
+        raise ValueError(f"signal must have shape (batch, channels, *spatial); got {tuple(signal.shape)}")
+    padding_ = to_ntuple(padding, n)
+    stride_ = to_ntuple(stride, n)
+    dilation_ = to_ntuple(dilation, n)
+    opad_ = to_ntuple(output_padding, n)
+    if kernel.ndim != signal.ndim:
+        raise ValueError(f"kernel must have {signal.ndim} dims like the signal; got {kernel.ndim}")
+    if not isinstance(groups, int) or groups < 1:
+        raise ValueError(f"groups must be a positive int, got {groups!r}")
+    B, cin = int(signal.shape[0]), int(signal.shape[1])
+    if transposed:
+        if kernel.shape[0] != cin:
+            raise ValueError(f"transposed kernel must have shape (in_channels={cin}, out_channels/groups, ...); got {tuple(kernel.shape)}")
+        cout = int(kernel.shape[1]) * groups
+    else:
+        cout = int(kernel.shape[0])
+        if cin % groups or kernel.shape[1] != cin // groups:
+            raise ValueError(
+                f"kernel must have shape (out_channels, in_channels/groups={cin}/{groups}, ...); got {tuple(kernel.shape)}")
+    if bias is not None and tuple(bias.shape) != (cout,):
+        raise ValueError(f"bias must have shape ({cout},); got {tuple(bias.shape)}")
+    if torch.is_grad_enabled() and (signal.requires_grad or kernel.requires_grad or (bias is not None and bias.requires_grad)):
+        from .autograd import conv_with_grad  # local import: autograd wraps this module
+
+        return conv_with_grad(transposed, signal, kernel, bias, stride_, padding_, opad_, dilation_, groups, padding_mode)
+
+    _require_cuda()
+    entry = get_plan(transposed, B, cin, cout, groups, tuple(int(s) for s in signal.shape[2:]), tuple(int(s) for s in kernel.shape[2:]),
+                     stride_, padding_, dilation_, opad_, padding_mode, flags)
+    plan = entry.plan
+    lib = plan.lib
+    host_path = not signal.is_cuda
+    dev = kernel.device if kernel.is_cuda else (signal.device if signal.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+    if signal.is_cuda and kernel.is_cuda and signal.device != kernel.device:
+        raise ValueError(f"signal is on {signal.device} but kernel is on {kernel.device}")
+    with torch.cuda.device(dev):
+        b_dev = None if bias is None else (bias.detach().contiguous() if bias.is_cuda else bias.detach().to(dev))
+        const = entry.const_for(dev)
+        kspec = kernel_spectrum(entry, kernel, dev)
+        ws = torch.empty(int(plan.info.workspace_bytes), dtype=torch.uint8, device=dev)
+        out_shape = (B, cout) + plan.out_size
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if not host_path:
+            x = signal.detach().contiguous()
+            y = torch.empty(out_shape, dtype=torch.float32, device=dev)
+            L.check(lib, lib.fc_conv(plan.handle, _ptr(const), _ptr(x), _ptr(kspec), _ptr(b_dev), _ptr(y), _ptr(ws), stream), "fc_conv")
+            _launch_counter += int(plan.info.n_launches)
+            return y
+        # host buffers in, host buffers out: H2D + kernels + D2H on the current stream
+        x_host = signal.detach().contiguous()
+        if not x_host.is_pinned():
+            x_host = x_host.pin_memory()
+        y_host = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
+        x_stage = torch.empty(x_host.shape, dtype=torch.float32, device=dev)
+        y_stage = torch.empty(out_shape, dtype=torch.float32, device=dev)
+        L.check(lib, lib.fc_conv_host(plan.handle, _ptr(const), _ptr(x_host), _ptr(x_stage), _ptr(kspec), _ptr(b_dev), _ptr(y_stage),
+                                      _ptr(y_host), _ptr(ws), stream), "fc_conv_host")
+        _launch_counter += int(plan.info.n_launches)
+        torch.cuda.current_stream(dev).synchronize()
+        return y_host
+
+
+def fft_conv(
+    signal: Tensor,
+    kernel: Tensor,
+    bias: Tensor = None,
+    stride: IntOrSeq = 1,
+    padding: IntOrSeq = 0,
+    dilation: IntOrSeq = 1,
+    groups: int = 1,
+    padding_mode: str = "constant",
+) -> Tensor:
+    """N-d (1, 2 or 3 spatial dims) convolution through the frequency domain; equals ``F.conv{n}d``.
+
+    Same signature as the reference's ``fft_conv`` (reference functional.py:19-28).
+    signal (B, Cin, *L), kernel (Cout, Cin/groups, *K), bias (Cout,) or None -> (B, Cout, *Lout).
+    """
+    return _run(False, signal, kernel, bias, stride, padding, 0, dilation, groups, padding_mode)
+
+
+def fft_conv_transpose(
+    signal: Tensor,
+    kernel: Tensor,
+    bias: Tensor = None,
+    stride: IntOrSeq = 1,
+    padding: IntOrSeq = 0,
+    output_padding: IntOrSeq = 0,
+    dilation: IntOrSeq = 1,
+    groups: int = 1,
+) -> Tensor:
+    """Transposed convolution through the frequency domain; equals ``F.conv_transpose{n}d``.
+
+    Same signature as the reference's ``fft_conv_transpose`` (reference functional.py:92-101).
+    signal (B, Cin, *L), kernel (Cin, Cout/groups, *K), bias (Cout,) or None -> (B, Cout, *Lout).
+    """
+    return _run(True, signal, kernel, bias, stride, padding, output_padding, dilation, groups, "constant")
+
+
+def complex_matmul(a: Tensor, b: Tensor, groups: int = 1) -> Tensor:
+    """Grouped per-bin channel contraction ``einsum("bgi...,goi...->bgo...")`` (reference functional.py:11-16).
+
+    a: (B, Cin, *bins) complex64, b: (Cout, Cin/groups, *bins) complex64 -> (B, Cout, *bins) complex64.
+    """
+    global _launch_counter
+    if a.dtype != torch.complex64 or b.dtype != torch.complex64:
+        raise TypeError("complex_matmul expects complex64 tensors")
+    _require_cuda()
+    if not (a.is_cuda and b.is_cuda):
+        raise ValueError("complex_matmul expects CUDA tensors")
+    B, cin = int(a.shape[0]), int(a.shape[1])
+    cout = int(b.shape[0])
+    if cin % groups or cout % groups or b.shape[1] != cin // groups or tuple(a.shape[2:]) != tuple(b.shape[2:]):
+        raise ValueError(f"complex_matmul: incompatible shapes {tuple(a.shape)} x {tuple(b.shape)} with groups={groups}")
+    bins = 1
+    for s in a.shape[2:]:
+        bins *= int(s)
+    ar = torch.view_as_real(a.contiguous())
+    br = torch.view_as_real(b.contiguous())
+    y = torch.empty((B, cout) + tuple(a.shape[2:]), dtype=torch.complex64, device=a.device)
+    yr = torch.view_as_real(y)
+    lib = L.load()
+    with torch.cuda.device(a.device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+        L.check(lib, lib.fc_complex_matmul(_ptr(ar), _ptr(br), _ptr(yr), B, cin, cout, groups, bins, stream), "fc_complex_matmul")
+    _launch_counter += 1
+    return y

@@ -1,0 +1,40 @@
+// cuda_shim.cpp — TEST INFRASTRUCTURE ONLY (see cuda_shim.h).
+#include "cuda_shim.h"
+
+#include <barrier>
+#include <memory>
+#include <thread>
+#include <vector>
+
+thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
+char* fc_emul_smem = nullptr;
+static std::barrier<>* g_barrier = nullptr;
+
+void __syncthreads() { g_barrier->arrive_and_wait(); }
+
+void fc_emul_launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body) {
+  const unsigned nt = block.x;
+  std::vector<char> shared(smem + 64);
+  fc_emul_smem = shared.data();
+  std::barrier<> bar((std::ptrdiff_t)nt);
+  g_barrier = &bar;
+  std::vector<std::thread> th;
+  th.reserve(nt);
+  for (unsigned t = 0; t < nt; ++t) {
+    th.emplace_back([=, &body]() {
+      blockDim = block;
+      gridDim = grid;
+      threadIdx = dim3(t, 0, 0);
+      for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+          for (unsigned bx = 0; bx < grid.x; ++bx) {
+            blockIdx = dim3(bx, by, bz);
+            body();
+            g_barrier->arrive_and_wait();  // block boundary: shared memory is reused by the next block
+          }
+    });
+  }
+  for (auto& t : th) t.join();
+  g_barrier = nullptr;
+  fc_emul_smem = nullptr;
+}

@@ -1,0 +1,96 @@
+"""The generic CUDA kernels (fc_kernels.cuh), executed on host threads by tests/cpu_emul, against the golden
+outputs of the reference. This checks the kernels' index algebra — pass program, gather/scatter maps, layouts,
+four-step twiddles, Stockham stages — in a container without a GPU. The `-m gpu` tests repeat the same cases on
+the real device through the product library."""
+import numpy as np
+import pytest
+
+from tests.cpu_emul import emul
+from tests.helpers import golden, rel_err
+from fft_conv_pytorch_b200 import _lib as L
+
+N_CASES = len(golden())
+# every 3rd small case + all the medium / special ones at the end of the file
+SEL = sorted(set(range(0, N_CASES, 3)) | set(range(N_CASES - 24, N_CASES)))
+
+
+@pytest.mark.parametrize("i", SEL)
+def test_emulated_kernels_match_reference(i):
+    c = golden().case(i)
+    y, plan = emul.conv(c["x"], c["w"], c["b"], transposed=c["transposed"], **c["kw"])
+    assert y.shape == c["direct"].shape
+    assert not np.isnan(y).any()  # every output element was written
+    assert rel_err(y, c["direct"]) < 1e-5
+    if not c["ref_short"]:
+        assert rel_err(y, c["ref32"]) < 2e-5
+
+
+@pytest.mark.parametrize("i", SEL[::7])
+def test_stage_calls_equal_fused_call(i):
+    c = golden().case(i)
+    y0, _ = emul.conv(c["x"], c["w"], c["b"], transposed=c["transposed"], **c["kw"])
+    y1, _ = emul.conv(c["x"], c["w"], c["b"], transposed=c["transposed"], staged=True, **c["kw"])
+    assert np.array_equal(y0, y1)
+
+
+@pytest.mark.parametrize("i", SEL[::5])
+def test_polyphase_off_gives_same_result(i):
+    c = golden().case(i)
+    y0, p0 = emul.conv(c["x"], c["w"], c["b"], transposed=c["transposed"], **c["kw"])
+    y1, p1 = emul.conv(c["x"], c["w"], c["b"], transposed=c["transposed"], flags=L.FC_FLAG_NO_POLYPHASE, **c["kw"])
+    assert rel_err(y0, y1) < 1e-5
+
+
+@pytest.mark.parametrize("threads", [32, 96, 256])
+def test_thread_count_independent(threads):
+    c = golden().case(len(golden()) - 3)  # 2-d medium case
+    y, _ = emul.conv(c["x"], c["w"], c["b"], transposed=c["transposed"], threads=threads, **c["kw"])
+    assert rel_err(y, c["direct"]) < 1e-5
+
+
+def test_linearity_and_shift_property():
+    """Size-independent properties used at BASELINE sizes on the GPU: linearity in the signal and
+    conv(delta kernel) == shifted crop of the signal."""
+    rng = np.random.RandomState(5)
+    x1 = rng.standard_normal((1, 2, 40, 24)).astype(np.float32)
+    x2 = rng.standard_normal((1, 2, 40, 24)).astype(np.float32)
+    w = rng.standard_normal((2, 2, 7, 5)).astype(np.float32)
+    ya, _ = emul.conv(x1, w)
+    yb, _ = emul.conv(x2, w)
+    yc, _ = emul.conv(x1 + 2 * x2, w)
+    assert rel_err(yc, ya + 2 * yb) < 1e-5
+    d = np.zeros((2, 2, 7, 5), np.float32)
+    d[0, 0, 3, 2] = 1.0
+    d[1, 1, 0, 4] = 1.0
+    yd, _ = emul.conv(x1, d)
+    assert rel_err(yd[0, 0], x1[0, 0, 3:3 + 34, 2:2 + 20]) < 1e-5
+    assert rel_err(yd[0, 1], x1[0, 1, 0:34, 4:24]) < 1e-5
+
+
+def test_bad_problems_raise():
+    with pytest.raises(ValueError, match="exceeds the padded signal"):
+        emul.plan_for((1, 1, 4), (1, 1, 7))
+    with pytest.raises(ValueError, match="divisible by groups"):
+        emul.plan_for((1, 3, 8), (2, 1, 3), groups=2)
+    with pytest.raises(ValueError, match="reflect"):
+        emul.plan_for((1, 1, 4), (1, 1, 3), padding=4, padding_mode="reflect")
+    with pytest.raises(ValueError):
+        emul.plan_for((1, 1, 8), (1, 1, 3), stride=0)
+
+
+def test_plan_shapes_follow_reference_formulas():
+    # forward: Lout = (L + 2p - d(K-1) - 1)//s + 1 (reference functional.py:79); transposed: functional.py:144-154
+    p = emul.plan_for((8, 8, 512, 512), (8, 8, 65, 65))
+    assert p.out_size == (448, 448) and p.fft_size == (512, 512)
+    assert p.info.bins == 512 * 257
+    p = emul.plan_for((4, 64, 1024, 1024), (64, 16, 31, 31), transposed=True, stride=2, dilation=2, groups=4)
+    assert p.out_size == (2107, 2107)
+    assert p.fft_size == (2048, 2048)  # polyphase: dense 1024 (*) 31 -> 1054 per axis
+    p = emul.plan_for((16, 256, 65536), (256, 256, 4097))
+    assert p.out_size == (61440,) and p.fft_size == (65536,)
+    p = emul.plan_for((1, 8, 32768), (8, 8, 1025))
+    assert p.out_size == (31744,)
+    # SURVEY §8d algorithmic bytes at the reference extents for c1/c2
+    p = emul.plan_for((8, 8, 512, 512), (8, 8, 65, 65))
+    i = p.info
+    assert abs((i.algo_bytes_s1 + i.algo_bytes_s3 + i.algo_bytes_s4) / 1e6 - 455.3) < 0.5
