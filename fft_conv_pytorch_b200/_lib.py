@@ -78,6 +78,8 @@ SYMBOLS = {
     "fc_inverse": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "fc_conv": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "fc_conv_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fc_conv_profiled": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "fc_plan_launch_info": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int64)]),
     "fc_complex_matmul": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _P]),
 }
 

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "fc_kernels.cuh"
 #include "fc_plan.h"
@@ -21,6 +22,24 @@
 namespace {
 
 thread_local std::string g_err;
+
+// Optional per-launch event recorder (fc_conv_profiled).
+#ifndef FC_CPU_EMUL
+struct Recorder {
+  std::vector<cudaEvent_t> ev;
+  cudaStream_t st;
+};
+thread_local Recorder* g_rec = nullptr;
+void rec_mark() {
+  if (!g_rec) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, g_rec->st);
+  g_rec->ev.push_back(e);
+}
+#else
+void rec_mark() {}
+#endif
 
 int set_err(int code, const std::string& m) {
   g_err = m;
@@ -89,6 +108,7 @@ int launch_pass(const fc_plan* pl, const fc_pass& p, const void* in, void* out, 
       FC_LAUNCH(k, g, b, smem, st, a);
     } break;
   }
+  rec_mark();
   return check_cuda("axis pass launch");
 }
 
@@ -124,6 +144,7 @@ int launch_contract(const float2* X, const float2* K, float2* Y, int64_t bins, i
     auto k = fc_contract_kernel<2, 2>;
     FC_LAUNCH(k, g, b, 0, st, a);
   }
+  rec_mark();
   return check_cuda("contraction launch");
 }
 
@@ -266,6 +287,68 @@ int fc_conv_host(const fc_plan* plan, const void* d_const, const float* h_x, flo
   if (rc) return rc;
   e = cudaMemcpyAsync(h_y, d_y_stage, (size_t)plan->info.out_elems * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   if (e != cudaSuccess) return set_err((int)e, std::string("D2H copy: ") + cudaGetErrorString(e));
+  return FC_OK;
+}
+
+int fc_conv_profiled(const fc_plan* plan, const void* d_const, const float* d_x, const float* d_kspec, const float* d_bias, float* d_y,
+                     void* d_ws, void* stream, float* ms_out, int max_n, int* n_out) {
+  if (!ms_out || !n_out) return set_err(FC_ENULL, "fc_conv_profiled: NULL argument");
+  *n_out = 0;
+#ifdef FC_CPU_EMUL
+  return fc_conv(plan, d_const, d_x, d_kspec, d_bias, d_y, d_ws, stream);
+#else
+  Recorder rec;
+  rec.st = (cudaStream_t)stream;
+  g_rec = &rec;
+  rec_mark();
+  int rc = fc_conv(plan, d_const, d_x, d_kspec, d_bias, d_y, d_ws, stream);
+  g_rec = nullptr;
+  cudaError_t e = cudaStreamSynchronize(rec.st);
+  if (!rc && e != cudaSuccess) rc = set_err((int)e, std::string("fc_conv_profiled: ") + cudaGetErrorString(e));
+  int n = 0;
+  for (size_t i = 1; i < rec.ev.size(); ++i) {
+    float ms = 0.f;
+    if (!rc) cudaEventElapsedTime(&ms, rec.ev[i - 1], rec.ev[i]);
+    if (n < max_n) ms_out[n++] = ms;
+  }
+  for (cudaEvent_t ev : rec.ev) cudaEventDestroy(ev);
+  *n_out = n;
+  return rc;
+#endif
+}
+
+int fc_plan_launch_info(const fc_plan* plan, int i, char* name, size_t namelen, int64_t* algo_bytes) {
+  if (!plan || !name || !namelen || !algo_bytes) return set_err(FC_ENULL, "fc_plan_launch_info: NULL argument");
+  std::string nm;
+  int64_t bytes = 0;
+  auto pass_info = [&](const fc_pass& p, const char* prefix) {
+    static const char* kn[] = {"r2c", "c2c_fwd", "c2c_inv", "c2r"};
+    nm = std::string(prefix) + kn[p.kind] + "_N" + std::to_string(p.N);
+    const int64_t lines = p.n_outer * p.R;
+    const int64_t in_el = (p.kind == FC_R2C) ? 4 : 8, out_el = (p.kind == FC_C2R) ? 4 : 8;
+    bytes = lines * ((int64_t)p.n_in * in_el + (int64_t)p.n_out * out_el);
+  };
+#ifndef FC_CPU_EMUL
+  if (plan->fused.enabled) {
+    int rc = fc_fused_launch_info(plan, i, &nm, &bytes);
+    if (rc) return set_err(FC_EINVAL, "fc_plan_launch_info: index out of range");
+  } else
+#endif
+  {
+    const int nf = (int)plan->sig_fwd.size(), ni = (int)plan->inv.size();
+    if (i < 0 || i >= nf + 1 + ni) return set_err(FC_EINVAL, "fc_plan_launch_info: index out of range");
+    if (i < nf)
+      pass_info(plan->sig_fwd[i].pass, "fwd_");
+    else if (i == nf) {
+      nm = "contract";
+      bytes = plan->info.algo_bytes_s3;
+    } else
+      pass_info(plan->inv[i - nf - 1].pass, "inv_");
+  }
+  size_t n = nm.size() < namelen - 1 ? nm.size() : namelen - 1;
+  std::memcpy(name, nm.data(), n);
+  name[n] = 0;
+  *algo_bytes = bytes;
   return FC_OK;
 }
 

@@ -8,3 +8,4 @@ static inline void fc_fused_plan(fc_plan* pl) { pl->fused.enabled = 0; }
 static inline int fc_fused_conv(const fc_plan*, const float2*, const float*, const float2*, const float*, float*, void*, cudaStream_t) {
   return FC_EUNSUPPORTED;
 }
+static inline int fc_fused_launch_info(const fc_plan*, int, std::string*, int64_t*) { return FC_EINVAL; }

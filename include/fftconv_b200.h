@@ -124,6 +124,14 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
 int fc_conv_host(const fc_plan* plan, const void* d_const, const float* h_x, float* d_x_stage, const float* d_kspec,
                  const float* d_bias /*nullable*/, float* d_y_stage, float* h_y, void* d_ws, void* stream);
 
+/* Profiling helpers (bench.py roofline accounting). fc_conv_profiled = fc_conv with a CUDA event recorded around
+ * every launch; unlike the other calls it synchronises the stream before returning. It writes the duration of
+ * each launch (ms) to ms_out[0..*n_out), *n_out = min(max_n, n_launches). */
+int fc_conv_profiled(const fc_plan* plan, const void* d_const, const float* d_x, const float* d_kspec, const float* d_bias,
+                     float* d_y, void* d_ws, void* stream, float* ms_out, int max_n, int* n_out);
+/* Name and algorithmic (compulsory read + write) bytes of launch i of fc_conv. */
+int fc_plan_launch_info(const fc_plan* plan, int i, char* name, size_t namelen, int64_t* algo_bytes);
+
 /* Standalone grouped per-bin contraction = reference complex_matmul(a, b, groups) (functional.py:11-16):
  * a: (B, Cin, bins) complex, b: (Cout, Cin/groups, bins) complex -> y: (B, Cout, bins) complex. No conjugation. */
 int fc_complex_matmul(const float* d_a, const float* d_b, float* d_y, int64_t batch, int64_t cin, int64_t cout, int64_t groups,

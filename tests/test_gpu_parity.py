@@ -1,0 +1,328 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle, the reference's golden outputs and torch's direct
+convolution, on a real B200.  Tolerance: max|y - ref| / max|ref| <= 1e-4 (BASELINE.json north_star);
+small grid cases additionally keep the reference's own absolute tolerance (benchmark_utils.py:53-57)."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import fft_conv_pytorch_b200 as fcp
+from fft_conv_pytorch_b200 import functional as Fn
+from tests.helpers import golden, rel_err, spot_check
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _no_tf32():
+    # direct convolutions used as the expected value must not run in TF32
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _dev(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_native_library_is_loaded():
+    import ctypes
+
+    lib = Fn.L.load()
+    assert isinstance(lib, ctypes.CDLL)
+    assert torch.cuda.get_device_capability()[0] >= 10, "these kernels are built for sm_100a only"
+
+
+@pytest.mark.parametrize("i", range(len(golden())))
+def test_golden_cases(i):
+    c = golden().case(i)
+    fn = fcp.fft_conv_transpose if c["transposed"] else fcp.fft_conv
+    with torch.no_grad():
+        y = fn(_dev(c["x"]), _dev(c["w"]), _dev(c["b"]), **c["kw"])
+    assert y.is_contiguous() and y.dtype == torch.float32
+    y = y.cpu().numpy()
+    assert y.shape == c["direct"].shape
+    assert rel_err(y, c["direct"]) < TOL
+    if not c["ref_short"]:
+        assert rel_err(y, c["ref32"]) < TOL
+        if c["x"].size < 5000:
+            d = np.abs(y - c["ref32"])
+            assert d.mean() < 5e-5 and d.max() < 1e-4
+
+
+def _gcd(a, b):
+    while b:
+        a, b = b, a % b
+    return a
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+@pytest.mark.parametrize("input_size", [7, 8])
+def test_reference_forward_grid(ndim, input_size):
+    """The reference's full forward grid (reference tests/test_functional.py:11-20) against F.conv{n}d."""
+    torch.manual_seed(0)
+    conv = getattr(F, f"conv{ndim}d")
+    worst = 0.0
+    for cin, cout, groups, k, p, s, d in itertools.product([2, 3], [2, 3], [1, 2, 3], [2, 3], [0, 1], [1, 2], [1, 2]):
+        g = _gcd(cin, _gcd(cout, groups))
+        x = torch.randn(2, cin, *([input_size] * ndim), device="cuda")
+        w = torch.randn(cout, cin // g, *([k] * ndim), device="cuda")
+        b = torch.randn(cout, device="cuda")
+        with torch.no_grad():
+            y0 = fcp.fft_conv(x, w, bias=b, padding=p, stride=s, dilation=d, groups=g)
+            y1 = conv(x, w, bias=b, padding=p, stride=s, dilation=d, groups=g)
+        assert y0.shape == y1.shape
+        err = (y0 - y1).abs()
+        assert err.mean().item() < 5e-5 and err.max().item() < 1e-4, (cin, cout, g, k, p, s, d)
+        worst = max(worst, err.max().item())
+    print("worst abs err", worst)
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+@pytest.mark.parametrize("input_size", [7, 8])
+def test_reference_transposed_grid(ndim, input_size):
+    """The reference's transposed grid (reference tests/test_functional_transpose.py:60-88) against F.conv_transpose{n}d."""
+    torch.manual_seed(1)
+    conv = getattr(F, f"conv_transpose{ndim}d")
+    for cin, cout, groups, k, p, op, s, d in itertools.product([2, 3], [2, 3], [1, 2, 3], [2, 3], [0, 1], [0, 1, 2], [1, 2], [1, 2]):
+        d, s = d + op, s + op
+        if ndim == 3 and s > 3:
+            continue
+        g = _gcd(cin, _gcd(cout, groups))
+        x = torch.randn(2, cin, *([input_size] * ndim), device="cuda")
+        w = torch.randn(cin, cout // g, *([k] * ndim), device="cuda")
+        b = torch.randn(cout, device="cuda")
+        kw = dict(padding=p, output_padding=op, stride=s, dilation=d, groups=g)
+        with torch.no_grad():
+            y0 = fcp.fft_conv_transpose(x, w, bias=b, **kw)
+            y1 = conv(x, w, bias=b, **kw)
+        assert y0.shape == y1.shape
+        err = (y0 - y1).abs()
+        assert err.mean().item() < 5e-5 and err.max().item() < 1e-4, (cin, cout, g, k, kw)
+
+
+@pytest.mark.parametrize("mode", ["zeros", "reflect", "replicate", "circular"])
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_modules_match_torch_layers(mode, ndim):
+    torch.manual_seed(2)
+    cls = getattr(fcp, f"FFTConv{ndim}d")
+    ref_cls = getattr(torch.nn, f"Conv{ndim}d")
+    size = {1: 50, 2: 20, 3: 10}[ndim]
+    m = cls(4, 6, 3, stride=2, padding=2, dilation=1, groups=2, padding_mode=mode).cuda()
+    r = ref_cls(4, 6, 3, stride=2, padding=2, dilation=1, groups=2, padding_mode=mode).cuda()
+    r.load_state_dict(m.state_dict())
+    x = torch.randn(3, 4, *([size] * ndim), device="cuda")
+    with torch.no_grad():
+        y0, y1 = m(x), r(x)
+    assert y0.shape == y1.shape
+    assert rel_err(y0.cpu().numpy(), y1.cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_transposed_modules_match_torch_layers(ndim):
+    torch.manual_seed(3)
+    cls = getattr(fcp, f"FFTConvTranspose{ndim}d")
+    ref_cls = getattr(torch.nn, f"ConvTranspose{ndim}d")
+    size = {1: 50, 2: 20, 3: 10}[ndim]
+    m = cls(4, 6, 3, stride=3, padding=1, output_padding=2, dilation=2, groups=2).cuda()
+    r = ref_cls(4, 6, 3, stride=3, padding=1, output_padding=2, dilation=2, groups=2).cuda()
+    r.load_state_dict(m.state_dict())
+    x = torch.randn(3, 4, *([size] * ndim), device="cuda")
+    with torch.no_grad():
+        y0, y1 = m(x), r(x)
+    assert y0.shape == y1.shape
+    assert rel_err(y0.cpu().numpy(), y1.cpu().numpy()) < TOL
+
+
+def test_anisotropic_arguments_and_no_bias():
+    torch.manual_seed(4)
+    x = torch.randn(2, 6, 33, 47, device="cuda")
+    w = torch.randn(9, 2, 5, 3, device="cuda")
+    kw = dict(stride=(2, 3), padding=(4, 1), dilation=(3, 2), groups=3)
+    with torch.no_grad():
+        y0 = fcp.fft_conv(x, w, None, **kw)
+        y1 = F.conv2d(x, w, None, **kw)
+    assert rel_err(y0.cpu().numpy(), y1.cpu().numpy()) < TOL
+    w1 = torch.randn(6, 1, 1, 1, device="cuda")  # kernel size 1, depthwise
+    with torch.no_grad():
+        assert rel_err(fcp.fft_conv(x, w1, groups=6).cpu().numpy(), F.conv2d(x, w1, groups=6).cpu().numpy()) < TOL
+
+
+def test_kernel_spectrum_cache_tracks_weight_version():
+    torch.manual_seed(5)
+    m = fcp.FFTConv1d(2, 2, 9).cuda()
+    x = torch.randn(1, 2, 100, device="cuda")
+    with torch.no_grad():
+        y0 = m(x).clone()
+        n0 = Fn.launches()
+        y0b = m(x)
+        per_call = Fn.launches() - n0  # cached: no kernel-spectrum launches
+        m.weight.mul_(2.0)  # in-place edit bumps the version counter
+        y1 = m(x)
+        ref = F.conv1d(x, m.weight, m.bias)
+    assert torch.equal(y0, y0b)
+    assert per_call == 3  # R2C, contraction, C2R
+    assert rel_err(y1.cpu().numpy(), ref.cpu().numpy()) < TOL
+
+
+def test_host_buffer_path_roundtrip():
+    """CPU tensors in -> CPU tensor out through fc_conv_host (what a CPU-tensor caller of the reference sees)."""
+    torch.manual_seed(6)
+    x = torch.randn(2, 3, 40, 36)
+    w = torch.randn(4, 3, 5, 5)
+    b = torch.randn(4)
+    with torch.no_grad():
+        y = fcp.fft_conv(x, w, b, padding=2)
+    assert not y.is_cuda
+    assert rel_err(y.numpy(), F.conv2d(x, w, b, padding=2).numpy()) < TOL
+
+
+def test_complex_matmul_matches_einsum():
+    torch.manual_seed(7)
+    a = torch.randn(3, 6, 5, 7, dtype=torch.complex64, device="cuda")
+    b = torch.randn(8, 3, 5, 7, dtype=torch.complex64, device="cuda")
+    y = fcp.complex_matmul(a, b, groups=2)
+    ref = torch.einsum("bgi...,goi...->bgo...", a.unflatten(1, [2, 3]), b.unflatten(0, [2, 4])).flatten(1, 2)
+    assert rel_err(torch.view_as_real(y).cpu().numpy(), torch.view_as_real(ref).cpu().numpy()) < 1e-5
+
+
+def test_inputs_are_not_mutated():
+    torch.manual_seed(8)
+    x = torch.randn(1, 4, 30, device="cuda")
+    w = torch.randn(4, 2, 5, device="cuda")
+    x0, w0 = x.clone(), w.clone()
+    with torch.no_grad():
+        fcp.fft_conv_transpose(x, w, stride=2, groups=2)
+    assert torch.equal(x, x0) and torch.equal(w, w0)
+
+
+# ------------------------------------------------------------------------------------------- BASELINE.json shapes
+def _seeded(shape_x, shape_w, cout, seed=0):
+    g = torch.Generator().manual_seed(seed)  # order: signal, weight, bias
+    x = torch.randn(*shape_x, generator=g)
+    w = torch.randn(*shape_w, generator=g)
+    b = torch.randn(cout, generator=g)
+    return x, w, b
+
+
+def test_baseline_c1_full():
+    x, w, b = _seeded((1, 8, 32768), (8, 8, 1025), 8)
+    with torch.no_grad():
+        y = fcp.fft_conv(x.cuda(), w.cuda(), b.cuda())
+        ref = F.conv1d(x.double(), w.double(), b.double())
+    assert y.shape == (1, 8, 31744)
+    assert rel_err(y.cpu().numpy(), ref.numpy()) < TOL
+
+
+def test_baseline_c2_full():
+    torch.manual_seed(0)
+    m = fcp.FFTConv2d(8, 8, 65).cuda()
+    x = torch.randn(8, 8, 512, 512, device="cuda")
+    with torch.no_grad():
+        y = m(x)
+        ref = F.conv2d(x, m.weight, m.bias)
+    assert y.shape == (8, 8, 448, 448)
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < TOL
+    err, n = spot_check(x.cpu().numpy(), m.weight.detach().cpu().numpy(), m.bias.detach().cpu().numpy(), y, n=200)
+    assert err < TOL, (err, n)
+
+
+def test_baseline_c3_full():
+    torch.manual_seed(0)
+    m = fcp.FFTConv3d(8, 8, 17).cuda()
+    x = torch.randn(4, 8, 64, 64, 64, device="cuda")
+    with torch.no_grad():
+        y = m(x)
+        ref = F.conv3d(x, m.weight, m.bias)
+    assert y.shape == (4, 8, 48, 48, 48)
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < TOL
+
+
+def test_baseline_c4_spot_checked_and_linear():
+    """c4 (16,256,65536) x (256,256,4097): a direct convolution is intractable here, so the full-size result is
+    checked at random output positions against the definition in fp64, and through linearity."""
+    x, w, b = _seeded((16, 256, 65536), (256, 256, 4097), 256)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    with torch.no_grad():
+        y = fcp.fft_conv(xd, wd, bd)
+    assert y.shape == (16, 256, 61440)
+    err, n = spot_check(x.numpy(), w.numpy(), b.numpy(), y, n=64)
+    assert err < TOL, (err, n)
+    with torch.no_grad():
+        y2 = fcp.fft_conv(xd * 0.5, wd, None)
+    lin = (y - bd.view(1, -1, 1)) * 0.5
+    assert rel_err(y2[:2].cpu().numpy(), lin[:2].cpu().numpy()) < 1e-5
+
+
+def test_baseline_c5_shard_spot_checked():
+    """c5 per-GPU shard (B=4 of 32): fft_conv_transpose (4,64,1024,1024), kernel (64,16,31,31), stride 2, dilation 2,
+    groups 4. Checked at random positions against the definition, plus the lattice property: with
+    stride = dilation = 2 every odd output position is exactly the bias."""
+    x, w, b = _seeded((4, 64, 1024, 1024), (64, 16, 31, 31), 64)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    with torch.no_grad():
+        y = fcp.fft_conv_transpose(xd, wd, bd, stride=2, dilation=2, groups=4)
+    assert y.shape == (4, 64, 2107, 2107)
+    err, n = spot_check(x.numpy(), w.numpy(), b.numpy(), y, n=200, transposed=True, stride=2, dilation=2, groups=4)
+    assert err < TOL, (err, n)
+    odd = y[:, :, 1::2, :]
+    assert torch.equal(odd, bd.view(1, -1, 1, 1).expand_as(odd))
+
+
+# ------------------------------------------------------------------------------------------- backward
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_backward_matches_torch_forward_conv(ndim):
+    """reference tests/test_functional.py:72-117: weight / bias gradients of y.sum(); input gradient as well."""
+    torch.manual_seed(9)
+    conv = getattr(F, f"conv{ndim}d")
+    for cin, cout, groups, k, p, s, d, size in [(2, 2, 1, 2, 0, 1, 1, 7), (3, 3, 3, 3, 1, 2, 2, 8), (2, 4, 2, 3, 1, 1, 2, 8), (3, 2, 1, 2, 1, 2, 1, 7)]:
+        x0 = torch.randn(2, cin, *([size] * ndim), device="cuda", requires_grad=True)
+        w0 = torch.randn(cout, cin // groups, *([k] * ndim), device="cuda", requires_grad=True)
+        b0 = torch.randn(cout, device="cuda", requires_grad=True)
+        x1, w1, b1 = (t.detach().clone().requires_grad_() for t in (x0, w0, b0))
+        kw = dict(padding=p, stride=s, dilation=d, groups=groups)
+        y0 = fcp.fft_conv(x0, w0, bias=b0, **kw)
+        y1 = conv(x1, w1, bias=b1, **kw)
+        y0.sum().backward()
+        y1.sum().backward()
+        for a, r in ((y0, y1), (w0.grad, w1.grad), (b0.grad, b1.grad), (x0.grad, x1.grad)):
+            e = (a - r).abs()
+            assert e.mean().item() < 5e-5 and e.max().item() < 1e-4
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_backward_matches_torch_transposed_conv(ndim):
+    """reference tests/test_functional_transpose.py:73-124."""
+    torch.manual_seed(10)
+    conv = getattr(F, f"conv_transpose{ndim}d")
+    for cin, cout, groups, k, p, op, s, d, size in [(2, 2, 1, 2, 0, 0, 1, 1, 7), (3, 3, 3, 3, 1, 1, 3, 3, 8), (2, 4, 2, 3, 1, 0, 2, 2, 8), (2, 3, 1, 2, 1, 1, 2, 2, 7)]:
+        x0 = torch.randn(2, cin, *([size] * ndim), device="cuda", requires_grad=True)
+        w0 = torch.randn(cin, cout // groups, *([k] * ndim), device="cuda", requires_grad=True)
+        b0 = torch.randn(cout, device="cuda", requires_grad=True)
+        x1, w1, b1 = (t.detach().clone().requires_grad_() for t in (x0, w0, b0))
+        kw = dict(padding=p, output_padding=op, stride=s, dilation=d, groups=groups)
+        y0 = fcp.fft_conv_transpose(x0, w0, bias=b0, **kw)
+        y1 = conv(x1, w1, bias=b1, **kw)
+        y0.sum().backward()
+        y1.sum().backward()
+        for a, r in ((y0, y1), (w0.grad, w1.grad), (b0.grad, b1.grad), (x0.grad, x1.grad)):
+            e = (a - r).abs()
+            assert e.mean().item() < 5e-5 and e.max().item() < 1e-4
+
+
+def test_module_backward_trains():
+    torch.manual_seed(11)
+    m = fcp.FFTConv2d(3, 4, 5, padding=2, padding_mode="reflect").cuda()
+    r = torch.nn.Conv2d(3, 4, 5, padding=2, padding_mode="reflect").cuda()
+    r.load_state_dict(m.state_dict())
+    x = torch.randn(2, 3, 16, 16, device="cuda")
+    m(x).square().mean().backward()
+    r(x).square().mean().backward()
+    assert rel_err(m.weight.grad.cpu().numpy(), r.weight.grad.cpu().numpy()) < TOL
+    assert rel_err(m.bias.grad.cpu().numpy(), r.bias.grad.cpu().numpy()) < TOL
