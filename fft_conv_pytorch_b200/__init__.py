@@ -6,6 +6,7 @@ See DESIGN.md for the architecture and INTEGRATION.md for the C ABI.
 """
 from . import functional, nn
 from .functional import complex_matmul, fft_conv, fft_conv_transpose
+from .graphs import GraphedConv, graphed
 from .nn import (
     FFTConv1d,
     FFTConv2d,
@@ -18,6 +19,6 @@ from .utils import to_ntuple
 
 __version__ = "0.1.0"
 __all__ = [
-    "functional", "nn", "fft_conv", "fft_conv_transpose", "complex_matmul", "to_ntuple",
+    "functional", "nn", "fft_conv", "fft_conv_transpose", "complex_matmul", "to_ntuple", "graphed", "GraphedConv",
     "FFTConv1d", "FFTConv2d", "FFTConv3d", "FFTConvTranspose1d", "FFTConvTranspose2d", "FFTConvTranspose3d",
 ]

@@ -13,6 +13,9 @@ FC_MAX_ND = 3
 PAD_MODES = {"constant": 0, "zeros": 0, "reflect": 1, "replicate": 2, "circular": 3}
 FC_FLAG_NO_FUSED = 1
 FC_FLAG_NO_POLYPHASE = 2
+FC_FLAG_NO_FAST_R2C = 4
+FC_FLAG_NO_FAST_C2R = 8
+FC_FLAG_NO_FUSED_MID = 16
 
 _I3 = ctypes.c_int32 * FC_MAX_ND
 

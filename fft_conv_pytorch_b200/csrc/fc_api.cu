@@ -8,10 +8,8 @@
 #include <vector>
 
 #include "fc_kernels.cuh"
-#include "fc_plan.h"
-#ifndef FC_CPU_EMUL
 #include "fc_fused.cuh"
-#endif
+#include "fc_plan.h"
 
 #ifdef FC_CPU_EMUL
 #define FC_LAUNCH(kfn, grid, block, smem, stream, arg) fc_emul_launch(grid, block, smem, [=]() { kfn(arg); })
@@ -66,7 +64,15 @@ void init_once() {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
       g_num_sms = sms;
-    fc_fused_init();
+    cudaFuncSetAttribute(fc_fast_r2c_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(fc_fast_r2c_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(fc_fast_c2r_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(fc_fast_c2r_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(fc_fused_axis_kernel<256, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(fc_fused_axis_kernel<256, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(fc_fused_axis_kernel<512, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(fc_fused_axis_kernel<512, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(fc_fused_axis_kernel<1024, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaGetLastError();
 #endif
   });
@@ -148,6 +154,102 @@ int launch_contract(const float2* X, const float2* K, float2* Y, int64_t bins, i
   return check_cuda("contraction launch");
 }
 
+int launch_fast_r2c(const fc_pass& p, const void* in, void* out, const float2* tw, cudaStream_t st) {
+  fc_fast_r2c_args a;
+  a.p = p;
+  a.x = (const float*)in;
+  a.out = (float2*)out;
+  a.tw = tw;
+  const size_t smem = ((size_t)FC_FAST_WARPS * p.M + (size_t)(p.M + 1) * (FC_FAST_TR + 1)) * sizeof(float2);
+  int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(smem + 1024);
+  int64_t grid = (int64_t)g_num_sms * (per_sm < 1 ? 1 : per_sm);
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  if (grid < 1) return FC_OK;
+  dim3 g((unsigned)grid), b(FC_FAST_WARPS * 32);
+  if (p.M == 256) {
+    auto k = fc_fast_r2c_kernel<256>;
+    FC_LAUNCH(k, g, b, smem, st, a);
+  } else {
+    auto k = fc_fast_r2c_kernel<512>;
+    FC_LAUNCH(k, g, b, smem, st, a);
+  }
+  rec_mark();
+  return check_cuda("fast r2c launch");
+}
+
+int launch_fast_c2r(const fc_pass& p, const void* in, void* out, const float2* tw, const float* bias, cudaStream_t st) {
+  fc_fast_c2r_args a;
+  a.p = p;
+  a.p.has_bias = bias ? 1 : 0;
+  a.in = (const float2*)in;
+  a.out = (float*)out;
+  a.tw = tw;
+  a.bias = bias;
+  const size_t smem = ((size_t)FC_FAST_WARPS * p.M + (size_t)(p.M + 1) * (FC_FAST_TR + 1)) * sizeof(float2);
+  int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(smem + 1024);
+  int64_t grid = (int64_t)g_num_sms * (per_sm < 1 ? 1 : per_sm);
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  if (grid < 1) return FC_OK;
+  dim3 g((unsigned)grid), b(FC_FAST_WARPS * 32);
+  if (p.M == 256) {
+    auto k = fc_fast_c2r_kernel<256>;
+    FC_LAUNCH(k, g, b, smem, st, a);
+  } else {
+    auto k = fc_fast_c2r_kernel<512>;
+    FC_LAUNCH(k, g, b, smem, st, a);
+  }
+  rec_mark();
+  return check_cuda("fast c2r launch");
+}
+
+int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, const float2* kspec, void* out, const float2* tw, cudaStream_t st) {
+  const fc_problem& P = pl->prob;
+  fc_fused_args a;
+  a.xin = (const float2*)in;
+  a.kspec = kspec;
+  a.yout = (float2*)out;
+  a.tw = tw;
+  a.tw_len = pl->tw_len;
+  a.B = P.batch;
+  a.Cin = P.cin;
+  a.Cout = P.cout;
+  a.G = P.groups;
+  a.Ig = P.cin / P.groups;
+  a.Og = P.cout / P.groups;
+  a.n_in = f.n_in;
+  a.n_out = f.n_out;
+  a.nbs = (P.batch + f.nb - 1) / f.nb;
+  a.R = f.R;
+  a.n_units = (int64_t)P.groups * f.R * a.nbs;
+  a.imap = f.imap;
+  a.omap = f.omap;
+  const size_t smem = (size_t)f.nb * f.ci * f.N * sizeof(float2);
+  int64_t grid = a.n_units;
+  const int64_t cap = (int64_t)g_num_sms * 16;
+  if (grid > cap) grid = cap;
+  dim3 g((unsigned)grid), b(FC_FAST_WARPS * 32);
+  if (f.N == 256 && f.nb == 2) {
+    auto k = fc_fused_axis_kernel<256, 8, 2>;
+    FC_LAUNCH(k, g, b, smem, st, a);
+  } else if (f.N == 256) {
+    auto k = fc_fused_axis_kernel<256, 8, 1>;
+    FC_LAUNCH(k, g, b, smem, st, a);
+  } else if (f.N == 512 && f.nb == 2) {
+    auto k = fc_fused_axis_kernel<512, 8, 2>;
+    FC_LAUNCH(k, g, b, smem, st, a);
+  } else if (f.N == 512) {
+    auto k = fc_fused_axis_kernel<512, 8, 1>;
+    FC_LAUNCH(k, g, b, smem, st, a);
+  } else if (f.N == 1024 && f.nb == 1) {
+    auto k = fc_fused_axis_kernel<1024, 8, 1>;
+    FC_LAUNCH(k, g, b, smem, st, a);
+  } else {
+    return set_err(FC_EUNSUPPORTED, "no fused kernel instantiation for this shape");
+  }
+  rec_mark();
+  return check_cuda("fused axis launch");
+}
+
 // Resolve a buffer id of a step to a pointer.
 struct Bufs {
   const void* user_in;
@@ -191,9 +293,6 @@ int fc_plan_create(fc_plan** out, const fc_problem* problem) {
     delete pl;
     return set_err(rc, msg);
   }
-#ifndef FC_CPU_EMUL
-  fc_fused_plan(pl);
-#endif
   *out = pl;
   return FC_OK;
 }
@@ -263,16 +362,35 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
             void* stream) {
   if (!plan || !d_const || !d_x || !d_kspec || !d_y || !d_ws) return set_err(FC_ENULL, "fc_conv: NULL argument");
   init_once();
-#ifndef FC_CPU_EMUL
-  if (plan->fused.enabled) return fc_fused_conv(plan, (const float2*)d_const, d_x, (const float2*)d_kspec, d_bias, d_y, d_ws, (cudaStream_t)stream);
-#endif
-  float* xspec = (float*)((char*)d_ws + plan->off_xspec);
-  float* yspec = (float*)((char*)d_ws + plan->off_yspec);
-  int rc = fc_signal_spectrum(plan, d_const, d_x, xspec, d_ws, stream);
-  if (rc) return rc;
-  rc = fc_contract(plan, xspec, d_kspec, yspec, stream);
-  if (rc) return rc;
-  return fc_inverse(plan, d_const, yspec, d_bias, d_y, d_ws, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float2* tw = (const float2*)d_const;
+  char* ws = (char*)d_ws;
+  void* xspec = ws + plan->off_xspec;
+  void* yspec = ws + plan->off_yspec;
+  for (const fc_launch& L : plan->prog) {
+    Bufs b{d_x, L.spec_is_y ? yspec : xspec, ws + plan->off_sA, ws + plan->off_sB, d_y};
+    int rc;
+    switch (L.type) {
+      case FC_L_PASS:
+        rc = launch_pass(plan, L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, d_bias, st);
+        break;
+      case FC_L_FAST_R2C:
+        rc = launch_fast_r2c(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, st);
+        break;
+      case FC_L_FAST_C2R:
+        rc = launch_fast_c2r(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, d_bias, st);
+        break;
+      case FC_L_CONTRACT: {
+        const fc_contract_desc& c = plan->contract;
+        rc = launch_contract((const float2*)xspec, (const float2*)d_kspec, (float2*)yspec, c.bins, c.batch, c.cin, c.cout, c.groups, st);
+      } break;
+      default:
+        rc = launch_fused(plan, L.fused, buf_ptr(b, L.src), (const float2*)d_kspec, buf_ptr(b, L.dst), tw, st);
+        break;
+    }
+    if (rc) return rc;
+  }
+  return FC_OK;
 }
 
 int fc_conv_host(const fc_plan* plan, const void* d_const, const float* h_x, float* d_x_stage, const float* d_kspec, const float* d_bias,
@@ -295,6 +413,7 @@ int fc_conv_profiled(const fc_plan* plan, const void* d_const, const float* d_x,
   if (!ms_out || !n_out) return set_err(FC_ENULL, "fc_conv_profiled: NULL argument");
   *n_out = 0;
 #ifdef FC_CPU_EMUL
+  (void)max_n;
   return fc_conv(plan, d_const, d_x, d_kspec, d_bias, d_y, d_ws, stream);
 #else
   Recorder rec;
@@ -319,36 +438,12 @@ int fc_conv_profiled(const fc_plan* plan, const void* d_const, const float* d_x,
 
 int fc_plan_launch_info(const fc_plan* plan, int i, char* name, size_t namelen, int64_t* algo_bytes) {
   if (!plan || !name || !namelen || !algo_bytes) return set_err(FC_ENULL, "fc_plan_launch_info: NULL argument");
-  std::string nm;
-  int64_t bytes = 0;
-  auto pass_info = [&](const fc_pass& p, const char* prefix) {
-    static const char* kn[] = {"r2c", "c2c_fwd", "c2c_inv", "c2r"};
-    nm = std::string(prefix) + kn[p.kind] + "_N" + std::to_string(p.N);
-    const int64_t lines = p.n_outer * p.R;
-    const int64_t in_el = (p.kind == FC_R2C) ? 4 : 8, out_el = (p.kind == FC_C2R) ? 4 : 8;
-    bytes = lines * ((int64_t)p.n_in * in_el + (int64_t)p.n_out * out_el);
-  };
-#ifndef FC_CPU_EMUL
-  if (plan->fused.enabled) {
-    int rc = fc_fused_launch_info(plan, i, &nm, &bytes);
-    if (rc) return set_err(FC_EINVAL, "fc_plan_launch_info: index out of range");
-  } else
-#endif
-  {
-    const int nf = (int)plan->sig_fwd.size(), ni = (int)plan->inv.size();
-    if (i < 0 || i >= nf + 1 + ni) return set_err(FC_EINVAL, "fc_plan_launch_info: index out of range");
-    if (i < nf)
-      pass_info(plan->sig_fwd[i].pass, "fwd_");
-    else if (i == nf) {
-      nm = "contract";
-      bytes = plan->info.algo_bytes_s3;
-    } else
-      pass_info(plan->inv[i - nf - 1].pass, "inv_");
-  }
-  size_t n = nm.size() < namelen - 1 ? nm.size() : namelen - 1;
-  std::memcpy(name, nm.data(), n);
+  if (i < 0 || i >= (int)plan->prog.size()) return set_err(FC_EINVAL, "fc_plan_launch_info: index out of range");
+  const fc_launch& L = plan->prog[i];
+  size_t n = L.name.size() < namelen - 1 ? L.name.size() : namelen - 1;
+  std::memcpy(name, L.name.data(), n);
   name[n] = 0;
-  *algo_bytes = bytes;
+  *algo_bytes = L.bytes;
   return FC_OK;
 }
 

@@ -421,7 +421,6 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   const fc_problem& P = *prob;
   pl->prob = P;
   std::memset(&pl->info, 0, sizeof(pl->info));
-  std::memset(&pl->fused, 0, sizeof(pl->fused));
   const int nd = P.ndim;
   if (nd < 1 || nd > FC_MAX_ND) return fail(FC_EUNSUPPORTED, "ndim must be 1, 2 or 3 (got " + std::to_string(nd) + ")");
   if (P.batch < 1 || P.cin < 1 || P.cout < 1 || P.groups < 1) return fail(FC_EINVAL, "batch, channels and groups must be positive");
@@ -621,7 +620,122 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   I.algo_bytes_s2 = 4 * (int64_t)P.cout * Ig * k_vol + I.kspec_bytes;
   I.algo_bytes_s3 = I.xspec_bytes + I.kspec_bytes + I.yspec_bytes;
   I.algo_bytes_s4 = I.yspec_bytes + 4 * I.out_elems + 4 * (int64_t)P.cout;
+  fc_plan_build_program(pl);
   return FC_OK;
+}
+
+namespace {
+
+const char* kKindName[] = {"r2c", "c2c_fwd", "c2c_inv", "c2r"};
+
+int64_t pass_bytes(const fc_pass& p) {
+  const int64_t lines = p.n_outer * p.R;
+  const int64_t in_el = (p.kind == FC_R2C) ? 4 : 8, out_el = (p.kind == FC_C2R) ? 4 : 8;
+  return lines * ((int64_t)p.n_in * in_el + (int64_t)p.n_out * out_el);
+}
+
+bool fast_line_len(int M) { return M == 256 || M == 512; }
+
+// Re-tile a pass for the transposing fast kernels (16 lines per tile, tiles never straddle an outer item).
+void retile16(fc_pass& p) {
+  p.T = 16;
+  p.log2T = 4;
+  p.flat = 0;
+  p.tiles_per_outer = (p.R + 15) / 16;
+  p.n_tiles = p.tiles_per_outer * p.n_outer;
+}
+
+}  // namespace
+
+void fc_plan_build_program(fc_plan* pl) {
+  const fc_problem& P = pl->prob;
+  const int flags = P.flags;
+  const bool allow = !(flags & FC_FLAG_NO_FUSED);
+  pl->prog.clear();
+  const int nf = (int)pl->sig_fwd.size(), ni = (int)pl->inv.size();
+  const int Ig = P.cin / P.groups, Og = P.cout / P.groups;
+
+  // fused middle: last forward pass + contraction + first inverse pass
+  bool fuse_mid = allow && !(flags & FC_FLAG_NO_FUSED_MID) && nf >= 2 && ni >= 2;
+  if (fuse_mid) {
+    const fc_pass& f = pl->sig_fwd[nf - 1].pass;
+    const fc_pass& b = pl->inv[0].pass;
+    fuse_mid = f.kind == FC_C2C_FWD && b.kind == FC_C2C_INV && !f.in_rfast && !f.out_rfast && !b.in_rfast && !b.out_rfast && f.N == b.N &&
+               (f.N == 256 || f.N == 512 || f.N == 1024) && Ig <= 8 && Og <= 8 && f.R == b.R && f.in_es == 1 && b.out_es == 1;
+  }
+  for (int i = 0; i < nf; ++i) {
+    if (fuse_mid && i == nf - 1) break;
+    fc_launch L;
+    L.type = FC_L_PASS;
+    L.pass = pl->sig_fwd[i].pass;
+    L.src = pl->sig_fwd[i].src;
+    L.dst = pl->sig_fwd[i].dst;
+    L.spec_is_y = 0;
+    std::memset(&L.fused, 0, sizeof(L.fused));
+    const fc_pass& p = L.pass;
+    if (i == 0 && allow && !(flags & FC_FLAG_NO_FAST_R2C) && p.kind == FC_R2C && !p.in_rfast && p.out_rfast && !p.twiddle && fast_line_len(p.M) &&
+        p.imap.mode == FC_PAD_CONSTANT && p.imap.pad == 0 && p.imap.up == 1 && p.imap.sub == 1 && p.imap.ext == p.imap.L && !(p.in_rs & 1) &&
+        !(p.o_sA & 1) && !(p.o_sB & 1) && !(p.o_sC & 1) && p.scale == 1.f && !p.conj_out && p.pos_n == 1 && p.pos_r == 0) {
+      L.type = FC_L_FAST_R2C;
+      retile16(L.pass);
+    }
+    L.name = std::string(L.type == FC_L_FAST_R2C ? "fast_r2c_N" : "fwd_") + (L.type == FC_L_FAST_R2C ? "" : kKindName[p.kind]) +
+             (L.type == FC_L_FAST_R2C ? "" : "_N") + std::to_string(p.N);
+    L.bytes = pass_bytes(p);
+    pl->prog.push_back(L);
+  }
+  if (fuse_mid) {
+    const fc_step& fs = pl->sig_fwd[nf - 1];
+    const fc_step& bs = pl->inv[0];
+    fc_launch L;
+    L.type = FC_L_FUSED;
+    L.pass = fs.pass;
+    L.src = fs.src;
+    L.dst = FC_BUF_SPEC;  // the product-spectrum buffer is free in the fused program; fs.src and bs.dst may alias
+    L.spec_is_y = 1;
+    L.fused.N = fs.pass.N;
+    L.fused.n_in = fs.pass.n_in;
+    L.fused.n_out = bs.pass.n_out;
+    L.fused.nb = (P.batch >= 2 && fs.pass.N <= 512) ? 2 : 1;
+    L.fused.ci = 8;
+    L.fused.R = fs.pass.R;
+    L.fused.imap = fs.pass.imap;
+    L.fused.omap = bs.pass.omap;
+    L.name = "fused_axis_N" + std::to_string(fs.pass.N);
+    L.bytes = 8 * ((int64_t)P.batch * P.cin * fs.pass.R * fs.pass.n_in + (int64_t)P.cout * Ig * fs.pass.R * fs.pass.N +
+                   (int64_t)P.batch * P.cout * bs.pass.R * bs.pass.n_out);
+    pl->prog.push_back(L);
+  } else {
+    fc_launch L;
+    L.type = FC_L_CONTRACT;
+    std::memset(&L.pass, 0, sizeof(L.pass));
+    std::memset(&L.fused, 0, sizeof(L.fused));
+    L.src = L.dst = FC_BUF_SPEC;
+    L.spec_is_y = 0;
+    L.name = "contract";
+    L.bytes = pl->info.algo_bytes_s3;
+    pl->prog.push_back(L);
+  }
+  for (int i = fuse_mid ? 1 : 0; i < ni; ++i) {
+    fc_launch L;
+    L.type = FC_L_PASS;
+    L.pass = pl->inv[i].pass;
+    L.src = (fuse_mid && i == 1) ? FC_BUF_SPEC : pl->inv[i].src;
+    L.dst = pl->inv[i].dst;
+    L.spec_is_y = 1;
+    std::memset(&L.fused, 0, sizeof(L.fused));
+    const fc_pass& p = L.pass;
+    if (i == ni - 1 && allow && !(flags & FC_FLAG_NO_FAST_C2R) && p.kind == FC_C2R && p.in_rfast && !p.out_rfast && !p.twiddle && fast_line_len(p.M) &&
+        p.pos_n == 1 && p.pos_r == 0 && p.out_es == 1) {
+      L.type = FC_L_FAST_C2R;
+      retile16(L.pass);
+    }
+    L.name = (L.type == FC_L_FAST_C2R ? std::string("fast_c2r_N") : std::string("inv_") + kKindName[p.kind] + "_N") + std::to_string(p.N);
+    L.bytes = pass_bytes(p);
+    pl->prog.push_back(L);
+  }
+  pl->info.n_launches = (int)pl->prog.size();
+  pl->info.fused = fuse_mid ? 1 : 0;
 }
 
 std::string fc_plan_to_string(const fc_plan* pl) {
@@ -652,6 +766,7 @@ std::string fc_plan_to_string(const fc_plan* pl) {
   dump("sig", pl->sig_fwd);
   dump("ker", pl->ker_fwd);
   dump("inv", pl->inv);
-  os << "  fused=" << pl->fused.enabled << " workspace=" << pl->info.workspace_bytes << " launches=" << pl->info.n_launches << "\n";
+  for (const fc_launch& L : pl->prog) os << "  launch " << L.name << " type=" << L.type << " bytes=" << L.bytes << "\n";
+  os << "  fused=" << pl->info.fused << " workspace=" << pl->info.workspace_bytes << " launches=" << pl->info.n_launches << "\n";
   return os.str();
 }

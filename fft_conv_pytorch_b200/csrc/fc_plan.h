@@ -21,16 +21,29 @@ struct fc_step {
   int dst;
 };
 
+// One kernel launch of fc_conv.
+enum { FC_L_PASS = 0, FC_L_FAST_R2C = 1, FC_L_FAST_C2R = 2, FC_L_CONTRACT = 3, FC_L_FUSED = 4 };
+
 // Geometry of the fused "last forward axis -> contraction -> first inverse axis" kernel (fc_fused.cuh).
 struct fc_fused_desc {
-  int32_t enabled;
-  int32_t N;        // transform length of the fused axis
-  int32_t n_in;     // stored input elements per line
-  int32_t n_out;    // stored output elements per line
-  int32_t nb;       // batches per CTA
-  int32_t lines;    // lines (bins of the other axes) per (batch, channel)
+  int32_t N;      // transform length of the fused axis
+  int32_t n_in;   // stored input elements per line
+  int32_t n_out;  // stored output elements per line
+  int32_t nb;     // batches per CTA
+  int32_t ci;     // channel bound of the instantiation
+  int64_t R;      // lines (bins of the other axes) per (batch, channel)
   fc_imap imap;
   fc_omap omap;
+};
+
+struct fc_launch {
+  int type;
+  fc_pass pass;  // FC_L_PASS / FC_L_FAST_*
+  fc_fused_desc fused;
+  int src, dst;  // FC_BUF_* (FC_BUF_SPEC as src of an inverse step = product spectrum; as dst of a forward step = signal spectrum)
+  int spec_is_y; // which spectrum buffer FC_BUF_SPEC means for this launch: 0 = xspec, 1 = yspec
+  std::string name;
+  int64_t bytes;  // algorithmic bytes: compulsory reads + writes of this launch
 };
 
 struct fc_axis {
@@ -54,11 +67,13 @@ struct fc_plan {
   fc_axis ax[FC_MAX_ND];
   std::vector<fc_step> sig_fwd, ker_fwd, inv;
   fc_contract_desc contract;
-  fc_fused_desc fused;
+  std::vector<fc_launch> prog;  // what fc_conv launches, in order
   int64_t off_xspec, off_yspec, off_sA, off_sB;
   int64_t scratch_bytes;
 };
 
 // Returns FC_OK or a negative code; msg receives the reason.
 int fc_plan_build(fc_plan* plan, const fc_problem* prob, std::string* msg);
+// Choose fast / fused kernels where they apply and lay out the launch program of fc_conv.
+void fc_plan_build_program(fc_plan* plan);
 std::string fc_plan_to_string(const fc_plan* plan);

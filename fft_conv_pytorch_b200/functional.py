@@ -15,6 +15,7 @@ Differences from the reference, all documented in DESIGN.md:
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 import weakref
 from collections import OrderedDict
@@ -35,6 +36,8 @@ _kspec_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
 _KSPEC_CACHE_MAX_BYTES = 64 << 30
 _kspec_cache_bytes = 0
 _launch_counter = 0  # kernels queued by this module (bench.py reports it)
+# FC_FLAG_* bits OR-ed into every plan (A/B timing of the specialised kernels: 1 = generic kernels only)
+_DEFAULT_FLAGS = int(os.environ.get("FFTCONV_B200_FLAGS", "0"))
 
 
 def launches() -> int:
@@ -81,6 +84,7 @@ def get_plan(
     flags: int = 0,
     threads: int = 0,
 ) -> _PlanEntry:
+    flags |= _DEFAULT_FLAGS
     key = (transposed, batch, cin, cout, groups, in_size, kernel_size, stride, padding, dilation, output_padding, padding_mode, flags, threads)
     with _lock:
         e = _plans.get(key)

@@ -72,8 +72,11 @@ typedef struct fc_problem {
 } fc_problem;
 
 enum {
-  FC_FLAG_NO_FUSED = 1, /* force the unfused pass pipeline (K1 / axis passes / K3 / K4) */
-  FC_FLAG_NO_POLYPHASE = 2 /* keep stride/dilation lattices dense (no gcd reduction) */
+  FC_FLAG_NO_FUSED = 1,     /* generic kernels only: K1 / axis passes / K3 / K4, nothing specialised or fused */
+  FC_FLAG_NO_POLYPHASE = 2, /* keep stride/dilation lattices dense (no gcd reduction) */
+  FC_FLAG_NO_FAST_R2C = 4,  /* the three below switch the specialised kernels off one by one (tests, A/B timing) */
+  FC_FLAG_NO_FAST_C2R = 8,
+  FC_FLAG_NO_FUSED_MID = 16
 };
 
 typedef struct fc_plan fc_plan; /* opaque */

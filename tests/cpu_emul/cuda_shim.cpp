@@ -9,8 +9,10 @@
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 char* fc_emul_smem = nullptr;
 static std::barrier<>* g_barrier = nullptr;
+static std::vector<std::unique_ptr<std::barrier<>>> g_warp_barriers;
 
 void __syncthreads() { g_barrier->arrive_and_wait(); }
+void __syncwarp() { g_warp_barriers[threadIdx.x / 32]->arrive_and_wait(); }
 
 void fc_emul_launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body) {
   const unsigned nt = block.x;
@@ -18,6 +20,11 @@ void fc_emul_launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bo
   fc_emul_smem = shared.data();
   std::barrier<> bar((std::ptrdiff_t)nt);
   g_barrier = &bar;
+  g_warp_barriers.clear();
+  for (unsigned wi = 0; wi < (nt + 31) / 32; ++wi) {
+    const unsigned lanes = (wi * 32 + 32 <= nt) ? 32 : nt - wi * 32;
+    g_warp_barriers.emplace_back(new std::barrier<>((std::ptrdiff_t)lanes));
+  }
   std::vector<std::thread> th;
   th.reserve(nt);
   for (unsigned t = 0; t < nt; ++t) {

@@ -15,6 +15,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __shared__ static
+#define __launch_bounds__(...)
 
 struct float2 {
   float x, y;
@@ -23,6 +24,7 @@ struct float4 {
   float x, y, z, w;
 };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
 struct dim3 {
   unsigned x, y, z;
@@ -32,6 +34,7 @@ struct dim3 {
 extern thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 extern char* fc_emul_smem;
 void __syncthreads();
+void __syncwarp();  // barrier over the 32 host threads standing in for one warp
 void fc_emul_launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body);
 
 #define FC_DYN_SMEM(name) float2* name = reinterpret_cast<float2*>(fc_emul_smem)

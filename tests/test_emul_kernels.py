@@ -94,3 +94,41 @@ def test_plan_shapes_follow_reference_formulas():
     p = emul.plan_for((8, 8, 512, 512), (8, 8, 65, 65))
     i = p.info
     assert abs((i.algo_bytes_s1 + i.algo_bytes_s3 + i.algo_bytes_s4) / 1e6 - 455.3) < 0.5
+
+
+# ------------------------------------------------------------------------------------ specialised kernels (fc_fused.cuh)
+_FAST_SHAPES = [
+    # x, w, kwargs -> transform sizes that select the warp-FFT kernels (last axis 512/1024, fused axis 256/512)
+    ((2, 2, 250, 500), (3, 2, 7, 9), {}),
+    ((3, 4, 130, 300), (4, 2, 5, 3), dict(groups=2, padding=(3, 0), stride=(2, 1))),
+    ((1, 2, 260, 600), (2, 2, 3, 3), dict(padding=(1, 1), padding_mode="reflect")),
+]
+
+
+@pytest.mark.parametrize("xs,ws,kw", _FAST_SHAPES)
+def test_fast_kernels_match_generic_and_oracle(xs, ws, kw):
+    from oracle import fftconv_oracle as O
+
+    rng = np.random.RandomState(11)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = rng.standard_normal(ws).astype(np.float32)
+    b = rng.standard_normal(ws[0]).astype(np.float32)
+    ref = O.fft_conv(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), **kw)
+    y_gen, p_gen = emul.conv(x, w, b, threads=256, flags=L.FC_FLAG_NO_FUSED, **kw)
+    y_fast, p_fast = emul.conv(x, w, b, threads=256, **kw)
+    assert p_gen.info.n_launches == 5 and "fast" not in p_gen.describe().split("launch", 1)[1]
+    assert "fused_axis" in p_fast.describe() or "fast_" in p_fast.describe()
+    assert rel_err(y_gen, ref) < 1e-5
+    assert rel_err(y_fast, ref) < 1e-5
+    assert not np.isnan(y_fast).any()
+
+
+def test_fast_kernels_one_at_a_time():
+    rng = np.random.RandomState(12)
+    x = rng.standard_normal((2, 2, 250, 500)).astype(np.float32)
+    w = rng.standard_normal((3, 2, 7, 9)).astype(np.float32)
+    y0, _ = emul.conv(x, w, None, threads=256, flags=L.FC_FLAG_NO_FUSED)
+    for fl in (L.FC_FLAG_NO_FAST_C2R | L.FC_FLAG_NO_FUSED_MID, L.FC_FLAG_NO_FAST_R2C | L.FC_FLAG_NO_FUSED_MID,
+               L.FC_FLAG_NO_FAST_R2C | L.FC_FLAG_NO_FAST_C2R):
+        y1, p = emul.conv(x, w, None, threads=256, flags=fl)
+        assert rel_err(y1, y0) < 2e-6, fl
