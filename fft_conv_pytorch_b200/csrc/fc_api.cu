@@ -53,6 +53,22 @@ int check_cuda(const char* what) {
 const int kMaxSmem = 200 * 1024;
 int g_num_sms = 148;
 
+// every instantiation of the fused kernel: (N, NB, warps, plain)
+#define FC_FUSED_ALL(X) \
+  X(256, 2, 8, true) X(256, 2, 8, false) X(256, 1, 8, true) X(256, 1, 8, false) \
+  X(512, 2, 8, true) X(512, 2, 8, false) X(512, 1, 8, true) X(512, 1, 8, false) \
+  X(512, 2, 4, true) X(512, 1, 4, true) X(256, 2, 4, true) \
+  X(1024, 1, 8, true) X(1024, 1, 8, false)
+
+void fused_set_attr() {
+#ifndef FC_CPU_EMUL
+#define FC_FUSED_ATTR(NN, NBB, WW, PL) \
+  cudaFuncSetAttribute(fc_fused_axis_kernel<NN, 8, NBB, WW, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  FC_FUSED_ALL(FC_FUSED_ATTR)
+#undef FC_FUSED_ATTR
+#endif
+}
+
 void init_once() {
   static std::once_flag flag;
   std::call_once(flag, []() {
@@ -68,11 +84,7 @@ void init_once() {
     cudaFuncSetAttribute(fc_fast_r2c_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(fc_fast_c2r_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(fc_fast_c2r_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(fc_fused_axis_kernel<256, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(fc_fused_axis_kernel<256, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(fc_fused_axis_kernel<512, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(fc_fused_axis_kernel<512, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(fc_fused_axis_kernel<1024, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    fused_set_attr();
     cudaGetLastError();
 #endif
   });
@@ -160,7 +172,7 @@ int launch_fast_r2c(const fc_pass& p, const void* in, void* out, const float2* t
   a.x = (const float*)in;
   a.out = (float2*)out;
   a.tw = tw;
-  const size_t smem = ((size_t)FC_FAST_WARPS * p.M + (size_t)(p.M + 1) * (FC_FAST_TR + 1)) * sizeof(float2);
+  const size_t smem = ((size_t)FC_FAST_TR * p.M + (size_t)(p.M + 1) * (FC_FAST_TR + 1)) * sizeof(float2);
   int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(smem + 1024);
   int64_t grid = (int64_t)g_num_sms * (per_sm < 1 ? 1 : per_sm);
   if (grid > p.n_tiles) grid = p.n_tiles;
@@ -185,7 +197,7 @@ int launch_fast_c2r(const fc_pass& p, const void* in, void* out, const float2* t
   a.out = (float*)out;
   a.tw = tw;
   a.bias = bias;
-  const size_t smem = ((size_t)FC_FAST_WARPS * p.M + (size_t)(p.M + 1) * (FC_FAST_TR + 1)) * sizeof(float2);
+  const size_t smem = ((size_t)FC_FAST_TR * p.M + (size_t)(p.M + 1) * (FC_FAST_TR + 1)) * sizeof(float2);
   int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(smem + 1024);
   int64_t grid = (int64_t)g_num_sms * (per_sm < 1 ? 1 : per_sm);
   if (grid > p.n_tiles) grid = p.n_tiles;
@@ -224,28 +236,27 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
   a.imap = f.imap;
   a.omap = f.omap;
   const size_t smem = (size_t)f.nb * f.ci * f.N * sizeof(float2);
+  {  // distance (in units) to the CTA of the next wave on the same SM: what this CTA prefetches into L2
+    int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(smem + 1024);
+    const int64_t reg_lim = f.warps <= 4 ? 3 : 2;  // launch bounds
+    if (per_sm > reg_lim) per_sm = reg_lim;
+    if (per_sm < 1) per_sm = 1;
+    a.prefetch_dist = (int)(g_num_sms * per_sm);
+  }
   int64_t grid = a.n_units;
   const int64_t cap = (int64_t)g_num_sms * 16;
   if (grid > cap) grid = cap;
-  dim3 g((unsigned)grid), b(FC_FAST_WARPS * 32);
-  if (f.N == 256 && f.nb == 2) {
-    auto k = fc_fused_axis_kernel<256, 8, 2>;
-    FC_LAUNCH(k, g, b, smem, st, a);
-  } else if (f.N == 256) {
-    auto k = fc_fused_axis_kernel<256, 8, 1>;
-    FC_LAUNCH(k, g, b, smem, st, a);
-  } else if (f.N == 512 && f.nb == 2) {
-    auto k = fc_fused_axis_kernel<512, 8, 2>;
-    FC_LAUNCH(k, g, b, smem, st, a);
-  } else if (f.N == 512) {
-    auto k = fc_fused_axis_kernel<512, 8, 1>;
-    FC_LAUNCH(k, g, b, smem, st, a);
-  } else if (f.N == 1024 && f.nb == 1) {
-    auto k = fc_fused_axis_kernel<1024, 8, 1>;
-    FC_LAUNCH(k, g, b, smem, st, a);
-  } else {
-    return set_err(FC_EUNSUPPORTED, "no fused kernel instantiation for this shape");
+  dim3 g((unsigned)grid), b((unsigned)f.warps * 32);
+  bool ok = false;
+#define FC_FUSED_CASE(NN, NBB, WW, PL)                                   \
+  if (!ok && f.N == NN && f.nb == NBB && f.warps == WW && (f.plain != 0) == PL) { \
+    auto k = fc_fused_axis_kernel<NN, 8, NBB, WW, PL>;                   \
+    FC_LAUNCH(k, g, b, smem, st, a);                                     \
+    ok = true;                                                           \
   }
+  FC_FUSED_ALL(FC_FUSED_CASE)
+#undef FC_FUSED_CASE
+  if (!ok) return set_err(FC_EUNSUPPORTED, "no fused kernel instantiation for this shape");
   rec_mark();
   return check_cuda("fused axis launch");
 }

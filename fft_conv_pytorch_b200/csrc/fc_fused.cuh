@@ -1,9 +1,11 @@
 // fc_fused.cuh — specialised sm_100a kernels for the hot shapes (checked against the generic fc_kernels.cuh).
 //
-// All three use the same register-resident warp FFT: one warp owns one line of M complex points, each lane keeps
-// E = M/32 points in registers in the "lane + 32q" layout (which is both the coalesced HBM layout and the input
-// layout of every Stockham stage), and consecutive radix-8/4 stages exchange data through a warp-private,
-// XOR-swizzled shared-memory line with __syncwarp only — no block-wide barrier inside a transform.
+// All three use the same register-resident warp FFT: one warp owns NL lines of M complex points at a time, each
+// lane keeps E = M/32 points per line in registers in the "lane + 32q" layout (which is both the coalesced HBM
+// layout and the input layout of every Stockham stage), and consecutive radix-8/4 stages exchange data through
+// warp-private, XOR-swizzled shared-memory lines with __syncwarp only — no block-wide barrier inside a
+// transform. Processing NL = 2 lines per warp shares the twiddle factors and the swizzled addresses between the
+// lines and doubles the instruction-level parallelism of a warp.
 //
 //   fc_fast_r2c_kernel   K1: coalesced real rows -> R2C -> half spectrum stored transposed ([bin][row], 128-byte
 //                        segments), so that the next axis is contiguous
@@ -17,6 +19,13 @@
 
 #define FC_SYNCWARP() __syncwarp()
 
+#ifdef FC_CPU_EMUL
+FC_DEV void fc_prefetch_l2(const void*) {}
+#else
+// Pull one 128-byte line into L2 ahead of the CTA that will read it (no register is tied up).
+FC_DEV void fc_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
 // Swizzle of a warp's exchange line. For the three access patterns of the stages (16 consecutive points;
 // stride-8 writes of the first stage; "8 consecutive, jump 64" writes of the second stage) the 16 lanes of a half
 // warp touch 16 distinct 8-byte bank pairs.
@@ -25,33 +34,48 @@ FC_DEV int fc_swz2(int p) {
   return p ^ ((h & 7) | (((h >> 2) & 1) << 3));
 }
 
-// One radix-R stage on registers. v[t + NBF*r] = input r of butterfly t (= element lane + 32*(t + NBF*r)).
-template <int M, int R, int Ns>
-FC_DEV void fc_wstage(float2 (&v)[M / 32], const float2* tw, int tw_len, int lane) {
+// Powers w[1..R-1] of a twiddle factor with a shallow dependency tree.
+template <int R>
+FC_DEV void fc_twiddle_powers(float2 w1, float2 (&w)[R]) {
+  w[1] = w1;
+  if (R > 2) w[2] = fc_mul(w1, w1);
+  if (R > 3) w[3] = fc_mul(w[2], w1);
+  if (R > 4) {
+    w[4] = fc_mul(w[2], w[2]);
+    w[5] = fc_mul(w[4], w1);
+    w[6] = fc_mul(w[4], w[2]);
+    w[7] = fc_mul(w[4], w[3]);
+  }
+}
+
+// One radix-R stage on registers, NL lines at once. v[l][t + NBF*r] = input r of butterfly t of line l
+// (= element lane + 32*(t + NBF*r)).
+template <int M, int NL, int R, int Ns>
+FC_DEV void fc_wstage(float2 (&v)[NL][M / 32], const float2* tw, int tw_len, int lane) {
   constexpr int E = M / 32, NBF = E / R;
+  float2 w[R];
+  if (Ns > 1 && Ns <= 32) fc_twiddle_powers<R>(__ldg(tw + (lane & (Ns - 1)) * (tw_len / (Ns * R))), w);  // same for every t
 #pragma unroll
   for (int t = 0; t < NBF; ++t) {
-    float2 a[R];
+    if (Ns > 32) fc_twiddle_powers<R>(__ldg(tw + ((lane + 32 * t) & (Ns - 1)) * (tw_len / (Ns * R))), w);
 #pragma unroll
-    for (int r = 0; r < R; ++r) a[r] = v[t + NBF * r];
-    if (Ns > 1) {
-      const int k = (lane + 32 * t) & (Ns - 1);
-      const float2 w1 = __ldg(tw + k * (tw_len / (Ns * R)));
-      float2 w = w1;
+    for (int l = 0; l < NL; ++l) {
+      float2 a[R];
 #pragma unroll
-      for (int r = 1; r < R; ++r) {
-        a[r] = fc_mul(a[r], w);
-        if (r + 1 < R) w = fc_mul(w, w1);
+      for (int r = 0; r < R; ++r) a[r] = v[l][t + NBF * r];
+      if (Ns > 1) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) a[r] = fc_mul(a[r], w[r]);
       }
-    }
-    fc_butterfly<R>(a);
+      fc_butterfly<R>(a);
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[t + NBF * r] = a[r];
+      for (int r = 0; r < R; ++r) v[l][t + NBF * r] = a[r];
+    }
   }
 }
 
 // Per-lane swizzled offsets of the exchange patterns, computed once per kernel (the XOR swizzle makes them
-// non-affine in the lane id, so evaluating fc_swz2 at every access would cost more than the butterflies):
+// non-affine in the lane id):
 //   rd[j]  lane + 32q layout, q % 4 == j : element offset = rd[j] + 32*q                  (all stages read this way)
 //   w1[r]  outputs of the (R=8, Ns=1) stage: 8*lane + r              (+ 256 per extra butterfly t)
 //   w2[r]  outputs of the (R=8, Ns=8) stage: 64*(lane>>3) + (lane&7) + 8r  (+ 256 per extra butterfly t)
@@ -72,90 +96,82 @@ struct fc_wofs {
   }
 };
 
-template <int M>
-FC_DEV void fc_wread(float2 (&v)[M / 32], const float2* line, const fc_wofs& o) {
+// Line l of a warp lives at line0 + l*LS.
+template <int M, int NL, int LS>
+FC_DEV void fc_wread(float2 (&v)[NL][M / 32], const float2* line0, const fc_wofs& o) {
 #pragma unroll
-  for (int q = 0; q < M / 32; ++q) v[q] = line[o.rd[q & 3] + 32 * q];
+  for (int l = 0; l < NL; ++l)
+#pragma unroll
+    for (int q = 0; q < M / 32; ++q) v[l][q] = line0[l * LS + o.rd[q & 3] + 32 * q];
 }
-template <int M>
-FC_DEV void fc_wwrite(const float2 (&v)[M / 32], float2* line, const fc_wofs& o) {
+template <int M, int NL, int LS>
+FC_DEV void fc_wwrite(const float2 (&v)[NL][M / 32], float2* line0, const fc_wofs& o) {
 #pragma unroll
-  for (int q = 0; q < M / 32; ++q) line[o.rd[q & 3] + 32 * q] = v[q];
+  for (int l = 0; l < NL; ++l)
+#pragma unroll
+    for (int q = 0; q < M / 32; ++q) line0[l * LS + o.rd[q & 3] + 32 * q] = v[l][q];
 }
 
-// Exchange after the (8, Ns=1) or (8, Ns=8) stage: outputs go to their Stockham positions in the warp's line,
+// Exchange after the (8, Ns=1) or (8, Ns=8) stage: outputs go to their Stockham positions in the warp's lines,
 // then every lane reads the lane + 32q layout back.
-template <int M, int Ns>
-FC_DEV void fc_wxchg8(float2 (&v)[M / 32], float2* line, const fc_wofs& o) {
+template <int M, int NL, int LS, int Ns>
+FC_DEV void fc_wxchg8(float2 (&v)[NL][M / 32], float2* line0, const fc_wofs& o) {
   constexpr int E = M / 32, NBF = E / 8;
 #pragma unroll
-  for (int t = 0; t < NBF; ++t)
+  for (int l = 0; l < NL; ++l)
 #pragma unroll
-    for (int r = 0; r < 8; ++r) line[(Ns == 1 ? o.w1[r] : o.w2[r]) + 256 * t] = v[t + NBF * r];
+    for (int t = 0; t < NBF; ++t)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) line0[l * LS + (Ns == 1 ? o.w1[r] : o.w2[r]) + 256 * t] = v[l][t + NBF * r];
   FC_SYNCWARP();
-  fc_wread<M>(v, line, o);
+  fc_wread<M, NL, LS>(v, line0, o);
   FC_SYNCWARP();
 }
 
 // Generic exchange (any stage), used by the long transforms only.
-template <int M, int R, int Ns>
-FC_DEV void fc_wxchg(float2 (&v)[M / 32], float2* line, int lane) {
+template <int M, int NL, int LS, int R, int Ns>
+FC_DEV void fc_wxchg(float2 (&v)[NL][M / 32], float2* line0, int lane) {
   constexpr int E = M / 32, NBF = E / R;
 #pragma unroll
-  for (int t = 0; t < NBF; ++t) {
-    const int j = lane + 32 * t;
-    const int k = j & (Ns - 1);
-    const int j0 = (j - k) * R + k;
+  for (int l = 0; l < NL; ++l)
 #pragma unroll
-    for (int r = 0; r < R; ++r) line[fc_swz2(j0 + r * Ns)] = v[t + NBF * r];
-  }
+    for (int t = 0; t < NBF; ++t) {
+      const int j = lane + 32 * t;
+      const int k = j & (Ns - 1);
+      const int j0 = (j - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) line0[l * LS + fc_swz2(j0 + r * Ns)] = v[l][t + NBF * r];
+    }
   FC_SYNCWARP();
 #pragma unroll
-  for (int q = 0; q < E; ++q) v[q] = line[fc_swz2(lane + 32 * q)];
+  for (int l = 0; l < NL; ++l)
+#pragma unroll
+    for (int q = 0; q < E; ++q) v[l][q] = line0[l * LS + fc_swz2(lane + 32 * q)];
   FC_SYNCWARP();
 }
 
-// Forward, unnormalised FFT of M points held by one warp. `line` = M float2 of warp-private shared memory.
-template <int M>
-struct fc_wfft;
-
-template <>
-struct fc_wfft<256> {
-  static FC_DEV void run(float2 (&v)[8], float2* line, const fc_wofs& o, const float2* tw, int tw_len, int lane) {
-    fc_wstage<256, 8, 1>(v, tw, tw_len, lane);
-    fc_wxchg8<256, 1>(v, line, o);
-    fc_wstage<256, 8, 8>(v, tw, tw_len, lane);
-    fc_wxchg8<256, 8>(v, line, o);
-    fc_wstage<256, 4, 64>(v, tw, tw_len, lane);
+// Forward, unnormalised FFT of NL lines of M points held by one warp. Line l uses M float2 of warp-private shared
+// memory at line0 + l*LS as its exchange buffer.
+template <int M, int NL, int LS>
+FC_DEV void fc_wfft(float2 (&v)[NL][M / 32], float2* line0, const fc_wofs& o, const float2* tw, int tw_len, int lane) {
+  static_assert(M == 256 || M == 512 || M == 1024, "unsupported warp FFT length");
+  fc_wstage<M, NL, 8, 1>(v, tw, tw_len, lane);
+  fc_wxchg8<M, NL, LS, 1>(v, line0, o);
+  fc_wstage<M, NL, 8, 8>(v, tw, tw_len, lane);
+  fc_wxchg8<M, NL, LS, 8>(v, line0, o);
+  if (M == 256) {
+    fc_wstage<M, NL, 4, 64>(v, tw, tw_len, lane);
+  } else if (M == 512) {
+    fc_wstage<M, NL, 8, 64>(v, tw, tw_len, lane);
+  } else {
+    fc_wstage<M, NL, 8, 64>(v, tw, tw_len, lane);
+    fc_wxchg<M, NL, LS, 8, 64>(v, line0, lane);
+    fc_wstage<M, NL, 2, 512>(v, tw, tw_len, lane);
   }
-};
-
-template <>
-struct fc_wfft<512> {
-  static FC_DEV void run(float2 (&v)[16], float2* line, const fc_wofs& o, const float2* tw, int tw_len, int lane) {
-    fc_wstage<512, 8, 1>(v, tw, tw_len, lane);
-    fc_wxchg8<512, 1>(v, line, o);
-    fc_wstage<512, 8, 8>(v, tw, tw_len, lane);
-    fc_wxchg8<512, 8>(v, line, o);
-    fc_wstage<512, 8, 64>(v, tw, tw_len, lane);
-  }
-};
-
-template <>
-struct fc_wfft<1024> {
-  static FC_DEV void run(float2 (&v)[32], float2* line, const fc_wofs& o, const float2* tw, int tw_len, int lane) {
-    fc_wstage<1024, 8, 1>(v, tw, tw_len, lane);
-    fc_wxchg8<1024, 1>(v, line, o);
-    fc_wstage<1024, 8, 8>(v, tw, tw_len, lane);
-    fc_wxchg8<1024, 8>(v, line, o);
-    fc_wstage<1024, 8, 64>(v, tw, tw_len, lane);
-    fc_wxchg<1024, 8, 64>(v, line, lane);
-    fc_wstage<1024, 2, 512>(v, tw, tw_len, lane);
-  }
-};
+}
 
 #define FC_FAST_WARPS 8
-#define FC_FAST_TR 16 /* lines per tile of the transposing kernels */
+#define FC_FAST_TR 16 /* lines per tile of the transposing kernels = 2 per warp */
 
 // ------------------------------------------------------------------------------------------------ K1
 struct fc_fast_r2c_args {
@@ -165,15 +181,15 @@ struct fc_fast_r2c_args {
   const float2* tw;
 };
 
-// Shared memory: FC_FAST_WARPS lines of M float2 + a (M+1) x (TR+1) transposition tile.
+// Shared memory: TR lines of M float2 + a (M+1) x (TR+1) transposition tile.
 template <int M>
-__global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 2) fc_fast_r2c_kernel(fc_fast_r2c_args a) {
-  constexpr int E = M / 32, TR = FC_FAST_TR, TP = TR + 1;
+__global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fast_r2c_kernel(fc_fast_r2c_args a) {
+  constexpr int E = M / 32, TR = FC_FAST_TR, TP = TR + 1, NL = 2;
   const fc_pass& p = a.p;
   FC_DYN_SMEM(smem);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  float2* line = smem + w * M;
-  float2* tile = smem + FC_FAST_WARPS * M;
+  float2* line0 = smem + (NL * w) * M;
+  float2* tile = smem + TR * M;
   const int L = p.imap.L;
   const int tstep = p.tw_len / (2 * M);
   fc_wofs ofs;
@@ -183,13 +199,25 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 2) fc_fas
     const int64_t r0 = (t - o * p.tiles_per_outer) * TR;
     const int64_t o1 = o / p.o_c2, o2 = o - o1 * p.o_c2;
     const int64_t base = (o1 / p.o_q) * p.o_sA + (o1 % p.o_q) * p.o_sB + o2 * p.o_sC;
-#pragma unroll 1
-    for (int it = 0; it < TR / FC_FAST_WARPS; ++it) {
-      const int l = w + FC_FAST_WARPS * it;
-      const int64_t r = r0 + l;
+    {  // L2 prefetch of the next tile of this CTA: its TR rows are one contiguous run of TR*in_rs floats
+      const int64_t tn = t + gridDim.x;
+      if (tn < p.n_tiles) {
+        const int64_t on = tn / p.tiles_per_outer;
+        const int64_t rn = (tn - on * p.tiles_per_outer) * TR;
+        const int64_t on1 = on / p.o_c2, on2 = on - on1 * p.o_c2;
+        const int64_t bn = (on1 / p.o_q) * p.o_sA + (on1 % p.o_q) * p.o_sB + on2 * p.o_sC + rn * p.in_rs;
+        int64_t rows = p.R - rn;
+        if (rows > TR) rows = TR;
+        const int64_t span = rows * p.in_rs;  // floats
+        for (int64_t e = (int64_t)tid * 32; e < span; e += FC_FAST_WARPS * 32 * 32) fc_prefetch_l2(a.x + bn + e);
+      }
+    }
+    float2 v[NL][E];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const int64_t r = r0 + NL * w + l;
       const bool valid = r < p.R;
       const float* row = a.x + base + (valid ? r : 0) * p.in_rs;
-      float2 v[E];
 #pragma unroll
       for (int q = 0; q < E; ++q) {
         const int i0 = 2 * (lane + 32 * q);
@@ -200,26 +228,33 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 2) fc_fas
           else if (i0 < L)
             val.x = __ldg(row + i0);
         }
-        v[q] = val;
+        v[l][q] = val;
       }
-      fc_wfft<M>::run(v, line, ofs, a.tw, p.tw_len, lane);
-      fc_wwrite<M>(v, line, ofs);
-      FC_SYNCWARP();
-      // untangle the packed real transform (same algebra as the generic R2C pass)
+    }
+    fc_wfft<M, NL, M>(v, line0, ofs, a.tw, p.tw_len, lane);
+    fc_wwrite<M, NL, M>(v, line0, ofs);
+    FC_SYNCWARP();
+    // untangle the packed real transforms (same algebra as the generic R2C pass)
 #pragma unroll
-      for (int q = 0; q < E; ++q) {
-        const int k = lane + 32 * q;
-        const float2 zk = v[q];
-        const float2 zc = fc_conj(line[fc_swz2((M - k) & (M - 1))]);
+    for (int q = 0; q < E; ++q) {
+      const int k = lane + 32 * q;
+      const float2 wk = __ldg(a.tw + k * tstep);
+      const int km = fc_swz2((M - k) & (M - 1));
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const float2 zk = v[l][q];
+        const float2 zc = fc_conj(line0[l * M + km]);
         const float2 e = fc_scale(fc_add(zk, zc), 0.5f);
         const float2 od = fc_scale(fc_mul_mi(fc_sub(zk, zc)), 0.5f);
-        tile[k * TP + l] = fc_add(e, fc_mul(__ldg(a.tw + k * tstep), od));
+        tile[k * TP + NL * w + l] = fc_add(e, fc_mul(wk, od));
       }
-      if (lane == 0) {  // Nyquist bin k = M: E[0] - O[0]
-        const float2 z0 = line[fc_swz2(0)];
-        tile[M * TP + l] = make_float2(z0.x - z0.y, 0.f);
+    }
+    if (lane == 0) {  // Nyquist bin k = M: E[0] - O[0]
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const float2 z0 = line0[l * M + fc_swz2(0)];
+        tile[M * TP + NL * w + l] = make_float2(z0.x - z0.y, 0.f);
       }
-      FC_SYNCWARP();
     }
     __syncthreads();
     for (int idx = tid; idx < (M + 1) * TR; idx += FC_FAST_WARPS * 32) {
@@ -240,15 +275,16 @@ struct fc_fast_c2r_args {
 };
 
 template <int M>
-__global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 2) fc_fast_c2r_kernel(fc_fast_c2r_args a) {
-  constexpr int E = M / 32, TR = FC_FAST_TR, TP = TR + 1;
+__global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fast_c2r_kernel(fc_fast_c2r_args a) {
+  constexpr int E = M / 32, TR = FC_FAST_TR, TP = TR + 1, NL = 2;
   const fc_pass& p = a.p;
   FC_DYN_SMEM(smem);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  float2* line = smem + w * M;
-  float2* tile = smem + FC_FAST_WARPS * M;
+  float2* line0 = smem + (NL * w) * M;
+  float2* tile = smem + TR * M;
   const int tstep = p.tw_len / (2 * M);
   const fc_omap om = p.omap;
+  const bool plain_out = om.os == 1 && om.ob == 0 && om.og == 1 && !(om.Lout & 1) && !(p.out_rs & 1) && !(p.out_os & 1);
   fc_wofs ofs;
   ofs.init(lane);
   for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
@@ -258,50 +294,67 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 2) fc_fas
       const int l = idx & (TR - 1), k = idx >> 4;
       tile[k * TP + l] = (r0 + l < p.R) ? __ldg(a.in + o * p.in_os + (int64_t)k * p.in_es + r0 + l) : make_float2(0.f, 0.f);
     }
+    {  // L2 prefetch of the next tile of this CTA: (M+1) segments of TR float2 = 128 bytes
+      const int64_t tn = t + gridDim.x;
+      if (tn < p.n_tiles) {
+        const int64_t on = tn / p.tiles_per_outer;
+        const int64_t rn = (tn - on * p.tiles_per_outer) * TR;
+        for (int k = tid; k <= M; k += FC_FAST_WARPS * 32) fc_prefetch_l2(a.in + on * p.in_os + (int64_t)k * p.in_es + rn);
+      }
+    }
     __syncthreads();
     const float b = p.has_bias ? __ldg(a.bias + (int)(o % p.cout)) : 0.f;
-#pragma unroll 1
-    for (int it = 0; it < TR / FC_FAST_WARPS; ++it) {
-      const int l = w + FC_FAST_WARPS * it;
-      const int64_t r = r0 + l;
-      float2 v[E];
+    float2 v[NL][E];
 #pragma unroll
-      for (int q = 0; q < E; ++q) {
-        const int k = lane + 32 * q;
-        const float2 yk = tile[k * TP + l];
-        const float2 ym = fc_conj(tile[(M - k) * TP + l]);
+    for (int q = 0; q < E; ++q) {
+      const int k = lane + 32 * q;
+      const float2 wk = fc_conj(__ldg(a.tw + k * tstep));
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const float2 yk = tile[k * TP + NL * w + l];
+        const float2 ym = fc_conj(tile[(M - k) * TP + NL * w + l]);
         const float2 s = fc_add(yk, ym);
-        const float2 d = fc_mul(fc_sub(yk, ym), fc_conj(__ldg(a.tw + k * tstep)));
-        v[q] = make_float2(s.x - d.y, -(s.y + d.x));  // conj(Z[k]), Z = s + i*d
+        const float2 d = fc_mul(fc_sub(yk, ym), wk);
+        v[l][q] = make_float2(s.x - d.y, -(s.y + d.x));  // conj(Z[k]), Z = s + i*d
       }
-      fc_wfft<M>::run(v, line, ofs, a.tw, p.tw_len, lane);
-      if (r < p.R) {
-        float* yrow = a.out + o * p.out_os + r * p.out_rs;
-        if (om.os == 1 && om.ob == 0 && om.og == 1 && !(om.Lout & 1) && !(p.out_rs & 1) && !(p.out_os & 1)) {
+    }
+    fc_wfft<M, NL, M>(v, line0, ofs, a.tw, p.tw_len, lane);
+    if (plain_out) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const int64_t r = r0 + NL * w + l;
+        if (r < p.R) {
+          float* yrow = a.out + o * p.out_os + r * p.out_rs;
 #pragma unroll
           for (int q = 0; q < E; ++q) {
             const int n0 = 2 * (lane + 32 * q);
-            if (n0 < om.Lout) *reinterpret_cast<float2*>(yrow + n0) = make_float2(v[q].x + b, -v[q].y + b);
-          }
-        } else {
-          // general crop / stride / lattice map: stage the real row in the warp's line and scatter from there
-          float* rl = reinterpret_cast<float*>(line);
-#pragma unroll
-          for (int q = 0; q < E; ++q) line[lane + 32 * q] = make_float2(v[q].x, -v[q].y);
-          FC_SYNCWARP();
-          for (int n = lane; n < 2 * M; n += 32) {
-            const float val = rl[n];
-            for (int e = 0; e < om.og; ++e) {
-              const int tt = n * om.og + e - om.ob;
-              if (tt < 0 || (tt % om.os)) continue;
-              const int j = tt / om.os;
-              if (j >= om.Lout) continue;
-              yrow[j] = ((e == 0 && n < om.lim) ? val : 0.f) + b;
-            }
+            if (n0 < om.Lout) *reinterpret_cast<float2*>(yrow + n0) = make_float2(v[l][q].x + b, -v[l][q].y + b);
           }
         }
       }
+    } else {
+      // general crop / stride / lattice map: stage the real rows in the warp's lines and scatter from there
+#pragma unroll
+      for (int l = 0; l < NL; ++l)
+#pragma unroll
+        for (int q = 0; q < E; ++q) line0[l * M + lane + 32 * q] = make_float2(v[l][q].x, -v[l][q].y);
       FC_SYNCWARP();
+      for (int l = 0; l < NL; ++l) {
+        const int64_t r = r0 + NL * w + l;
+        if (r >= p.R) continue;
+        float* yrow = a.out + o * p.out_os + r * p.out_rs;
+        const float* rl = reinterpret_cast<const float*>(line0 + l * M);
+        for (int n = lane; n < 2 * M; n += 32) {
+          const float val = rl[n];
+          for (int e = 0; e < om.og; ++e) {
+            const int tt = n * om.og + e - om.ob;
+            if (tt < 0 || (tt % om.os)) continue;
+            const int j = tt / om.os;
+            if (j >= om.Lout) continue;
+            yrow[j] = ((e == 0 && n < om.lim) ? val : 0.f) + b;
+          }
+        }
+      }
     }
     __syncthreads();
   }
@@ -316,131 +369,193 @@ struct fc_fused_args {
   int32_t tw_len;
   int32_t B, Cin, Cout, G, Ig, Og;
   int32_t n_in, n_out, nbs;
+  int32_t prefetch_dist;  // units between a CTA and the one whose operands it pulls into L2 (0 = off)
   int64_t R;
   int64_t n_units;
   fc_imap imap;
   fc_omap omap;
 };
 
-// N: transform length of the fused axis. CI: bound on channels per group (in and out). NB: batches per CTA.
+// N: transform length of the fused axis. CI: bound on channels per group (in and out). NB: batches per CTA
+// (= lines per warp: a warp transforms one channel of all NB batches together). W: warps per CTA. PLAIN: the axis
+// has an identity gather map and a plain crop on store (compiled without the general map code).
 // Shared memory: NB*CI lines of N float2 (each line doubles as its warp's exchange buffer).
-template <int N, int CI, int NB>
-__global__ void __launch_bounds__(FC_FAST_WARPS * 32, (N * NB <= 1024) ? 2 : 1) fc_fused_axis_kernel(fc_fused_args a) {
-  constexpr int E = N / 32;
+template <int N, int CI, int NB, int W, bool PLAIN>
+__global__ void __launch_bounds__(W * 32, (N * NB <= 1024) ? (W <= 4 ? 3 : 2) : 1) fc_fused_axis_kernel(fc_fused_args a) {
+  constexpr int E = N / 32, LS = CI * N;  // line (b, c) at xy + (b*CI + c)*N
   FC_DYN_SMEM(xy);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int Ig = a.Ig, Og = a.Og;
   fc_wofs ofs;
   ofs.init(lane);
   const fc_omap om = a.omap;
-  const bool plain_in = a.imap.mode == FC_PAD_CONSTANT && a.imap.pad == 0 && a.imap.up == 1 && a.imap.sub == 1;
+  const bool plain_in = PLAIN;  // host guarantees: constant mode, no pad / zero-stuffing / subsampling on this axis
   const int in_lim = a.imap.ext < a.imap.L ? a.imap.ext : a.imap.L;
-  const bool plain_out = om.og == 1 && om.os == 1 && om.ob == 0;
+  const bool plain_out = PLAIN;  // host guarantees: og == 1, os == 1, ob == 0
   const int out_lim = om.Lout < om.lim ? om.Lout : om.lim;
+  const int64_t kstride = a.R * N;  // kernel-spectrum stride between input channels
   for (int64_t unit = blockIdx.x; unit < a.n_units; unit += gridDim.x) {
     const int bs = (int)(unit % a.nbs);
     const int64_t gr = unit / a.nbs;
     const int64_t r = gr % a.R;
     const int g = (int)(gr / a.R);
     const int b0 = bs * NB;
-    // ---- phase 1: forward transform of every (batch, input channel) line of this bin
-    const int n_it1 = (NB * Ig + FC_FAST_WARPS - 1) / FC_FAST_WARPS;
-#pragma unroll 1
-    for (int it = 0; it < n_it1; ++it) {
-      const int ln = w + FC_FAST_WARPS * it;
-      if (ln >= NB * Ig) continue;  // warp-uniform
-      const int bl = ln / Ig;
-      const int i = ln - bl * Ig;
-      const bool active = b0 + bl < a.B;
-      float2* line = xy + (size_t)(bl * CI + i) * N;
-      const float2* src = a.xin + (((int64_t)(b0 + (active ? bl : 0)) * a.Cin + g * Ig + i) * a.R + r) * a.n_in;
-      float2 v[E];
-      if (plain_in) {
-#pragma unroll
-        for (int q = 0; q < E; ++q) {
-          const int n = lane + 32 * q;
-          v[q] = (active && n < in_lim) ? __ldg(src + n) : make_float2(0.f, 0.f);
+    // ---- L2 prefetch for the unit that runs `prefetch_dist` units later (the next wave on this SM): its input
+    // lines and, once per bin (bs == 0), its slice of the kernel spectrum
+    if (a.prefetch_dist > 0) {
+      const int64_t un = unit + a.prefetch_dist;
+      if (un < a.n_units) {
+        const int bsn = (int)(un % a.nbs);
+        const int64_t grn = un / a.nbs;
+        const int64_t rn = grn % a.R;
+        const int gn = (int)(grn / a.R);
+        const int per_line = (a.n_in * 8 + 127) / 128;  // 128-byte lines per input line
+        for (int idx = tid; idx < NB * Ig * per_line; idx += W * 32) {
+          const int ln = idx / per_line, seg = idx - ln * per_line;
+          const int bl = ln / Ig, i = ln - bl * Ig;
+          if (bsn * NB + bl < a.B)
+            fc_prefetch_l2(a.xin + (((int64_t)(bsn * NB + bl) * a.Cin + gn * Ig + i) * a.R + rn) * a.n_in + seg * 16);
         }
-      } else {
-#pragma unroll
-        for (int q = 0; q < E; ++q) {
-          const int s = fc_imap_src(a.imap, lane + 32 * q);
-          v[q] = (active && s >= 0) ? __ldg(src + s) : make_float2(0.f, 0.f);
+        if (bsn == 0) {
+          constexpr int kper = N * 8 / 128;
+          for (int idx = tid; idx < Og * Ig * kper; idx += W * 32) {
+            const int ln = idx / kper, seg = idx - ln * kper;
+            fc_prefetch_l2(a.kspec + ((int64_t)(gn * Og * Ig + ln) * a.R + rn) * N + seg * 16);
+          }
         }
       }
-      fc_wfft<N>::run(v, line, ofs, a.tw, a.tw_len, lane);  // the line itself is the warp's exchange buffer
+    }
+    // ---- phase 1: forward transform of every (batch, input channel) line of this bin
+    const int n_it1 = (Ig + W - 1) / W;
+#pragma unroll 1
+    for (int it = 0; it < n_it1; ++it) {
+      const int i = w + W * it;
+      if (i >= Ig) continue;  // warp-uniform
+      float2* line0 = xy + (size_t)i * N;
+      float2 v[NB][E];
 #pragma unroll
-      for (int q = 0; q < E; ++q) line[lane + 32 * q] = v[q];
+      for (int bl = 0; bl < NB; ++bl) {
+        const bool active = b0 + bl < a.B;
+        const float2* src = a.xin + (((int64_t)(b0 + (active ? bl : 0)) * a.Cin + g * Ig + i) * a.R + r) * a.n_in;
+        if (plain_in) {
+#pragma unroll
+          for (int q = 0; q < E; ++q) {
+            const int n = lane + 32 * q;
+            v[bl][q] = (active && n < in_lim) ? __ldg(src + n) : make_float2(0.f, 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < E; ++q) {
+            const int s = fc_imap_src(a.imap, lane + 32 * q);
+            v[bl][q] = (active && s >= 0) ? __ldg(src + s) : make_float2(0.f, 0.f);
+          }
+        }
+      }
+      fc_wfft<N, NB, LS>(v, line0, ofs, a.tw, a.tw_len, lane);  // the lines themselves are the exchange buffers
+#pragma unroll
+      for (int bl = 0; bl < NB; ++bl)
+#pragma unroll
+        for (int q = 0; q < E; ++q) line0[bl * LS + lane + 32 * q] = v[bl][q];
     }
     __syncthreads();
     // ---- phase 2: per-bin contraction over the input channels of the group, in place (X -> Y).
-    // One bin per thread and iteration; the kernel-spectrum loads of output channel o+1 are in flight while
-    // output channel o is accumulated.
-    for (int u = tid; u < N; u += FC_FAST_WARPS * 32) {
-      float2 xr[NB][CI];
+    // Two adjacent bins per thread (16-byte accesses). The kernel-spectrum loads are software-pipelined in two
+    // half-sets (input channels [0, CI/2) and [CI/2, CI)): one half is always in flight while the other is used.
+    for (int u = tid; u < N / 2; u += W * 32) {
+      constexpr int H = CI / 2;
+      float4 xr[NB][CI];
 #pragma unroll
       for (int b = 0; b < NB; ++b)
 #pragma unroll
-        for (int i = 0; i < CI; ++i) xr[b][i] = xy[(size_t)(b * CI + i) * N + u];
-      const int64_t kstride = a.R * N;  // between input channels
-      const float2* kl = a.kspec + (((int64_t)(g * Og) * Ig) * a.R + r) * N + u;
-      float2 kv[CI], kn[CI];
+        for (int i = 0; i < CI; ++i) xr[b][i] = *reinterpret_cast<const float4*>(xy + (size_t)(b * CI + i) * N + 2 * u);
+      const float2* kl = a.kspec + (((int64_t)(g * Og) * Ig) * a.R + r) * N + 2 * u;
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 ka[H], kb[H];
 #pragma unroll
-      for (int i = 0; i < CI; ++i) kv[i] = (i < Ig) ? __ldg(kl + (int64_t)i * kstride) : make_float2(0.f, 0.f);
+      for (int i = 0; i < H; ++i) {
+        ka[i] = (i < Ig) ? __ldg(reinterpret_cast<const float4*>(kl + (int64_t)i * kstride)) : zero4;
+        kb[i] = (i + H < Ig) ? __ldg(reinterpret_cast<const float4*>(kl + (int64_t)(i + H) * kstride)) : zero4;
+      }
+#pragma unroll 1
       for (int o = 0; o < Og; ++o) {
-        const float2* kl1 = kl + (int64_t)((o + 1 < Og) ? (o + 1) : o) * Ig * kstride;
+        const float2* kn = kl + (int64_t)((o + 1 < Og) ? (o + 1) : o) * Ig * kstride;
+        float4 acc[NB];
 #pragma unroll
-        for (int i = 0; i < CI; ++i) kn[i] = (i < Ig) ? __ldg(kl1 + (int64_t)i * kstride) : make_float2(0.f, 0.f);
-        float2 acc[NB];
+        for (int b = 0; b < NB; ++b) acc[b] = zero4;
 #pragma unroll
-        for (int b = 0; b < NB; ++b) acc[b] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < CI; ++i) {
+        for (int i = 0; i < H; ++i) {
 #pragma unroll
           for (int b = 0; b < NB; ++b) {
-            acc[b].x += xr[b][i].x * kv[i].x - xr[b][i].y * kv[i].y;
-            acc[b].y += xr[b][i].x * kv[i].y + xr[b][i].y * kv[i].x;
+            acc[b].x = fmaf(xr[b][i].x, ka[i].x, acc[b].x);
+            acc[b].y = fmaf(xr[b][i].x, ka[i].y, acc[b].y);
+            acc[b].z = fmaf(xr[b][i].z, ka[i].z, acc[b].z);
+            acc[b].w = fmaf(xr[b][i].z, ka[i].w, acc[b].w);
+            acc[b].x = fmaf(-xr[b][i].y, ka[i].y, acc[b].x);
+            acc[b].y = fmaf(xr[b][i].y, ka[i].x, acc[b].y);
+            acc[b].z = fmaf(-xr[b][i].w, ka[i].w, acc[b].z);
+            acc[b].w = fmaf(xr[b][i].w, ka[i].z, acc[b].w);
           }
         }
 #pragma unroll
-        for (int b = 0; b < NB; ++b) xy[(size_t)(b * CI + o) * N + u] = acc[b];
+        for (int i = 0; i < H; ++i) ka[i] = (i < Ig) ? __ldg(reinterpret_cast<const float4*>(kn + (int64_t)i * kstride)) : zero4;
 #pragma unroll
-        for (int i = 0; i < CI; ++i) kv[i] = kn[i];
+        for (int i = 0; i < H; ++i) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            acc[b].x = fmaf(xr[b][i + H].x, kb[i].x, acc[b].x);
+            acc[b].y = fmaf(xr[b][i + H].x, kb[i].y, acc[b].y);
+            acc[b].z = fmaf(xr[b][i + H].z, kb[i].z, acc[b].z);
+            acc[b].w = fmaf(xr[b][i + H].z, kb[i].w, acc[b].w);
+            acc[b].x = fmaf(-xr[b][i + H].y, kb[i].y, acc[b].x);
+            acc[b].y = fmaf(xr[b][i + H].y, kb[i].x, acc[b].y);
+            acc[b].z = fmaf(-xr[b][i + H].w, kb[i].w, acc[b].z);
+            acc[b].w = fmaf(xr[b][i + H].w, kb[i].z, acc[b].w);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < H; ++i) kb[i] = (i + H < Ig) ? __ldg(reinterpret_cast<const float4*>(kn + (int64_t)(i + H) * kstride)) : zero4;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) *reinterpret_cast<float4*>(xy + (size_t)(b * CI + o) * N + 2 * u) = acc[b];
       }
     }
     __syncthreads();
     // ---- phase 3: inverse transform of every (batch, output channel) line, crop / stride on store
-    const int n_it3 = (NB * Og + FC_FAST_WARPS - 1) / FC_FAST_WARPS;
+    const int n_it3 = (Og + W - 1) / W;
 #pragma unroll 1
     for (int it = 0; it < n_it3; ++it) {
-      const int ln = w + FC_FAST_WARPS * it;
-      if (ln >= NB * Og) continue;  // warp-uniform
-      const int bl = ln / Og;
-      const int o = ln - bl * Og;
-      const bool active = b0 + bl < a.B;
-      float2* line = xy + (size_t)(bl * CI + o) * N;
-      float2 v[E];
+      const int o = w + W * it;
+      if (o >= Og) continue;  // warp-uniform
+      float2* line0 = xy + (size_t)o * N;
+      float2 v[NB][E];
 #pragma unroll
-      for (int q = 0; q < E; ++q) v[q] = fc_conj(line[lane + 32 * q]);
-      FC_SYNCWARP();  // the line becomes the exchange buffer: every lane must have read its inputs
-      fc_wfft<N>::run(v, line, ofs, a.tw, a.tw_len, lane);
-      float2* dst = a.yout + (((int64_t)(b0 + (active ? bl : 0)) * a.Cout + g * Og + o) * a.R + r) * a.n_out;
+      for (int bl = 0; bl < NB; ++bl)
+#pragma unroll
+        for (int q = 0; q < E; ++q) v[bl][q] = fc_conj(line0[bl * LS + lane + 32 * q]);
+      FC_SYNCWARP();  // the lines become the exchange buffers: every lane must have read its inputs
+      fc_wfft<N, NB, LS>(v, line0, ofs, a.tw, a.tw_len, lane);
       if (plain_out) {
-        if (active) {
+#pragma unroll
+        for (int bl = 0; bl < NB; ++bl) {
+          if (b0 + bl >= a.B) continue;
+          float2* dst = a.yout + (((int64_t)(b0 + bl) * a.Cout + g * Og + o) * a.R + r) * a.n_out;
 #pragma unroll
           for (int q = 0; q < E; ++q) {
             const int n = lane + 32 * q;
-            if (n < om.Lout) dst[n] = (n < out_lim) ? fc_conj(v[q]) : make_float2(0.f, 0.f);
+            if (n < om.Lout) dst[n] = (n < out_lim) ? fc_conj(v[bl][q]) : make_float2(0.f, 0.f);
           }
         }
       } else {
-        // general crop / stride / lattice map: stage the line in shared memory and scatter from there
+        // general crop / stride / lattice map: stage the lines in shared memory and scatter from there
 #pragma unroll
-        for (int q = 0; q < E; ++q) line[lane + 32 * q] = fc_conj(v[q]);
+        for (int bl = 0; bl < NB; ++bl)
+#pragma unroll
+          for (int q = 0; q < E; ++q) line0[bl * LS + lane + 32 * q] = fc_conj(v[bl][q]);
         FC_SYNCWARP();
-        if (active) {
+        for (int bl = 0; bl < NB; ++bl) {
+          if (b0 + bl >= a.B) continue;
+          float2* dst = a.yout + (((int64_t)(b0 + bl) * a.Cout + g * Og + o) * a.R + r) * a.n_out;
           for (int n = lane; n < N; n += 32) {
-            const float2 val = line[n];
+            const float2 val = line0[bl * LS + n];
             for (int e = 0; e < om.og; ++e) {
               const int tt = n * om.og + e - om.ob;
               if (tt < 0 || (tt % om.os)) continue;

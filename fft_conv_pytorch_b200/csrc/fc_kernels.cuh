@@ -502,8 +502,10 @@ __global__ void fc_contract_kernel(fc_contract_args a) {
     for (int i = 0; i < TB; ++i)
 #pragma unroll
       for (int j = 0; j < TO; ++j) {
-        acc[i][j].x += xv[i].x * kv[j].x - xv[i].y * kv[j].y;
-        acc[i][j].y += xv[i].x * kv[j].y + xv[i].y * kv[j].x;
+        acc[i][j].x = fmaf(xv[i].x, kv[j].x, acc[i][j].x);
+        acc[i][j].y = fmaf(xv[i].x, kv[j].y, acc[i][j].y);
+        acc[i][j].x = fmaf(-xv[i].y, kv[j].y, acc[i][j].x);
+        acc[i][j].y = fmaf(xv[i].y, kv[j].x, acc[i][j].y);
       }
   }
 #pragma unroll

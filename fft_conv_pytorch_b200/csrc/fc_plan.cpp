@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -698,6 +699,18 @@ void fc_plan_build_program(fc_plan* pl) {
     L.fused.n_out = bs.pass.n_out;
     L.fused.nb = (P.batch >= 2 && fs.pass.N <= 512) ? 2 : 1;
     L.fused.ci = 8;
+    L.fused.warps = 8;
+    {
+      const fc_imap& im = fs.pass.imap;
+      const fc_omap& om = bs.pass.omap;
+      L.fused.plain = im.mode == FC_PAD_CONSTANT && im.pad == 0 && im.up == 1 && im.sub == 1 && om.og == 1 && om.os == 1 && om.ob == 0;
+    }
+    if (const char* tune = std::getenv("FFTCONV_B200_TUNE")) {  // A/B timing knobs: "nb=1,warps=4"
+      const char* q;
+      if ((q = std::strstr(tune, "nb="))) L.fused.nb = std::atoi(q + 3) >= 2 && fs.pass.N <= 512 && P.batch >= 2 ? 2 : 1;
+      if ((q = std::strstr(tune, "warps="))) L.fused.warps = (std::atoi(q + 6) == 4 && L.fused.plain && fs.pass.N <= 512) ? 4 : 8;
+      if (L.fused.warps == 4 && fs.pass.N == 256 && L.fused.nb == 1) L.fused.warps = 8;
+    }
     L.fused.R = fs.pass.R;
     L.fused.imap = fs.pass.imap;
     L.fused.omap = bs.pass.omap;

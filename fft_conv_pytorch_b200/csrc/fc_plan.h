@@ -31,6 +31,8 @@ struct fc_fused_desc {
   int32_t n_out;  // stored output elements per line
   int32_t nb;     // batches per CTA
   int32_t ci;     // channel bound of the instantiation
+  int32_t warps;  // warps per CTA
+  int32_t plain;  // identity gather map and plain crop: use the instantiation without the general map code
   int64_t R;      // lines (bins of the other axes) per (batch, channel)
   fc_imap imap;
   fc_omap omap;

@@ -225,18 +225,69 @@ def _run(transposed: bool, signal: Tensor, kernel: Tensor, bias: Optional[Tensor
             L.check(lib, lib.fc_conv(plan.handle, _ptr(const), _ptr(x), _ptr(kspec), _ptr(b_dev), _ptr(y), _ptr(ws), stream), "fc_conv")
             _launch_counter += int(plan.info.n_launches)
             return y
-        # host buffers in, host buffers out: H2D + kernels + D2H on the current stream
+        # host buffers in, host buffers out
         x_host = signal.detach().contiguous()
         if not x_host.is_pinned():
             x_host = x_host.pin_memory()
         y_host = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
         x_stage = torch.empty(x_host.shape, dtype=torch.float32, device=dev)
         y_stage = torch.empty(out_shape, dtype=torch.float32, device=dev)
-        L.check(lib, lib.fc_conv_host(plan.handle, _ptr(const), _ptr(x_host), _ptr(x_stage), _ptr(kspec), _ptr(b_dev), _ptr(y_stage),
-                                      _ptr(y_host), _ptr(ws), stream), "fc_conv_host")
-        _launch_counter += int(plan.info.n_launches)
-        torch.cuda.current_stream(dev).synchronize()
+        n_chunks = min(B, _HOST_PIPELINE_CHUNKS)
+        if n_chunks < 2:
+            # one shot: H2D + kernels + D2H on the current stream (fc_conv_host)
+            L.check(lib, lib.fc_conv_host(plan.handle, _ptr(const), _ptr(x_host), _ptr(x_stage), _ptr(kspec), _ptr(b_dev), _ptr(y_stage),
+                                          _ptr(y_host), _ptr(ws), stream), "fc_conv_host")
+            _launch_counter += int(plan.info.n_launches)
+            torch.cuda.current_stream(dev).synchronize()
+            return y_host
+        # batch-chunked pipeline: the upload of chunk c+1 and the download of chunk c-1 overlap the kernels of chunk c
+        # (PCIe is full duplex); every chunk is an independent convolution, so the result is unchanged
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_out = _side_streams(dev)
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        bounds = [(B * c) // n_chunks for c in range(n_chunks + 1)]
+        ev_in = []
+        with torch.cuda.stream(s_in):
+            for c in range(n_chunks):
+                a0, a1 = bounds[c], bounds[c + 1]
+                x_stage[a0:a1].copy_(x_host[a0:a1], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+                ev_in.append(e)
+        for c in range(n_chunks):
+            a0, a1 = bounds[c], bounds[c + 1]
+            sub = entry if a1 - a0 == B else get_plan(transposed, a1 - a0, cin, cout, groups, tuple(int(v) for v in signal.shape[2:]),
+                                                      tuple(int(v) for v in kernel.shape[2:]), stride_, padding_, dilation_, opad_, padding_mode, flags)
+            sp = sub.plan
+            cur.wait_event(ev_in[c])
+            L.check(lib, lib.fc_conv(sp.handle, _ptr(sub.const_for(dev)), ctypes.c_void_p(x_stage[a0:a1].data_ptr()), _ptr(kspec), _ptr(b_dev),
+                                     ctypes.c_void_p(y_stage[a0:a1].data_ptr()), _ptr(ws), stream), "fc_conv")
+            _launch_counter += int(sp.info.n_launches)
+            e = torch.cuda.Event()
+            e.record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(e)
+                y_host[a0:a1].copy_(y_stage[a0:a1], non_blocking=True)
+        cur.wait_stream(s_out)
+        s_out.synchronize()
+        for t in (x_stage, y_stage, ws, kspec):
+            t.record_stream(s_in)
+            t.record_stream(s_out)
         return y_host
+
+
+_HOST_PIPELINE_CHUNKS = int(os.environ.get("FFTCONV_B200_HOST_CHUNKS", "4"))
+_side = {}
+
+
+def _side_streams(dev: torch.device):
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    s = _side.get(idx)
+    if s is None:
+        s = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        _side[idx] = s
+    return s
 
 
 def fft_conv(

@@ -4,6 +4,7 @@
 // one after another, __syncthreads() is a real barrier. Never linked into the shipped library.
 #pragma once
 #include <cmath>
+using std::fmaf;
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
