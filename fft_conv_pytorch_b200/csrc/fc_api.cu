@@ -55,15 +55,16 @@ int g_num_sms = 148;
 
 // every instantiation of the fused kernel: (N, NB, warps, plain)
 #define FC_FUSED_ALL(X) \
-  X(256, 2, 8, true) X(256, 2, 8, false) X(256, 1, 8, true) X(256, 1, 8, false) \
-  X(512, 2, 8, true) X(512, 2, 8, false) X(512, 1, 8, true) X(512, 1, 8, false) \
-  X(512, 2, 4, true) X(512, 1, 4, true) X(256, 2, 4, true) \
-  X(1024, 1, 8, true) X(1024, 1, 8, false)
+  X(256, 2, 8, true, 2) X(256, 2, 8, false, 2) X(256, 1, 8, true, 2) X(256, 1, 8, false, 2) \
+  X(512, 2, 8, true, 2) X(512, 2, 8, false, 2) X(512, 1, 8, true, 2) X(512, 1, 8, false, 2) \
+  X(512, 2, 8, true, 3) X(512, 1, 8, true, 3) X(512, 1, 8, true, 4) \
+  X(512, 2, 4, true, 3) X(512, 1, 4, true, 3) X(256, 2, 4, true, 3) \
+  X(1024, 1, 8, true, 2) X(1024, 1, 8, false, 2)
 
 void fused_set_attr() {
 #ifndef FC_CPU_EMUL
-#define FC_FUSED_ATTR(NN, NBB, WW, PL) \
-  cudaFuncSetAttribute(fc_fused_axis_kernel<NN, 8, NBB, WW, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+#define FC_FUSED_ATTR(NN, NBB, WW, PL, OC) \
+  cudaFuncSetAttribute(fc_fused_axis_kernel<NN, 8, NBB, WW, PL, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   FC_FUSED_ALL(FC_FUSED_ATTR)
 #undef FC_FUSED_ATTR
 #endif
@@ -238,7 +239,7 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
   const size_t smem = (size_t)f.nb * f.ci * f.N * sizeof(float2);
   {  // distance (in units) to the CTA of the next wave on the same SM: what this CTA prefetches into L2
     int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(smem + 1024);
-    const int64_t reg_lim = f.warps <= 4 ? 3 : 2;  // launch bounds
+    const int64_t reg_lim = f.occ;  // launch bounds
     if (per_sm > reg_lim) per_sm = reg_lim;
     if (per_sm < 1) per_sm = 1;
     a.prefetch_dist = (int)(g_num_sms * per_sm);
@@ -248,9 +249,9 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
   if (grid > cap) grid = cap;
   dim3 g((unsigned)grid), b((unsigned)f.warps * 32);
   bool ok = false;
-#define FC_FUSED_CASE(NN, NBB, WW, PL)                                   \
-  if (!ok && f.N == NN && f.nb == NBB && f.warps == WW && (f.plain != 0) == PL) { \
-    auto k = fc_fused_axis_kernel<NN, 8, NBB, WW, PL>;                   \
+#define FC_FUSED_CASE(NN, NBB, WW, PL, OC)                                   \
+  if (!ok && f.N == NN && f.nb == NBB && f.warps == WW && (f.plain != 0) == PL && f.occ == OC) { \
+    auto k = fc_fused_axis_kernel<NN, 8, NBB, WW, PL, OC>;                   \
     FC_LAUNCH(k, g, b, smem, st, a);                                     \
     ok = true;                                                           \
   }

@@ -700,16 +700,23 @@ void fc_plan_build_program(fc_plan* pl) {
     L.fused.nb = (P.batch >= 2 && fs.pass.N <= 512) ? 2 : 1;
     L.fused.ci = 8;
     L.fused.warps = 8;
+    L.fused.occ = fs.pass.N * L.fused.nb <= 1024 ? 2 : 1;
     {
       const fc_imap& im = fs.pass.imap;
       const fc_omap& om = bs.pass.omap;
-      L.fused.plain = im.mode == FC_PAD_CONSTANT && im.pad == 0 && im.up == 1 && im.sub == 1 && om.og == 1 && om.os == 1 && om.ob == 0;
+      L.fused.plain = im.mode == FC_PAD_CONSTANT && im.pad == 0 && im.up == 1 && im.sub == 1 && im.L >= fs.pass.N && im.ext >= fs.pass.N &&
+                      om.og == 1 && om.os == 1 && om.ob == 0 && om.Lout <= om.lim && Ig == 8 && Og == 8;
     }
     if (const char* tune = std::getenv("FFTCONV_B200_TUNE")) {  // A/B timing knobs: "nb=1,warps=4"
       const char* q;
       if ((q = std::strstr(tune, "nb="))) L.fused.nb = std::atoi(q + 3) >= 2 && fs.pass.N <= 512 && P.batch >= 2 ? 2 : 1;
       if ((q = std::strstr(tune, "warps="))) L.fused.warps = (std::atoi(q + 6) == 4 && L.fused.plain && fs.pass.N <= 512) ? 4 : 8;
       if (L.fused.warps == 4 && fs.pass.N == 256 && L.fused.nb == 1) L.fused.warps = 8;
+      L.fused.occ = fs.pass.N * L.fused.nb <= 1024 ? (L.fused.warps == 4 ? 3 : 2) : 1;
+      if ((q = std::strstr(tune, "occ=")) && L.fused.plain && fs.pass.N == 512 && L.fused.warps == 8) {
+        const int o = std::atoi(q + 4);
+        if (o == 3 || (o == 4 && L.fused.nb == 1)) L.fused.occ = o;
+      }
     }
     L.fused.R = fs.pass.R;
     L.fused.imap = fs.pass.imap;

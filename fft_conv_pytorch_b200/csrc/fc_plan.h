@@ -32,6 +32,7 @@ struct fc_fused_desc {
   int32_t nb;     // batches per CTA
   int32_t ci;     // channel bound of the instantiation
   int32_t warps;  // warps per CTA
+  int32_t occ;    // CTAs per SM the instantiation is compiled for (register cap)
   int32_t plain;  // identity gather map and plain crop: use the instantiation without the general map code
   int64_t R;      // lines (bins of the other axes) per (batch, channel)
   fc_imap imap;
