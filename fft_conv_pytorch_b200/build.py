@@ -44,6 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     # library next to the system libstdc++ that numpy/torch load; the distro g++ links it dynamically.
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]
+    if os.environ.get("FFTCONV_B200_PACKED", "1") != "0":
+        cmd += ["-DFC_PACKED_F32X2"]  # FADD2 for complex add/sub (sm_100a packed fp32)
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]

@@ -2,6 +2,7 @@
 // Compiled by nvcc for sm_100a into libfftconv_b200.so. (tests/cpu_emul compiles the same file with
 // -DFC_CPU_EMUL as host C++ to exercise the kernel logic without a GPU; that build is test-only.)
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -108,7 +109,12 @@ int launch_pass(const fc_plan* pl, const fc_pass& p, const void* in, void* out, 
   int64_t grid = (int64_t)g_num_sms * per_sm;
   if (grid > p.n_tiles) grid = p.n_tiles;
   if (grid < 1) return FC_OK;
-  dim3 g((unsigned)grid), b((unsigned)pl->threads);
+  // big tiles leave room for one CTA per SM only: give that CTA more warps to hide latency
+  unsigned threads = (unsigned)pl->threads;
+  if (pl->prob.threads == 0) {
+    if (smem > 100 * 1024) threads = 1024;
+  }
+  dim3 g((unsigned)grid), b(threads);
   switch (p.kind) {
     case FC_R2C: {
       auto k = fc_pass_kernel<FC_R2C>;
@@ -173,6 +179,10 @@ int launch_fast_r2c(const fc_pass& p, const void* in, void* out, const float2* t
   a.x = (const float*)in;
   a.out = (float2*)out;
   a.tw = tw;
+  {
+    static const int dbg = std::getenv("FFTCONV_B200_DBG") ? std::atoi(std::getenv("FFTCONV_B200_DBG")) : 0;
+    a.dbg = dbg;
+  }
   const size_t smem = ((size_t)FC_FAST_TR * p.M + (size_t)(p.M + 1) * (FC_FAST_TR + 1)) * sizeof(float2);
   int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(smem + 1024);
   int64_t grid = (int64_t)g_num_sms * (per_sm < 1 ? 1 : per_sm);

@@ -179,6 +179,7 @@ struct fc_fast_r2c_args {
   const float* x;
   float2* out;
   const float2* tw;
+  int32_t dbg;  // timing experiments only (FFTCONV_B200_DBG): 1 = skip the transform, 2 = skip the global stores
 };
 
 // Shared memory: TR lines of M float2 + a (M+1) x (TR+1) transposition tile.
@@ -194,25 +195,13 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
   const int tstep = p.tw_len / (2 * M);
   fc_wofs ofs;
   ofs.init(lane);
-  for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+  // Software pipeline over the tiles of this CTA: the rows of tile t+1 are requested (into the registers the
+  // transform has just released) before tile t is stored, so the load latency overlaps the transposed store.
+  auto load_rows = [&](int64_t t, float2 (&v)[NL][E]) {
     const int64_t o = t / p.tiles_per_outer;
     const int64_t r0 = (t - o * p.tiles_per_outer) * TR;
     const int64_t o1 = o / p.o_c2, o2 = o - o1 * p.o_c2;
     const int64_t base = (o1 / p.o_q) * p.o_sA + (o1 % p.o_q) * p.o_sB + o2 * p.o_sC;
-    {  // L2 prefetch of the next tile of this CTA: its TR rows are one contiguous run of TR*in_rs floats
-      const int64_t tn = t + gridDim.x;
-      if (tn < p.n_tiles) {
-        const int64_t on = tn / p.tiles_per_outer;
-        const int64_t rn = (tn - on * p.tiles_per_outer) * TR;
-        const int64_t on1 = on / p.o_c2, on2 = on - on1 * p.o_c2;
-        const int64_t bn = (on1 / p.o_q) * p.o_sA + (on1 % p.o_q) * p.o_sB + on2 * p.o_sC + rn * p.in_rs;
-        int64_t rows = p.R - rn;
-        if (rows > TR) rows = TR;
-        const int64_t span = rows * p.in_rs;  // floats
-        for (int64_t e = (int64_t)tid * 32; e < span; e += FC_FAST_WARPS * 32 * 32) fc_prefetch_l2(a.x + bn + e);
-      }
-    }
-    float2 v[NL][E];
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       const int64_t r = r0 + NL * w + l;
@@ -220,18 +209,18 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
       const float* row = a.x + base + (valid ? r : 0) * p.in_rs;
 #pragma unroll
       for (int q = 0; q < E; ++q) {
-        const int i0 = 2 * (lane + 32 * q);
-        float2 val = make_float2(0.f, 0.f);
-        if (valid) {
-          if (i0 + 1 < L)
-            val = __ldg(reinterpret_cast<const float2*>(row + i0));
-          else if (i0 < L)
-            val.x = __ldg(row + i0);
-        }
-        v[l][q] = val;
+        const int i0 = 2 * (lane + 32 * q);  // L is even (host check), so the pair (i0, i0 + 1) is in or out together
+        v[l][q] = (valid && i0 < L) ? __ldg(reinterpret_cast<const float2*>(row + i0)) : make_float2(0.f, 0.f);
       }
     }
-    fc_wfft<M, NL, M>(v, line0, ofs, a.tw, p.tw_len, lane);
+  };
+  float2 v[NL][E];
+  if ((int64_t)blockIdx.x < p.n_tiles) load_rows(blockIdx.x, v);
+  for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+    const int64_t o = t / p.tiles_per_outer;
+    const int64_t r0 = (t - o * p.tiles_per_outer) * TR;
+    const int64_t tn = t + gridDim.x;
+    if (a.dbg != 1) fc_wfft<M, NL, M>(v, line0, ofs, a.tw, p.tw_len, lane);
     fc_wwrite<M, NL, M>(v, line0, ofs);
     FC_SYNCWARP();
     // untangle the packed real transforms (same algebra as the generic R2C pass)
@@ -257,9 +246,24 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
       }
     }
     __syncthreads();
+    if (tn < p.n_tiles) {
+      load_rows(tn, v);  // in flight during the store below
+      // and pull the tile after that one into L2: its TR rows are one contiguous run of TR*in_rs floats
+      const int64_t t2 = tn + gridDim.x;
+      if (t2 < p.n_tiles) {
+        const int64_t on = t2 / p.tiles_per_outer;
+        const int64_t rn = (t2 - on * p.tiles_per_outer) * TR;
+        const int64_t on1 = on / p.o_c2, on2 = on - on1 * p.o_c2;
+        const int64_t bn = (on1 / p.o_q) * p.o_sA + (on1 % p.o_q) * p.o_sB + on2 * p.o_sC + rn * p.in_rs;
+        int64_t rows = p.R - rn;
+        if (rows > TR) rows = TR;
+        const int64_t span = rows * p.in_rs;  // floats
+        for (int64_t e = (int64_t)tid * 32; e < span; e += FC_FAST_WARPS * 32 * 32) fc_prefetch_l2(a.x + bn + e);
+      }
+    }
     for (int idx = tid; idx < (M + 1) * TR; idx += FC_FAST_WARPS * 32) {
       const int l = idx & (TR - 1), k = idx >> 4;
-      if (r0 + l < p.R) a.out[o * p.out_os + (int64_t)k * p.out_es + r0 + l] = tile[k * TP + l];
+      if (r0 + l < p.R && a.dbg != 2) a.out[o * p.out_os + (int64_t)k * p.out_es + r0 + l] = tile[k * TP + l];
     }
     __syncthreads();
   }
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
   float2* tile = smem + TR * M;
   const int tstep = p.tw_len / (2 * M);
   const fc_omap om = p.omap;
-  const bool plain_out = om.os == 1 && om.ob == 0 && om.og == 1 && !(om.Lout & 1) && !(p.out_rs & 1) && !(p.out_os & 1);
+  const bool plain_out = om.os == 1 && om.ob == 0 && om.og == 1 && !(om.Lout & 1) && !(p.out_rs & 1) && !(p.out_os & 1) && p.row_og == 1;
   fc_wofs ofs;
   ofs.init(lane);
   for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
@@ -342,16 +346,20 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
       for (int l = 0; l < NL; ++l) {
         const int64_t r = r0 + NL * w + l;
         if (r >= p.R) continue;
-        float* yrow = a.out + o * p.out_os + r * p.out_rs;
         const float* rl = reinterpret_cast<const float*>(line0 + l * M);
-        for (int n = lane; n < 2 * M; n += 32) {
-          const float val = rl[n];
-          for (int e = 0; e < om.og; ++e) {
-            const int tt = n * om.og + e - om.ob;
-            if (tt < 0 || (tt % om.os)) continue;
-            const int j = tt / om.os;
-            if (j >= om.Lout) continue;
-            yrow[j] = ((e == 0 && n < om.lim) ? val : 0.f) + b;
+        for (int er = 0; er < p.row_og; ++er) {  // output rows owned by this dense line (one unless row lattice)
+          const int64_t jr = r * p.row_og + er - p.row_ob;
+          if (jr < 0 || jr >= p.row_Lout) continue;
+          float* yrow = a.out + o * p.out_os + jr * p.out_rs;
+          for (int n = lane; n < 2 * M; n += 32) {
+            const float val = rl[n];
+            for (int e = 0; e < om.og; ++e) {
+              const int tt = n * om.og + e - om.ob;
+              if (tt < 0 || (tt % om.os)) continue;
+              const int j = tt / om.os;
+              if (j >= om.Lout) continue;
+              yrow[j] = ((e == 0 && er == 0 && n < om.lim) ? val : 0.f) + b;
+            }
           }
         }
       }

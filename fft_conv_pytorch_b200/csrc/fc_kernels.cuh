@@ -20,8 +20,27 @@
 
 // ------------------------------------------------------------------------------------------------ complex helpers
 FC_DEV float2 fc_c(float x, float y) { return make_float2(x, y); }
+#if defined(FC_CPU_EMUL) || !defined(FC_PACKED_F32X2)
 FC_DEV float2 fc_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 FC_DEV float2 fc_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#else
+// Blackwell packed fp32: one FADD2 adds both components of a complex number (halves the issue slots of the
+// add/sub-dominated butterflies). Same IEEE result as two scalar adds.
+FC_DEV float2 fc_add(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+FC_DEV float2 fc_sub(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+#endif
 FC_DEV float2 fc_mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 FC_DEV float2 fc_conj(float2 a) { return make_float2(a.x, -a.y); }
 FC_DEV float2 fc_mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
@@ -441,13 +460,18 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
         const float val = (n & 1) ? -z.y : z.x;
         const float b = p.has_bias ? __ldg(a.bias + li.bias_idx) : 0.f;
         const int64_t u = (int64_t)n * p.pos_n + li.r * p.pos_r;
-        for (int e = 0; e < om.og; ++e) {
-          const int64_t t = u * om.og + e - om.ob;
-          if (t < 0 || (t % om.os)) continue;
-          const int64_t j = t / om.os;
-          if (j >= om.Lout) continue;
-          const bool live = (e == 0) && (u < om.lim);
-          y[li.out_base + j * p.out_es] = (live ? val : 0.f) + b;
+        for (int er = 0; er < p.row_og; ++er) {  // output rows owned by this dense line (one unless row lattice)
+          const int64_t jr = li.r * p.row_og + er - p.row_ob;
+          if (p.row_og > 1 && (jr < 0 || jr >= p.row_Lout)) continue;
+          float* yrow = y + li.out_base + (p.row_og > 1 ? (jr - li.r) * p.out_rs : 0);
+          for (int e = 0; e < om.og; ++e) {
+            const int64_t t = u * om.og + e - om.ob;
+            if (t < 0 || (t % om.os)) continue;
+            const int64_t j = t / om.os;
+            if (j >= om.Lout) continue;
+            const bool live = (e == 0) && (er == 0) && (u < om.lim);
+            yrow[j * p.out_es] = (live ? val : 0.f) + b;
+          }
         }
       }
     }

@@ -92,6 +92,7 @@ fc_pass blank_pass(int kind, int N, int tw_len) {
   p.o_c2 = 1;
   p.o_q = 1;
   p.twN = 1;
+  p.row_og = 1;
   p.imap = identity_imap(N);
   p.omap = identity_omap(N);
   return p;
@@ -282,6 +283,7 @@ void build_inverse(const fc_plan& pl, std::vector<fc_step>& out) {
     p.omap = a.omap;
     p.cout = pl.prob.cout;
     p.has_bias = has_bias;
+    if (!p.row_Lout) p.row_Lout = (int32_t)p.R;
     finish_pass(p);
     out.push_back({p, FC_BUF_SPEC, FC_BUF_USER_OUT});
   } else if (pl.structure == FC_S_1D_SPLIT) {
@@ -321,10 +323,16 @@ void build_inverse(const fc_plan& pl, std::vector<fc_step>& out) {
     p.omap = a.omap;
     p.cout = pl.prob.cout;
     p.has_bias = has_bias;
+    if (!p.row_Lout) p.row_Lout = (int32_t)p.R;
     finish_pass(p);
     out.push_back({p, FC_BUF_SA, FC_BUF_USER_OUT});
   } else if (pl.structure == FC_S_2D) {
     const fc_axis &ay = pl.ax[0], &ax = pl.ax[1];
+    // Rows of a polyphase-reduced transposed convolution: only every og-th output row carries data. The inverse
+    // pass over y keeps the dense rows only (D0 of them) and the C2R pass scatters each to its output row and
+    // fills the og-1 bias-only rows it owns.
+    const bool row_lattice = ay.omap.og > 1;
+    const int D0 = row_lattice ? (ay.Lout - 1 + ay.omap.ob) / ay.omap.og + 1 : ay.Lout;
     fc_pass q = blank_pass(FC_C2C_INV, ay.N, tw);
     q.n_outer = n_outer;
     q.R = ax.Nk;
@@ -333,18 +341,24 @@ void build_inverse(const fc_plan& pl, std::vector<fc_step>& out) {
     q.in_rs = ay.N;
     q.in_es = 1;
     q.n_in = ay.N;
-    q.n_out = ay.Lout;
-    q.out_os = (int64_t)ax.Nk * ay.Lout;  // [o][kx][jy]
-    q.out_rs = ay.Lout;
+    q.n_out = D0;
+    q.out_os = (int64_t)ax.Nk * D0;  // [o][kx][jy]
+    q.out_rs = D0;
     q.out_es = 1;
     q.omap = ay.omap;
+    if (row_lattice) {
+      q.omap.Lout = D0;
+      q.omap.os = 1;
+      q.omap.ob = 0;
+      q.omap.og = 1;
+    }
     finish_pass(q);
     out.push_back({q, FC_BUF_SPEC, FC_BUF_SA});
     fc_pass p = blank_pass(FC_C2R, ax.N, tw);
     p.n_outer = n_outer;
-    p.R = ay.Lout;
-    p.in_os = (int64_t)ax.Nk * ay.Lout;
-    p.in_es = ay.Lout;
+    p.R = D0;
+    p.in_os = (int64_t)ax.Nk * D0;
+    p.in_es = D0;
     p.in_rs = 1;
     p.in_rfast = 1;
     p.n_in = ax.Nk;
@@ -355,6 +369,11 @@ void build_inverse(const fc_plan& pl, std::vector<fc_step>& out) {
     p.omap = ax.omap;
     p.cout = pl.prob.cout;
     p.has_bias = has_bias;
+    p.row_Lout = ay.Lout;
+    if (row_lattice) {
+      p.row_og = ay.omap.og;
+      p.row_ob = ay.omap.ob;
+    }
     finish_pass(p);
     out.push_back({p, FC_BUF_SA, FC_BUF_USER_OUT});
   } else {
@@ -404,6 +423,7 @@ void build_inverse(const fc_plan& pl, std::vector<fc_step>& out) {
     p.omap = ax.omap;
     p.cout = pl.prob.cout;
     p.has_bias = has_bias;
+    if (!p.row_Lout) p.row_Lout = (int32_t)p.R;
     finish_pass(p);
     out.push_back({p, FC_BUF_SB, FC_BUF_USER_OUT});
   }
@@ -632,7 +652,10 @@ const char* kKindName[] = {"r2c", "c2c_fwd", "c2c_inv", "c2r"};
 int64_t pass_bytes(const fc_pass& p) {
   const int64_t lines = p.n_outer * p.R;
   const int64_t in_el = (p.kind == FC_R2C) ? 4 : 8, out_el = (p.kind == FC_C2R) ? 4 : 8;
-  return lines * ((int64_t)p.n_in * in_el + (int64_t)p.n_out * out_el);
+  // four-step 1-d layout: the real side of the R2C / C2R pass is one tensor of n_in / n_out elements per outer item
+  const int64_t in_b = (p.kind == FC_R2C && p.pos_r) ? p.n_outer * (int64_t)p.imap.L * in_el : lines * (int64_t)p.n_in * in_el;
+  const int64_t out_b = (p.kind == FC_C2R && p.pos_r) ? p.n_outer * (int64_t)p.omap.Lout * out_el : lines * (int64_t)p.n_out * out_el;
+  return in_b + out_b;
 }
 
 bool fast_line_len(int M) { return M == 256 || M == 512; }
@@ -675,7 +698,7 @@ void fc_plan_build_program(fc_plan* pl) {
     std::memset(&L.fused, 0, sizeof(L.fused));
     const fc_pass& p = L.pass;
     if (i == 0 && allow && !(flags & FC_FLAG_NO_FAST_R2C) && p.kind == FC_R2C && !p.in_rfast && p.out_rfast && !p.twiddle && fast_line_len(p.M) &&
-        p.imap.mode == FC_PAD_CONSTANT && p.imap.pad == 0 && p.imap.up == 1 && p.imap.sub == 1 && p.imap.ext == p.imap.L && !(p.in_rs & 1) &&
+        p.imap.mode == FC_PAD_CONSTANT && p.imap.pad == 0 && p.imap.up == 1 && p.imap.sub == 1 && p.imap.ext == p.imap.L && !(p.imap.L & 1) && !(p.in_rs & 1) &&
         !(p.o_sA & 1) && !(p.o_sB & 1) && !(p.o_sC & 1) && p.scale == 1.f && !p.conj_out && p.pos_n == 1 && p.pos_r == 0) {
       L.type = FC_L_FAST_R2C;
       retile16(L.pass);

@@ -58,6 +58,9 @@ struct fc_pass {
   int32_t tw_len;     // length of the twiddle table (power of two >= every N of the plan)
   int32_t cout;       // C2R: bias index = outer % cout
   int32_t has_bias;
+  // C2R: lattice on the line (row) index: dense line r owns the output rows j with (j + row_ob) / row_og == r; only
+  // the row with (j + row_ob) % row_og == 0 carries data, the others are bias only (polyphase-reduced transposed conv)
+  int32_t row_og, row_ob, row_Lout;
   float scale;        // forward passes: multiply on store (1/prod(N) folded into the kernel spectrum)
   int64_t twN;        // four-step twiddle modulus
   int64_t n_outer;

@@ -133,3 +133,22 @@ def test_fast_kernels_one_at_a_time():
                L.FC_FLAG_NO_FAST_R2C | L.FC_FLAG_NO_FAST_C2R):
         y1, p = emul.conv(x, w, None, threads=256, flags=fl)
         assert rel_err(y1, y0) < 2e-6, fl
+
+
+def test_fast_kernels_transposed_row_lattice():
+    """stride = dilation = 2 transposed conv at sizes that select the warp-FFT kernels: polyphase reduction keeps
+    only the dense rows between the passes; the C2R kernel scatters them and fills the bias-only rows."""
+    from oracle import fftconv_oracle as O
+
+    rng = np.random.RandomState(13)
+    x = rng.standard_normal((2, 4, 130, 400)).astype(np.float32)
+    w = rng.standard_normal((4, 3, 3, 5)).astype(np.float32)
+    b = rng.standard_normal(6).astype(np.float32)
+    kw = dict(stride=2, dilation=2, padding=(1, 0), output_padding=(1, 0), groups=2)
+    ref = O.fft_conv_transpose(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), **kw)
+    y, p = emul.conv(x, w, b, transposed=True, threads=256, **kw)
+    assert "fast_c2r" in p.describe() and "fused_axis" in p.describe()
+    assert y.shape == ref.shape and not np.isnan(y).any()
+    assert rel_err(y, ref) < 1e-5
+    y2, _ = emul.conv(x, w, b, transposed=True, threads=256, flags=L.FC_FLAG_NO_FUSED, **kw)
+    assert rel_err(y2, ref) < 1e-5
