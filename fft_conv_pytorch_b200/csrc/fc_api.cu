@@ -148,26 +148,56 @@ int launch_contract(const float2* X, const float2* K, float2* Y, int64_t bins, i
   a.cout = cout;
   a.groups = groups;
   const int Og = cout / groups;
-  const int threads = 128;
-  const unsigned gx = (unsigned)((bins + threads - 1) / threads);
-  if (batch >= 5 && Og >= 5) {
+  static const char* ctile = std::getenv("FFTCONV_B200_CTILE");  // timing experiments: "tb,to,bx,by"
+  if (ctile) {
+    int tb = 8, to = 8, bx = 128, by = 1;
+    std::sscanf(ctile, "%d,%d,%d,%d", &tb, &to, &bx, &by);
+    a.btiles = (batch + tb - 1) / tb;
+    a.otiles = (Og + to - 1) / to;
+    dim3 b(bx, by), g((unsigned)((bins + bx - 1) / bx), (unsigned)(a.btiles * ((a.otiles + by - 1) / by)), (unsigned)groups);
+    if (tb == 16 && to == 4) {
+      auto k = fc_contract_kernel<16, 4>;
+      FC_LAUNCH(k, g, b, 0, st, a);
+    } else if (tb == 8 && to == 8) {
+      auto k = fc_contract_kernel<8, 8>;
+      FC_LAUNCH(k, g, b, 0, st, a);
+    } else if (tb == 16 && to == 2) {
+      auto k = fc_contract_kernel<16, 2>;
+      FC_LAUNCH(k, g, b, 0, st, a);
+    } else {
+      auto k = fc_contract_kernel<4, 4>;
+      FC_LAUNCH(k, g, b, 0, st, a);
+    }
+  } else if (batch >= 5 && Og >= 32) {
+    // wide channels (BASELINE c4): 4 output tiles per CTA read the same signal spectrum (L1 hits for 3 of them)
     a.btiles = (batch + 7) / 8;
     a.otiles = (Og + 7) / 8;
-    dim3 g(gx, (unsigned)(a.btiles * a.otiles), (unsigned)groups), b(threads);
+    const int oy = 4;
+    dim3 b(32, oy), g((unsigned)((bins + 31) / 32), (unsigned)(a.btiles * ((a.otiles + oy - 1) / oy)), (unsigned)groups);
     auto k = fc_contract_kernel<8, 8>;
     FC_LAUNCH(k, g, b, 0, st, a);
-  } else if (batch >= 3 || Og >= 3) {
-    a.btiles = (batch + 3) / 4;
-    a.otiles = (Og + 3) / 4;
-    dim3 g(gx, (unsigned)(a.btiles * a.otiles), (unsigned)groups), b(threads);
-    auto k = fc_contract_kernel<4, 4>;
-    FC_LAUNCH(k, g, b, 0, st, a);
   } else {
-    a.btiles = (batch + 1) / 2;
-    a.otiles = (Og + 1) / 2;
-    dim3 g(gx, (unsigned)(a.btiles * a.otiles), (unsigned)groups), b(threads);
-    auto k = fc_contract_kernel<2, 2>;
-    FC_LAUNCH(k, g, b, 0, st, a);
+    const int threads = 128;
+    const unsigned gx = (unsigned)((bins + threads - 1) / threads);
+    if (batch >= 5 && Og >= 5) {
+      a.btiles = (batch + 7) / 8;
+      a.otiles = (Og + 7) / 8;
+      dim3 g(gx, (unsigned)(a.btiles * a.otiles), (unsigned)groups), b(threads);
+      auto k = fc_contract_kernel<8, 8>;
+      FC_LAUNCH(k, g, b, 0, st, a);
+    } else if (batch >= 3 || Og >= 3) {
+      a.btiles = (batch + 3) / 4;
+      a.otiles = (Og + 3) / 4;
+      dim3 g(gx, (unsigned)(a.btiles * a.otiles), (unsigned)groups), b(threads);
+      auto k = fc_contract_kernel<4, 4>;
+      FC_LAUNCH(k, g, b, 0, st, a);
+    } else {
+      a.btiles = (batch + 1) / 2;
+      a.otiles = (Og + 1) / 2;
+      dim3 g(gx, (unsigned)(a.btiles * a.otiles), (unsigned)groups), b(threads);
+      auto k = fc_contract_kernel<2, 2>;
+      FC_LAUNCH(k, g, b, 0, st, a);
+    }
   }
   rec_mark();
   return check_cuda("contraction launch");

@@ -122,11 +122,12 @@ FC_DEV void fc_butterfly<8>(float2* v) {
 // Ns = product of the radices already applied. tw is the table exp(-2*pi*i*j/tw_len).
 template <int R>
 FC_DEV void fc_fft_stage(const float2* in, float2* out, int M, int Ns, int T, int pitch, const float2* tw, int tw_len) {
-  const int per = M / R;  // butterflies per line
+  const int per = M / R;  // butterflies per line (a power of two)
+  const int lper = 31 - __clz(per);
   const int total = T * per;
   const int tw_step = tw_len / (Ns * R);
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int line = idx / per;
+    const int line = idx >> lper;
     const int j = idx - line * per;
     const int k = j & (Ns - 1);
     const float2* src = in + line * pitch;
@@ -218,6 +219,12 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
 
   const int T = p.T, M = p.M, N = p.N, pitch = p.pitch;
   const int tid = threadIdx.x, nth = blockDim.x;
+  const int lN = 31 - __clz(N), lM = 31 - __clz(M);
+  // idx / (M + 1) for idx < 2^20 through a multiply-high: ceil(2^32 / W) is exact there because W <= 4097
+  const unsigned rW = (unsigned)((0x100000000ull + (unsigned)M) / (unsigned)(M + 1));
+  (void)lN;
+  (void)lM;
+  (void)rW;
 
   for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     // ---- line bookkeeping
@@ -261,8 +268,8 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
           l = idx & (T - 1);
           n = idx >> p.log2T;
         } else {
-          l = idx / N;
-          n = idx - l * N;
+          l = idx >> lN;
+          n = idx & (N - 1);
         }
         const fc_line_info li = lines[l];
         float val = 0.f;
@@ -282,8 +289,8 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
           l = idx & (T - 1);
           n = idx >> p.log2T;
         } else {
-          l = idx / N;
-          n = idx - l * N;
+          l = idx >> lN;
+          n = idx & (N - 1);
         }
         const fc_line_info li = lines[l];
         float2 val = make_float2(0.f, 0.f);
@@ -302,8 +309,8 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
           l = idx & (T - 1);
           n = idx >> p.log2T;
         } else {
-          l = idx / N;
-          n = idx - l * N;
+          l = idx >> lN;
+          n = idx & (N - 1);
         }
         const fc_line_info li = lines[l];
         float2 val = make_float2(0.f, 0.f);
@@ -320,7 +327,7 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
           l = idx & (T - 1);
           k = idx >> p.log2T;
         } else {
-          l = idx / W;
+          l = (int)__umulhi((unsigned)idx, rW);
           k = idx - l * W;
         }
         const fc_line_info li = lines[l];
@@ -344,8 +351,8 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
       const int total = T * M;
       const int tstep = p.tw_len / N;
       for (int idx = tid; idx < total; idx += nth) {
-        const int l = idx / M;
-        const int k = idx - l * M;
+        const int l = idx >> lM;
+        const int k = idx & (M - 1);
         const float2 yk = bufA[l * pitch + k];
         const float2 ym = fc_conj(bufA[l * pitch + (M - k)]);
         const float2 s = fc_add(yk, ym);
@@ -367,7 +374,7 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
       const int total = T * W;
       const int tstep = p.tw_len / N;
       for (int idx = tid; idx < total; idx += nth) {
-        const int l = idx / W;
+        const int l = (int)__umulhi((unsigned)idx, rW);
         const int k = idx - l * W;
         const float2 zk = res[l * pitch + fc_swz(k & (M - 1))];
         const float2 zc = fc_conj(res[l * pitch + fc_swz((M - k) & (M - 1))]);
@@ -383,7 +390,7 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
           l = idx & (T - 1);
           k = idx >> p.log2T;
         } else {
-          l = idx / W;
+          l = (int)__umulhi((unsigned)idx, rW);
           k = idx - l * W;
         }
         const fc_line_info li = lines[l];
@@ -406,8 +413,8 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
           l = idx & (T - 1);
           k = idx >> p.log2T;
         } else {
-          l = idx / N;
-          k = idx - l * N;
+          l = idx >> lN;
+          k = idx & (N - 1);
         }
         const fc_line_info li = lines[l];
         if (!li.valid) continue;
@@ -425,8 +432,8 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
           l = idx & (T - 1);
           n = idx >> p.log2T;
         } else {
-          l = idx / N;
-          n = idx - l * N;
+          l = idx >> lN;
+          n = idx & (N - 1);
         }
         const fc_line_info li = lines[l];
         if (!li.valid) continue;
@@ -451,8 +458,8 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
           l = idx & (T - 1);
           n = idx >> p.log2T;
         } else {
-          l = idx / N;
-          n = idx - l * N;
+          l = idx >> lN;
+          n = idx & (N - 1);
         }
         const fc_line_info li = lines[l];
         if (!li.valid) continue;
@@ -481,7 +488,8 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
 
 // ------------------------------------------------------------------------------------------------ contraction
 // Y[b, g*Og + o, f] = sum_i X[b, g*Ig + i, f] * K[g*Og + o, i, f]      (reference complex_matmul, functional.py:11-16)
-// One thread per frequency bin (coalesced 8-byte accesses), a TB x TO register tile of outputs per thread.
+// One thread per frequency bin (coalesced 8-byte accesses), a TB x TO register tile of outputs per thread; wide
+// channel counts put several output tiles into one CTA so that they share the signal spectrum through L1.
 struct fc_contract_args {
   const float2* X;
   const float2* K;
@@ -493,11 +501,16 @@ struct fc_contract_args {
 
 template <int TB, int TO>
 __global__ void fc_contract_kernel(fc_contract_args a) {
+  // blockDim = (bins, output-channel tiles): the tiles of one CTA read the same signal spectrum, which then comes
+  // from L1 for all but the first of them
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= a.bins) return;
   const int Ig = a.cin / a.groups, Og = a.cout / a.groups;
   const int g = blockIdx.z;
-  const int bt = blockIdx.y / a.otiles, ot = blockIdx.y - bt * a.otiles;
+  const int oblocks = (a.otiles + blockDim.y - 1) / blockDim.y;
+  const int bt = blockIdx.y / oblocks;
+  const int ot = (blockIdx.y - bt * oblocks) * blockDim.y + threadIdx.y;
+  if (ot >= a.otiles) return;
   const int b0 = bt * TB, o0 = ot * TO;
   float2 acc[TB][TO];
 #pragma unroll

@@ -12,10 +12,10 @@ static std::barrier<>* g_barrier = nullptr;
 static std::vector<std::unique_ptr<std::barrier<>>> g_warp_barriers;
 
 void __syncthreads() { g_barrier->arrive_and_wait(); }
-void __syncwarp() { g_warp_barriers[threadIdx.x / 32]->arrive_and_wait(); }
+void __syncwarp() { g_warp_barriers[(threadIdx.y * blockDim.x + threadIdx.x) / 32]->arrive_and_wait(); }
 
 void fc_emul_launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body) {
-  const unsigned nt = block.x;
+  const unsigned nt = block.x * block.y;
   std::vector<char> shared(smem + 64);
   fc_emul_smem = shared.data();
   std::barrier<> bar((std::ptrdiff_t)nt);
@@ -31,7 +31,7 @@ void fc_emul_launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bo
     th.emplace_back([=, &body]() {
       blockDim = block;
       gridDim = grid;
-      threadIdx = dim3(t, 0, 0);
+      threadIdx = dim3(t % block.x, t / block.x, 0);
       for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
           for (unsigned bx = 0; bx < grid.x; ++bx) {

@@ -152,3 +152,19 @@ def test_fast_kernels_transposed_row_lattice():
     assert rel_err(y, ref) < 1e-5
     y2, _ = emul.conv(x, w, b, transposed=True, threads=256, flags=L.FC_FLAG_NO_FUSED, **kw)
     assert rel_err(y2, ref) < 1e-5
+
+
+@pytest.mark.parametrize("xs,ws,groups", [((10, 40, 70), (36, 40, 5), 1), ((17, 70, 40), (66, 35, 3), 2)])
+def test_wide_channel_contraction_tiling(xs, ws, groups):
+    """>= 32 output channels per group select the layout with several output tiles per CTA (BASELINE c4's
+    contraction); ragged batch / channel tails included."""
+    from oracle import fftconv_oracle as O
+
+    rng = np.random.RandomState(14)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = rng.standard_normal(ws).astype(np.float32)
+    b = rng.standard_normal(ws[0]).astype(np.float32)
+    y, _ = emul.conv(x, w, b, threads=64, groups=groups)
+    ref = O.fft_conv(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), groups=groups)
+    assert not np.isnan(y).any()
+    assert rel_err(y, ref) < 1e-5
