@@ -83,6 +83,10 @@ SYMBOLS = {
     "fc_conv_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fc_conv_profiled": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "fc_plan_launch_info": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int64)]),
+    "fc_tc_supported": (ctypes.c_int, [ctypes.c_int64] * 4),
+    "fc_tc_scratch_bytes": (ctypes.c_int64, [ctypes.c_int64] * 5),
+    "fc_tc_prepare_kernel": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _P]),
+    "fc_tc_complex_matmul": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _P]),
     "fc_complex_matmul": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _P]),
 }
 

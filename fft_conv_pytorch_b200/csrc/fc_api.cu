@@ -10,6 +10,7 @@
 
 #include "fc_kernels.cuh"
 #include "fc_fused.cuh"
+#include "fc_tc.cuh"
 #include "fc_plan.h"
 
 #ifdef FC_CPU_EMUL
@@ -87,6 +88,8 @@ void init_once() {
     cudaFuncSetAttribute(fc_fast_c2r_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(fc_fast_c2r_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     fused_set_attr();
+    cudaFuncSetAttribute(fc_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(fc_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     cudaGetLastError();
 #endif
   });
@@ -302,6 +305,63 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
   return check_cuda("fused axis launch");
 }
 
+// ---- tensor-core contraction (fc_tc.cuh)
+int tc_padded_batch(int batch) { return batch <= 8 ? 8 : (batch + 7) / 8 * 8; }
+bool tc_supported(int batch, int cin, int cout, int groups) {
+  const int I = cin / groups, O = cout / groups;
+  return I >= 32 && (2 * I) % 32 == 0 && O % 128 == 0 && tc_padded_batch(batch) <= 32;
+}
+
+int launch_tc_relayout(int mode, const void* in, void* out, int64_t bins, int batch, int cin, int cout, int groups, cudaStream_t st) {
+  fc_tc_relayout_args a;
+  a.in = (const float2*)in;
+  a.out = (float*)out;
+  a.bins = bins;
+  a.I = cin / groups;
+  a.C = cin;
+  a.O = cout;
+  a.B = batch;
+  a.Bp = tc_padded_batch(batch);
+  a.mode = mode;
+  a.rows = mode == 0 ? cout * a.I : (mode == 1 ? batch * cin : cout * a.Bp);
+  dim3 g((unsigned)((bins + 31) / 32), (unsigned)((a.rows + 31) / 32)), b(256);
+  auto k = fc_tc_relayout_kernel;
+  FC_LAUNCH(k, g, b, 0, st, a);
+  rec_mark();
+  return check_cuda("tc relayout launch");
+}
+
+int launch_tc_gemm(const float* A, const float* Bt, float* D, int64_t bins, int batch, int cin, int cout, int groups, cudaStream_t st) {
+#ifdef FC_CPU_EMUL
+  (void)A; (void)Bt; (void)D; (void)bins; (void)batch; (void)cin; (void)cout; (void)groups; (void)st;
+  return set_err(FC_EUNSUPPORTED, "tensor-core contraction is not available in the host emulation");
+#else
+  fc_tc_args a;
+  a.A = A;
+  a.Bt = Bt;
+  a.D = D;
+  a.n_items = bins * groups;
+  a.O = cout / groups;
+  a.I = cin / groups;
+  a.B = tc_padded_batch(batch);
+  const int N = 2 * a.B;
+  const int MT = (a.O % 256 == 0) ? 2 : 1;
+  const size_t stage = (size_t)2 * MT * 128 * 128 + 2 * (((size_t)N * 128 + 1023) & ~(size_t)1023);
+  const size_t smem = FC_TC_STAGES * stage + 1024;
+  int64_t grid = a.n_items < g_num_sms ? a.n_items : g_num_sms;
+  dim3 g((unsigned)grid), b(256);
+  if (MT == 2) {
+    auto k = fc_tc_gemm_kernel<2>;
+    k<<<g, b, smem, st>>>(a);
+  } else {
+    auto k = fc_tc_gemm_kernel<1>;
+    k<<<g, b, smem, st>>>(a);
+  }
+  rec_mark();
+  return check_cuda("tc gemm launch");
+#endif
+}
+
 // Resolve a buffer id of a step to a pointer.
 struct Bufs {
   const void* user_in;
@@ -497,6 +557,42 @@ int fc_plan_launch_info(const fc_plan* plan, int i, char* name, size_t namelen, 
   name[n] = 0;
   *algo_bytes = L.bytes;
   return FC_OK;
+}
+
+int fc_tc_supported(int64_t batch, int64_t cin, int64_t cout, int64_t groups) {
+  return tc_supported((int)batch, (int)cin, (int)cout, (int)groups) ? 1 : 0;
+}
+
+int64_t fc_tc_scratch_bytes(int64_t batch, int64_t cin, int64_t cout, int64_t groups, int64_t bins) {
+  const int64_t bp = tc_padded_batch((int)batch), I = cin / groups;
+  return (bins * groups * 2 * bp * 2 * I * 4 + 255) / 256 * 256 + bins * cout * 2 * bp * 4 + 512;
+}
+
+int fc_tc_prepare_kernel(const float* d_kspec, float* d_kspec_tc, int64_t cin, int64_t cout, int64_t groups, int64_t bins, void* stream) {
+  if (!d_kspec || !d_kspec_tc) return set_err(FC_ENULL, "fc_tc_prepare_kernel: NULL argument");
+  init_once();
+  return launch_tc_relayout(0, d_kspec, d_kspec_tc, bins, 1, (int)cin, (int)cout, (int)groups, (cudaStream_t)stream);
+}
+
+int fc_tc_complex_matmul(const float* d_a, const float* d_b_tc, float* d_y, void* d_scratch, int64_t batch, int64_t cin, int64_t cout,
+                         int64_t groups, int64_t bins, void* stream) {
+  if (!d_a || !d_b_tc || !d_y || !d_scratch) return set_err(FC_ENULL, "fc_tc_complex_matmul: NULL argument");
+  if (!tc_supported((int)batch, (int)cin, (int)cout, (int)groups)) return set_err(FC_EUNSUPPORTED, "fc_tc_complex_matmul: shape not supported");
+  init_once();
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t bp = tc_padded_batch((int)batch), I = cin / groups;
+  float* xtc = (float*)d_scratch;
+  const int64_t xtc_bytes = (bins * groups * 2 * bp * 2 * I * 4 + 255) / 256 * 256;
+  float* ytc = (float*)((char*)d_scratch + xtc_bytes);
+  if (bp != batch) {
+    cudaError_t e = cudaMemsetAsync(xtc, 0, (size_t)(bins * groups * 2 * bp * 2 * I * 4), st);
+    if (e != cudaSuccess) return set_err((int)e, "fc_tc_complex_matmul: memset failed");
+  }
+  int rc = launch_tc_relayout(1, d_a, xtc, bins, (int)batch, (int)cin, (int)cout, (int)groups, st);
+  if (rc) return rc;
+  rc = launch_tc_gemm(d_b_tc, xtc, ytc, bins, (int)batch, (int)cin, (int)cout, (int)groups, st);
+  if (rc) return rc;
+  return launch_tc_relayout(2, ytc, d_y, bins, (int)batch, (int)cin, (int)cout, (int)groups, st);
 }
 
 int fc_complex_matmul(const float* d_a, const float* d_b, float* d_y, int64_t batch, int64_t cin, int64_t cout, int64_t groups, int64_t bins,
