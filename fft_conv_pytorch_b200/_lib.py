@@ -16,6 +16,7 @@ FC_FLAG_NO_POLYPHASE = 2
 FC_FLAG_NO_FAST_R2C = 4
 FC_FLAG_NO_FAST_C2R = 8
 FC_FLAG_NO_FUSED_MID = 16
+FC_FLAG_NO_TC = 32
 
 _I3 = ctypes.c_int32 * FC_MAX_ND
 
@@ -61,6 +62,9 @@ class FcPlanInfo(ctypes.Structure):
         ("algo_bytes_s2", ctypes.c_int64),
         ("algo_bytes_s3", ctypes.c_int64),
         ("algo_bytes_s4", ctypes.c_int64),
+        ("kspec_workspace_bytes", ctypes.c_int64),
+        ("tensor_core", ctypes.c_int32),
+        ("reserved2", ctypes.c_int32),
     ]
 
 

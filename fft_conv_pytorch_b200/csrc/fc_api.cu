@@ -322,6 +322,8 @@ int launch_tc_relayout(int mode, const void* in, void* out, int64_t bins, int ba
   a.O = cout;
   a.B = batch;
   a.Bp = tc_padded_batch(batch);
+  a.Og = cout / groups;
+  a.MT = (a.Og % 256 == 0) ? 2 : 1;
   a.mode = mode;
   a.rows = mode == 0 ? cout * a.I : (mode == 1 ? batch * cin : cout * a.Bp);
   dim3 g((unsigned)((bins + 31) / 32), (unsigned)((a.rows + 31) / 32)), b(256);
@@ -346,10 +348,10 @@ int launch_tc_gemm(const float* A, const float* Bt, float* D, int64_t bins, int 
   a.B = tc_padded_batch(batch);
   const int N = 2 * a.B;
   const int MT = (a.O % 256 == 0) ? 2 : 1;
-  const size_t stage = (size_t)2 * MT * 128 * 128 + 2 * (((size_t)N * 128 + 1023) & ~(size_t)1023);
+  const size_t stage = (size_t)2 * MT * 128 * 128 + 2 * (size_t)N * 128;
   const size_t smem = FC_TC_STAGES * stage + 1024;
   int64_t grid = a.n_items < g_num_sms ? a.n_items : g_num_sms;
-  dim3 g((unsigned)grid), b(256);
+  dim3 g((unsigned)grid), b(288);
   if (MT == 2) {
     auto k = fc_tc_gemm_kernel<2>;
     k<<<g, b, smem, st>>>(a);
@@ -451,6 +453,16 @@ int fc_signal_spectrum(const fc_plan* plan, const void* d_const, const float* d_
 int fc_kernel_spectrum(const fc_plan* plan, const void* d_const, const float* d_w, float* d_kspec, void* d_ws, void* stream) {
   if (!plan || !d_const || !d_w || !d_kspec || !d_ws) return set_err(FC_ENULL, "fc_kernel_spectrum: NULL argument");
   init_once();
+  if (plan->use_tc) {
+    // pass-order spectrum into a temporary, then once into the bin-outermost planar layout of the tensor-core GEMM
+    const int64_t tmp_off = (plan->info.kspec_workspace_bytes - ((plan->info.kspec_bytes + 255) / 256 * 256)) / 256 * 256;
+    float* tmp = (float*)((char*)d_ws + tmp_off);
+    Bufs b{d_w, tmp, (char*)d_ws + plan->off_sA, (char*)d_ws + plan->off_sB, nullptr};
+    int rc = run_steps(plan, plan->ker_fwd, b, (const float2*)d_const, nullptr, (cudaStream_t)stream);
+    if (rc) return rc;
+    const fc_contract_desc& c = plan->contract;
+    return launch_tc_relayout(0, tmp, d_kspec, c.bins, 1, c.cin, c.cout, c.groups, (cudaStream_t)stream);
+  }
   Bufs b{d_w, d_kspec, (char*)d_ws + plan->off_sA, (char*)d_ws + plan->off_sB, nullptr};
   return run_steps(plan, plan->ker_fwd, b, (const float2*)d_const, nullptr, (cudaStream_t)stream);
 }
@@ -458,6 +470,7 @@ int fc_kernel_spectrum(const fc_plan* plan, const void* d_const, const float* d_
 int fc_contract(const fc_plan* plan, const float* d_xspec, const float* d_kspec, float* d_yspec, void* stream) {
   if (!plan || !d_xspec || !d_kspec || !d_yspec) return set_err(FC_ENULL, "fc_contract: NULL argument");
   init_once();
+  if (plan->use_tc) return set_err(FC_EUNSUPPORTED, "fc_contract: this plan keeps the kernel spectrum in the tensor-core layout; use fc_conv");
   const fc_contract_desc& c = plan->contract;
   return launch_contract((const float2*)d_xspec, (const float2*)d_kspec, (float2*)d_yspec, c.bins, c.batch, c.cin, c.cout, c.groups,
                          (cudaStream_t)stream);
@@ -495,6 +508,24 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
       case FC_L_CONTRACT: {
         const fc_contract_desc& c = plan->contract;
         rc = launch_contract((const float2*)xspec, (const float2*)d_kspec, (float2*)yspec, c.bins, c.batch, c.cin, c.cout, c.groups, st);
+      } break;
+      case FC_L_TC_X: {
+        const fc_contract_desc& c = plan->contract;
+        const int bp = tc_padded_batch(c.batch);
+        rc = FC_OK;
+        if (bp != c.batch) {
+          cudaError_t e = cudaMemsetAsync(ws + plan->off_xtc, 0, (size_t)(plan->off_ytc - plan->off_xtc), st);
+          if (e != cudaSuccess) rc = set_err((int)e, "tc operand memset failed");
+        }
+        if (!rc) rc = launch_tc_relayout(1, xspec, ws + plan->off_xtc, c.bins, c.batch, c.cin, c.cout, c.groups, st);
+      } break;
+      case FC_L_TC_GEMM: {
+        const fc_contract_desc& c = plan->contract;
+        rc = launch_tc_gemm(d_kspec, (const float*)(ws + plan->off_xtc), (float*)(ws + plan->off_ytc), c.bins, c.batch, c.cin, c.cout, c.groups, st);
+      } break;
+      case FC_L_TC_Y: {
+        const fc_contract_desc& c = plan->contract;
+        rc = launch_tc_relayout(2, ws + plan->off_ytc, yspec, c.bins, c.batch, c.cin, c.cout, c.groups, st);
       } break;
       default:
         rc = launch_fused(plan, L.fused, buf_ptr(b, L.src), (const float2*)d_kspec, buf_ptr(b, L.dst), tw, st);
@@ -565,7 +596,7 @@ int fc_tc_supported(int64_t batch, int64_t cin, int64_t cout, int64_t groups) {
 
 int64_t fc_tc_scratch_bytes(int64_t batch, int64_t cin, int64_t cout, int64_t groups, int64_t bins) {
   const int64_t bp = tc_padded_batch((int)batch), I = cin / groups;
-  return (bins * groups * 2 * bp * 2 * I * 4 + 255) / 256 * 256 + bins * cout * 2 * bp * 4 + 512;
+  return (bins * groups * 2 * bp * 2 * I * 4 * 2 + 255) / 256 * 256 + bins * cout * 2 * bp * 4 + 512;
 }
 
 int fc_tc_prepare_kernel(const float* d_kspec, float* d_kspec_tc, int64_t cin, int64_t cout, int64_t groups, int64_t bins, void* stream) {
@@ -582,10 +613,10 @@ int fc_tc_complex_matmul(const float* d_a, const float* d_b_tc, float* d_y, void
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t bp = tc_padded_batch((int)batch), I = cin / groups;
   float* xtc = (float*)d_scratch;
-  const int64_t xtc_bytes = (bins * groups * 2 * bp * 2 * I * 4 + 255) / 256 * 256;
+  const int64_t xtc_bytes = (bins * groups * 2 * bp * 2 * I * 4 * 2 + 255) / 256 * 256;
   float* ytc = (float*)((char*)d_scratch + xtc_bytes);
   if (bp != batch) {
-    cudaError_t e = cudaMemsetAsync(xtc, 0, (size_t)(bins * groups * 2 * bp * 2 * I * 4), st);
+    cudaError_t e = cudaMemsetAsync(xtc, 0, (size_t)(bins * groups * 2 * bp * 2 * I * 4 * 2), st);
     if (e != cudaSuccess) return set_err((int)e, "fc_tc_complex_matmul: memset failed");
   }
   int rc = launch_tc_relayout(1, d_a, xtc, bins, (int)batch, (int)cin, (int)cout, (int)groups, st);

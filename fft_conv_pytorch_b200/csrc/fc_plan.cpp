@@ -633,6 +633,28 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   pl->off_sB = align_up(pl->off_sA + sA, 256);
   pl->scratch_bytes = sA + sB;
   I.workspace_bytes = align_up(pl->off_sB + sB, 256) + 256;
+  // tensor-core contraction (fc_tc.cuh): wide channel groups, small batch
+  {
+    const int Og = P.cout / P.groups;
+    const int bp = P.batch <= 8 ? 8 : (P.batch + 7) / 8 * 8;
+    pl->use_tc = !(P.flags & (FC_FLAG_NO_TC | FC_FLAG_NO_FUSED)) && Ig >= 32 && (2 * Ig) % 32 == 0 && Og % 128 == 0 && bp <= 32;
+#ifdef FC_CPU_EMUL
+    pl->use_tc = 0;  // tcgen05 cannot run in the host emulation
+#endif
+    pl->off_xtc = pl->off_ytc = 0;
+    I.kspec_workspace_bytes = I.workspace_bytes;
+    if (pl->use_tc) {
+      pl->off_xtc = align_up(I.workspace_bytes, 256);
+      const int64_t xtc = bins * P.groups * 2 * bp * 2 * Ig * 4 * 2;  // hi and lo copies
+      pl->off_ytc = align_up(pl->off_xtc + xtc, 256);
+      const int64_t ytc = bins * P.cout * 2 * bp * 4;
+      I.workspace_bytes = align_up(pl->off_ytc + ytc, 256) + 256;
+      // building the cached kernel spectrum needs the pass-order spectrum as a temporary next to the usual scratch
+      I.kspec_workspace_bytes = align_up(pl->off_sB + sB, 256) + 256 + align_up(I.kspec_bytes, 256);
+      if (I.kspec_workspace_bytes < I.workspace_bytes) I.kspec_workspace_bytes = I.workspace_bytes;
+    }
+    I.tensor_core = pl->use_tc;
+  }
   I.const_bytes = (int64_t)tw_len * 8;
   I.n_launches = (int)(pl->sig_fwd.size() + 1 + pl->inv.size());
   I.n_launches_kspec = (int)pl->ker_fwd.size();
@@ -748,6 +770,22 @@ void fc_plan_build_program(fc_plan* pl) {
     L.bytes = 8 * ((int64_t)P.batch * P.cin * fs.pass.R * fs.pass.n_in + (int64_t)P.cout * Ig * fs.pass.R * fs.pass.N +
                    (int64_t)P.batch * P.cout * bs.pass.R * bs.pass.n_out);
     pl->prog.push_back(L);
+  } else if (pl->use_tc) {
+    const int bp = P.batch <= 8 ? 8 : (P.batch + 7) / 8 * 8;
+    const int64_t xtc = pl->info.bins * P.groups * 2 * bp * 2 * Ig * 4 * 2, ytc = pl->info.bins * P.cout * 2 * bp * 4;
+    const char* names[3] = {"tc_relayout_x", "tc_gemm_3xtf32", "tc_relayout_y"};
+    const int64_t bytes[3] = {pl->info.xspec_bytes + xtc, pl->info.kspec_bytes + xtc + ytc, ytc + pl->info.yspec_bytes};
+    for (int j = 0; j < 3; ++j) {
+      fc_launch L;
+      L.type = FC_L_TC_X + j;
+      std::memset(&L.pass, 0, sizeof(L.pass));
+      std::memset(&L.fused, 0, sizeof(L.fused));
+      L.src = L.dst = FC_BUF_SPEC;
+      L.spec_is_y = 0;
+      L.name = names[j];
+      L.bytes = bytes[j];
+      pl->prog.push_back(L);
+    }
   } else {
     fc_launch L;
     L.type = FC_L_CONTRACT;

@@ -22,7 +22,7 @@ struct fc_step {
 };
 
 // One kernel launch of fc_conv.
-enum { FC_L_PASS = 0, FC_L_FAST_R2C = 1, FC_L_FAST_C2R = 2, FC_L_CONTRACT = 3, FC_L_FUSED = 4 };
+enum { FC_L_PASS = 0, FC_L_FAST_R2C = 1, FC_L_FAST_C2R = 2, FC_L_CONTRACT = 3, FC_L_FUSED = 4, FC_L_TC_X = 5, FC_L_TC_GEMM = 6, FC_L_TC_Y = 7 };
 
 // Geometry of the fused "last forward axis -> contraction -> first inverse axis" kernel (fc_fused.cuh).
 struct fc_fused_desc {
@@ -72,6 +72,8 @@ struct fc_plan {
   fc_contract_desc contract;
   std::vector<fc_launch> prog;  // what fc_conv launches, in order
   int64_t off_xspec, off_yspec, off_sA, off_sB;
+  int64_t off_xtc, off_ytc;  // tensor-core contraction operands (use_tc)
+  int use_tc;
   int64_t scratch_bytes;
 };
 

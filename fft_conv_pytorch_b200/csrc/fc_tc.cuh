@@ -18,22 +18,32 @@
 #include "fc_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------ relayouts
-// in: [rows][bins] complex (bins contiguous)  ->  out per bin, see `mode`. One CTA moves a 32 x 32 tile through
-// shared memory so that both sides are coalesced.
-//   mode 0 (kernel spectrum): rows = (o, i);  out[f][o][0][i] = re, out[f][o][1][i] = im          (A rows)
-//   mode 1 (signal spectrum): rows = (b, i);  out[f][2b][i] = re, out[f][2b][I+i] = -im,
-//                                             out[f][2b+1][i] = im, out[f][2b+1][I+i] = re        (Bt rows)
-//   mode 2 (product, inverse direction): in: D[f][o][2B] (float pairs = complex Y[f][o][b]) -> out[(b*O + o)][f]
+// The GEMM operands live in HBM as the exact shared-memory images of the K-chunks the tensor core consumes
+// ("blobs"): a chunk is 32 consecutive fp32 of the K dimension (one 128-byte row per matrix row), rows in groups of 8
+// (1024 bytes), the eight 16-byte pieces of a row XOR-swizzled with the row index (UMMA SWIZZLE_128B, K-major). A
+// blob is contiguous, so one bulk async copy (cp.async.bulk) moves it into its pipeline stage at full DRAM efficiency.
+//   A blobs : [bin][group][pass][chunk] x (MT*128 rows x 32 fp32)          kernel spectrum, rows = output channels
+//   Bt blobs: [bin][group][chunk] x {hi, lo} x (N rows x 32 fp32)          signal spectrum, rows = (batch, re/im);
+//             hi = the raw value (the tensor core ignores the low 13 mantissa bits), lo = value - truncated value
+// One CTA of the relayout kernels moves a 32 x 32 (rows x bins) tile through shared memory so that the bin-innermost
+// side is coalesced; mode 2 brings the product D[bin][o][2*Bp] back to the pass-order layout [(b*Cout + o)][bin].
+FC_DEV int64_t fc_tc_swz_off(int r, int j) {  // float offset of (row r, fp32 column j < 32) inside a blob
+  return (int64_t)(r >> 3) * 256 + (r & 7) * 32 + ((((j >> 2) ^ (r & 7)) << 2) | (j & 3));
+}
+FC_DEV float fc_tc_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
 struct fc_tc_relayout_args {
   const float2* in;
   float* out;
   int64_t bins;
   int32_t I;     // input channels per group
-  int32_t C;     // mode 1: all input channels (G*I); mode 0 / 2: unused
+  int32_t C;     // all input channels (G*I)
   int32_t rows;  // mode 0: Cout*I, mode 1: B*Cin, mode 2: Cout*Bp (o-major, b inner)
-  int32_t O;     // mode 0 / 2: all output channels (G*O_g)
+  int32_t O;     // all output channels (G*Og)
+  int32_t Og;    // output channels per group
+  int32_t MT;    // 128-row tiles per pass (1 or 2)
   int32_t B;     // real batch
-  int32_t Bp;    // padded batch (N = 2*Bp columns per bin); rows b >= B of Bt must be zero-filled by the caller
+  int32_t Bp;    // padded batch (N = 2*Bp rows of Bt per bin); rows b >= B must be zero-filled by the caller
   int32_t mode;
 };
 
@@ -42,8 +52,8 @@ __global__ void fc_tc_relayout_kernel(fc_tc_relayout_args a) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
   const int64_t f0 = (int64_t)blockIdx.x * 32;
   const int r0 = blockIdx.y * 32;
+  const int KD = 2 * a.I, n_chunks = KD / 32;
   if (a.mode != 2) {
-    // read rows r0.. (bins contiguous), write per bin with the row index contiguous
     for (int j = ty; j < 32; j += 8) {
       const int r = r0 + j;
       const int64_t f = f0 + tx;
@@ -57,18 +67,28 @@ __global__ void fc_tc_relayout_kernel(fc_tc_relayout_args a) {
       const float2 v = tile[tx][j];
       if (a.mode == 0) {
         const int o = r / a.I, i = r - o * a.I;  // o over all groups
-        float* dst = a.out + ((int64_t)f * a.O + o) * (2 * a.I);
-        dst[i] = v.x;
-        dst[a.I + i] = v.y;
+        const int g = o / a.Og, og = o - g * a.Og;
+        const int G = a.O / a.Og, prow = a.MT * 128, passes = a.Og / prow;
+        const int pass = og / prow, row = og - pass * prow;
+        const int64_t blob = (((f * G + g) * passes + pass) * n_chunks);
+        // K column i holds re, column I + i holds im
+        a.out[(blob + (i >> 5)) * (prow * 32) + fc_tc_swz_off(row, i & 31)] = v.x;
+        a.out[(blob + ((a.I + i) >> 5)) * (prow * 32) + fc_tc_swz_off(row, (a.I + i) & 31)] = v.y;
       } else {
         const int b = r / a.C, c = r - b * a.C;
         const int g = c / a.I, i = c - g * a.I;
-        const int G = a.C / a.I;
-        float* dst = a.out + (((int64_t)f * G + g) * (2 * a.Bp) + 2 * b) * (2 * a.I);
-        dst[i] = v.x;
-        dst[a.I + i] = -v.y;
-        dst[2 * a.I + i] = v.y;
-        dst[3 * a.I + i] = v.x;
+        const int G = a.C / a.I, N = 2 * a.Bp;
+        const int64_t blob = (f * G + g) * n_chunks;
+        // rows 2b (-> Re Y) and 2b+1 (-> Im Y); columns i and I + i
+        const float vals[4] = {v.x, -v.y, v.y, v.x};
+        const int rows[4] = {2 * b, 2 * b, 2 * b + 1, 2 * b + 1};
+        const int cols[4] = {i, a.I + i, i, a.I + i};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float* dst = a.out + (blob + (cols[e] >> 5)) * (2 * N * 32) + fc_tc_swz_off(rows[e], cols[e] & 31);
+          dst[0] = vals[e];
+          dst[N * 32] = fc_tc_lo(vals[e]);
+        }
       }
     }
   } else {
@@ -113,6 +133,16 @@ FC_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+FC_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-d bulk async copy global -> shared (TMA engine, no tensor map); completion is counted in bytes on `bar`.
+FC_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+FC_DEV void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 FC_DEV void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 FC_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 FC_DEV void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -181,34 +211,40 @@ FC_DEV void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 // ------------------------------------------------------------------------------------------------ the GEMM kernel
 struct fc_tc_args {
-  const float* A;   // [bins][G][O][2I]   kernel spectrum, relayout mode 0
-  const float* Bt;  // [bins][G][2B][2I]  signal spectrum, relayout mode 1
-  float* D;         // [bins][G][O][2B]   product (complex Y[f][g][o][b])
+  const float* A;   // A blobs  [item][pass][chunk][MT*128 x 32]
+  const float* Bt;  // Bt blobs [item][chunk][2][N x 32]
+  float* D;         // [item][O][N]   product (complex Y[f][g][o][b])
   int64_t n_items;  // bins * G
-  int32_t O, I, B;  // per group; O % 128 == 0, (2I) % 32 == 0, B = padded batch: 2B in {16, 32, 48, 64}
+  int32_t O, I, B;  // per group; O % 128 == 0, (2I) % 32 == 0, B = padded batch: N = 2B in {16, 32, 48, 64}
 };
 
-// One CTA (256 threads) per SM, persistent over (bin, group) items. K loop in chunks of 32 fp32 (one 128-byte swizzle
-// row); 3 shared-memory stages, each holding A (raw + low part) for up to 256 rows and Bt (raw + low part). All 8
-// warps load (registers -> swizzled shared memory, computing the low parts on the way); thread 0 issues the MMAs;
-// tcgen05.commit frees a stage and publishes the accumulator; warps 0-3 / 4-7 drain the two 128-row accumulators.
+// One CTA per SM, persistent over (bin, group) items; 8 consumer warps + 1 producer warp.
+//   producer (warp 8, one lane): for every chunk, waits until the stage is free and issues two bulk async copies
+//     (A blob, Bt hi+lo blob) that complete on the stage's "full" mbarrier;
+//   consumers (warps 0-7): wait "full", derive the low part of A in shared memory, fence to the async proxy,
+//     barrier; thread 0 issues the 3 x 4 x MT tcgen05.mma of the chunk and commits them to the stage's "free"
+//     mbarrier (and, on the last chunk of an item, to the accumulator mbarrier);
+//   epilogue: warps 0-3 / 4-7 drain the two 128-row accumulators from TMEM straight to global memory.
 #define FC_TC_STAGES 3
-#define FC_TC_MAXN 64
-template <int MT /* 128-row tiles of O: 1 or 2 */>
-__global__ void __launch_bounds__(256, 1) fc_tc_gemm_kernel(fc_tc_args a) {
+template <int MT /* 128-row tiles of O per pass: 1 or 2 */>
+__global__ void __launch_bounds__(288, 1) fc_tc_gemm_kernel(fc_tc_args a) {
   using namespace fc_tc;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = 2 * a.B, KD = 2 * a.I, n_chunks = KD / 32;
-  constexpr int A_BYTES = MT * 128 * 128;  // one operand copy of A per stage: MT*128 rows x 128 bytes
-  const int B_BYTES = N * 128;
-  const int stage_bytes = 2 * A_BYTES + 2 * ((B_BYTES + 1023) & ~1023);
+  constexpr int A_BYTES = MT * 128 * 128;  // one copy of the A chunk: MT*128 rows x 128 bytes
+  const int B_BYTES = N * 128;             // one copy of the Bt chunk
+  const int stage_bytes = 2 * A_BYTES + 2 * B_BYTES;
   unsigned char* sbase = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bar_free[FC_TC_STAGES];  // MMA done with the stage
+  __shared__ __align__(8) uint64_t bar_full[FC_TC_STAGES];  // bulk copies of the stage have landed
+  __shared__ __align__(8) uint64_t bar_free[FC_TC_STAGES];  // MMAs reading the stage are done
   __shared__ __align__(8) uint64_t bar_acc;                 // accumulator of the current item complete
   __shared__ uint32_t tmem_slot;
   if (tid == 0) {
-    for (int s = 0; s < FC_TC_STAGES; ++s) mbar_init(&bar_free[s], 1);
+    for (int s = 0; s < FC_TC_STAGES; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_free[s], 1);
+    }
     mbar_init(&bar_acc, 1);
     fence_barrier_init();
   }
@@ -220,125 +256,96 @@ __global__ void __launch_bounds__(256, 1) fc_tc_gemm_kernel(fc_tc_args a) {
   const uint32_t tmem_base = tmem_slot;
   const uint32_t idesc = idesc_tf32(128, N);
 
-  // loader geometry: a chunk of A is MT*128 rows x 8 sixteen-byte pieces; thread t owns piece (t & 7) of rows t>>3 + 32*j
-  const int piece = tid & 7;
-  uint32_t free_phase[FC_TC_STAGES] = {0, 0, 0};  // parity to wait for on each stage (number of completed uses & 1)
-  uint32_t stage_used[FC_TC_STAGES] = {0, 0, 0};
-  uint32_t acc_phase = 0;
-  int64_t chunk_seq = 0;  // running chunk counter of this CTA -> stage = chunk_seq % STAGES
+  const int passes = a.O / (MT * 128);
+  const int64_t my_items = (a.n_items > (int64_t)blockIdx.x) ? (a.n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t total = my_items * passes * n_chunks;  // flat chunk sequence q = ((item_local*passes) + pass)*n_chunks + c
 
-  for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-    const float* Ag = a.A + item * (int64_t)a.O * KD;
-    const float* Bg = a.Bt + item * (int64_t)N * KD;
-    for (int mt0 = 0; mt0 < a.O; mt0 += MT * 128) {  // O > MT*128: several passes over the K loop
-      // global -> registers, one chunk ahead of the chunk being written to shared memory
-      float4 ra[MT * 4], rb[FC_TC_MAXN / 32], na[MT * 4], nb[FC_TC_MAXN / 32];
-      auto load_chunk = [&](int c, float4 (&xa)[MT * 4], float4 (&xb)[FC_TC_MAXN / 32]) {
-#pragma unroll
-        for (int j = 0; j < MT * 4; ++j) {
-          const int row = (tid >> 3) + 32 * j;
-          xa[j] = __ldg(reinterpret_cast<const float4*>(Ag + (int64_t)(mt0 + row) * KD + c * 32) + piece);
-        }
-#pragma unroll
-        for (int j = 0; j < FC_TC_MAXN / 32; ++j) {
-          const int row = (tid >> 3) + 32 * j;
-          xb[j] = (row < N) ? __ldg(reinterpret_cast<const float4*>(Bg + (int64_t)row * KD + c * 32) + piece) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      load_chunk(0, ra, rb);
-      for (int c = 0; c < n_chunks; ++c, ++chunk_seq) {
-        const int s = (int)(chunk_seq % FC_TC_STAGES);
+  if (warp == 8) {
+    // ---------------- producer
+    if (lane == 0) {
+      for (int64_t q = 0; q < total; ++q) {
+        const int s = (int)(q % FC_TC_STAGES);
+        const int64_t use = q / FC_TC_STAGES;
+        if (use > 0) mbar_wait(&bar_free[s], (uint32_t)((use - 1) & 1));
+        const int c = (int)(q % n_chunks);
+        const int64_t ip = q / n_chunks;
+        const int pass = (int)(ip % passes);
+        const int64_t item = blockIdx.x + (ip / passes) * gridDim.x;
         unsigned char* st = sbase + (size_t)s * stage_bytes;
-        unsigned char* a_hi = st;
-        unsigned char* a_lo = st + A_BYTES;
-        unsigned char* b_hi = st + 2 * A_BYTES;
-        unsigned char* b_lo = b_hi + ((B_BYTES + 1023) & ~1023);
-        if (c + 1 < n_chunks) load_chunk(c + 1, na, nb);  // in flight while chunk c is staged and multiplied
-        // wait until the MMAs that last read this stage are done
-        if (stage_used[s]) {
-          mbar_wait(&bar_free[s], free_phase[s]);
-          free_phase[s] ^= 1;
-        }
-        stage_used[s] = 1;
-        tc_fence_after();
-        // registers -> swizzled shared memory: raw value (the tensor core ignores the low 13 bits) and exact low part
-#pragma unroll
-        for (int j = 0; j < MT * 4; ++j) {
-          const int row = (tid >> 3) + 32 * j;
-          const uint32_t off = (uint32_t)(row >> 3) * 1024 + (uint32_t)(row & 7) * 128 + (uint32_t)((piece ^ (row & 7)) << 4);
-          const float4 v = ra[j];
-          float4 lo;
-          lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-          *reinterpret_cast<float4*>(a_hi + off) = v;
-          *reinterpret_cast<float4*>(a_lo + off) = lo;
-        }
-#pragma unroll
-        for (int j = 0; j < FC_TC_MAXN / 32; ++j) {
-          const int row = (tid >> 3) + 32 * j;
-          if (row < N) {
-            const uint32_t off = (uint32_t)(row >> 3) * 1024 + (uint32_t)(row & 7) * 128 + (uint32_t)((piece ^ (row & 7)) << 4);
-            const float4 v = rb[j];
-            float4 lo;
-            lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-            lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-            lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-            lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-            *reinterpret_cast<float4*>(b_hi + off) = v;
-            *reinterpret_cast<float4*>(b_lo + off) = lo;
-          }
-        }
-        fence_proxy_async();  // make the generic-proxy writes visible to the tensor core (async proxy)
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-          tc_fence_after();
-          const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint32_t d = tmem_base + (uint32_t)(mt * N);  // accumulator of this 128-row tile: N columns
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {  // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row
-              const uint64_t dah = smem_desc_sw128(ah + mt * 16384 + k * 32);
-              const uint64_t dal = smem_desc_sw128(al + mt * 16384 + k * 32);
-              const uint64_t dbh = smem_desc_sw128(bh + k * 32);
-              const uint64_t dbl = smem_desc_sw128(bl + k * 32);
-              umma_tf32(d, dah, dbh, idesc, (c | k) ? 1u : 0u);
-              umma_tf32(d, dal, dbh, idesc, 1u);
-              umma_tf32(d, dah, dbl, idesc, 1u);
-            }
-          }
-          umma_commit(&bar_free[s]);
-          if (c == n_chunks - 1) umma_commit(&bar_acc);
-        }
-#pragma unroll
-        for (int j = 0; j < MT * 4; ++j) ra[j] = na[j];
-#pragma unroll
-        for (int j = 0; j < FC_TC_MAXN / 32; ++j) rb[j] = nb[j];
+        mbar_expect_tx(&bar_full[s], (uint32_t)(A_BYTES + 2 * B_BYTES));
+        bulk_g2s(st, a.A + (((item * passes + pass) * n_chunks + c) * (int64_t)(A_BYTES / 4)), A_BYTES, &bar_full[s]);
+        bulk_g2s(st + 2 * A_BYTES, a.Bt + ((item * n_chunks + c) * (int64_t)(2 * B_BYTES / 4)), 2 * B_BYTES, &bar_full[s]);
       }
-      // ---- epilogue of this (item, row block): TMEM -> registers -> global
-      mbar_wait(&bar_acc, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after();
-      {
+    }
+  } else {
+    // ---------------- consumers
+    const int piece = tid & 7;
+    uint32_t acc_phase = 0;
+    for (int64_t q = 0; q < total; ++q) {
+      const int c = (int)(q % n_chunks);
+      const int64_t ip = q / n_chunks;
+      const int pass = (int)(ip % passes);
+      const int64_t item = blockIdx.x + (ip / passes) * gridDim.x;
+      const int s = (int)(q % FC_TC_STAGES);
+      unsigned char* st = sbase + (size_t)s * stage_bytes;
+      unsigned char* a_hi = st;
+      unsigned char* a_lo = st + A_BYTES;
+      unsigned char* b_hi = st + 2 * A_BYTES;
+      unsigned char* b_lo = b_hi + B_BYTES;
+      mbar_wait(&bar_full[s], (uint32_t)((q / FC_TC_STAGES) & 1));
+      // low part of A: thread t owns 16-byte piece (t & 7) of rows t>>3 + 32*j (the blob is already swizzled; the
+      // low part keeps the same positions)
+#pragma unroll
+      for (int j = 0; j < MT * 4; ++j) {
+        const int row = (tid >> 3) + 32 * j;
+        const uint32_t off = (uint32_t)row * 128 + (uint32_t)(piece << 4);
+        const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
+        *reinterpret_cast<float4*>(a_lo + off) = make_float4(fc_tc_lo(v.x), fc_tc_lo(v.y), fc_tc_lo(v.z), fc_tc_lo(v.w));
+      }
+      fence_proxy_async();  // generic-proxy writes of a_lo -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      named_bar_sync(1, 256);
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t d = tmem_base + (uint32_t)(mt * N);  // accumulator of this 128-row tile: N columns
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row
+            const uint64_t dah = smem_desc_sw128(ah + mt * 16384 + k * 32);
+            const uint64_t dal = smem_desc_sw128(al + mt * 16384 + k * 32);
+            const uint64_t dbh = smem_desc_sw128(bh + k * 32);
+            const uint64_t dbl = smem_desc_sw128(bl + k * 32);
+            umma_tf32(d, dah, dbh, idesc, (c | k) ? 1u : 0u);
+            umma_tf32(d, dal, dbh, idesc, 1u);
+            umma_tf32(d, dah, dbl, idesc, 1u);
+          }
+        }
+        umma_commit(&bar_free[s]);
+        if (c == n_chunks - 1) umma_commit(&bar_acc);
+      }
+      if (c == n_chunks - 1) {
+        // ---- epilogue of this (item, pass): TMEM -> registers -> global; the producer keeps the pipeline filled
+        mbar_wait(&bar_acc, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
         const int mt = warp >> 2;  // warps 0-3: tile 0, warps 4-7: tile 1
         if (mt < MT) {
           const int row = (warp & 3) * 32 + lane;  // TMEM lane = accumulator row
-          float* drow = a.D + (item * (int64_t)a.O + mt0 + mt * 128 + row) * N;
+          float* drow = a.D + (item * (int64_t)a.O + (int64_t)pass * MT * 128 + mt * 128 + row) * N;
           for (int c0 = 0; c0 < N; c0 += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * N + c0), v);
 #pragma unroll
-            for (int q = 0; q < 32; q += 4)
-              if (c0 + q < N) *reinterpret_cast<float4*>(drow + c0 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+            for (int qq = 0; qq < 32; qq += 4)
+              if (c0 + qq < N) *reinterpret_cast<float4*>(drow + c0 + qq) = make_float4(v[qq], v[qq + 1], v[qq + 2], v[qq + 3]);
           }
         }
+        tc_fence_before();
+        named_bar_sync(1, 256);  // the accumulator may be overwritten by the next item's first MMA
+        tc_fence_after();
       }
-      tc_fence_before();
-      __syncthreads();  // the accumulator may be overwritten by the next item's first MMA
-      tc_fence_after();
     }
   }
   __syncthreads();

@@ -142,7 +142,7 @@ def kernel_spectrum(entry: _PlanEntry, kernel: Tensor, device: torch.device, use
     lib = plan.lib
     const = entry.const_for(device)
     kspec = torch.empty(int(plan.info.kspec_bytes) // 4, dtype=torch.float32, device=device)
-    ws = torch.empty(int(plan.info.workspace_bytes), dtype=torch.uint8, device=device)
+    ws = torch.empty(int(plan.info.kspec_workspace_bytes), dtype=torch.uint8, device=device)
     stream = torch.cuda.current_stream(device).cuda_stream
     w = kernel.detach().to(device=device).contiguous()
     L.check(lib, lib.fc_kernel_spectrum(plan.handle, _ptr(const), _ptr(w), _ptr(kspec), _ptr(ws), ctypes.c_void_p(stream)), "fc_kernel_spectrum")

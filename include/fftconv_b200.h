@@ -76,7 +76,8 @@ enum {
   FC_FLAG_NO_POLYPHASE = 2, /* keep stride/dilation lattices dense (no gcd reduction) */
   FC_FLAG_NO_FAST_R2C = 4,  /* the three below switch the specialised kernels off one by one (tests, A/B timing) */
   FC_FLAG_NO_FAST_C2R = 8,
-  FC_FLAG_NO_FUSED_MID = 16
+  FC_FLAG_NO_FUSED_MID = 16,
+  FC_FLAG_NO_TC = 32        /* keep the contraction on the SIMT kernel even when the tensor-core path qualifies */
 };
 
 typedef struct fc_plan fc_plan; /* opaque */
@@ -98,6 +99,9 @@ typedef struct fc_plan_info {
   int64_t workspace_bytes;       /* scratch needed by fc_conv / the stage calls (includes x/y spectra) */
   int64_t const_bytes;           /* twiddle table to be initialised once by fc_plan_init_const */
   int64_t algo_bytes_s1, algo_bytes_s2, algo_bytes_s3, algo_bytes_s4; /* SURVEY §8d S1..S4 at N* */
+  int64_t kspec_workspace_bytes; /* scratch needed by fc_kernel_spectrum (>= workspace_bytes when the tensor-core layout is built) */
+  int32_t tensor_core;           /* 1 if the contraction of fc_conv runs on the tensor cores (fc_tc_* path) */
+  int32_t reserved2;
 } fc_plan_info;
 
 const char* fc_last_error(void);

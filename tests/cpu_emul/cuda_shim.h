@@ -40,6 +40,16 @@ void fc_emul_launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bo
 
 #define FC_DYN_SMEM(name) float2* name = reinterpret_cast<float2*>(fc_emul_smem)
 
+static inline unsigned __float_as_uint(float f) {
+  unsigned u;
+  std::memcpy(&u, &f, 4);
+  return u;
+}
+static inline float __uint_as_float(unsigned u) {
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 template <class T>

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(L.FcProblem) == 4 * (6 + 6 * 3 + 4)
-    assert ctypes.sizeof(L.FcPlanInfo) == 48 + 8 * 11
+    assert ctypes.sizeof(L.FcPlanInfo) == 48 + 8 * 11 + 8 + 8
 
 
 def test_plan_creation_needs_no_gpu():
