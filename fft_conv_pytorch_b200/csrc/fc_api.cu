@@ -351,7 +351,7 @@ int launch_tc_gemm(const float* A, const float* Bt, float* D, int64_t bins, int 
   const size_t stage = (size_t)2 * MT * 128 * 128 + 2 * (size_t)N * 128;
   const size_t smem = FC_TC_STAGES * stage + 1024;
   int64_t grid = a.n_items < g_num_sms ? a.n_items : g_num_sms;
-  dim3 g((unsigned)grid), b(288);
+  dim3 g((unsigned)grid), b(FC_TC_THREADS);
   if (MT == 2) {
     auto k = fc_tc_gemm_kernel<2>;
     k<<<g, b, smem, st>>>(a);

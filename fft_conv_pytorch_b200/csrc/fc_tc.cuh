@@ -133,6 +133,9 @@ FC_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+FC_DEV void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 FC_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -218,16 +221,18 @@ struct fc_tc_args {
   int32_t O, I, B;  // per group; O % 128 == 0, (2I) % 32 == 0, B = padded batch: N = 2B in {16, 32, 48, 64}
 };
 
-// One CTA per SM, persistent over (bin, group) items; 8 consumer warps + 1 producer warp.
+// One CTA per SM, persistent over (bin, group) items; warp-specialised:
 //   producer (warp 8, one lane): for every chunk, waits until the stage is free and issues two bulk async copies
 //     (A blob, Bt hi+lo blob) that complete on the stage's "full" mbarrier;
-//   consumers (warps 0-7): wait "full", derive the low part of A in shared memory, fence to the async proxy,
-//     barrier; thread 0 issues the 3 x 4 x MT tcgen05.mma of the chunk and commits them to the stage's "free"
-//     mbarrier (and, on the last chunk of an item, to the accumulator mbarrier);
-//   epilogue: warps 0-3 / 4-7 drain the two 128-row accumulators from TMEM straight to global memory.
+//   splitters (warps 0-7): wait "full", derive the low part of A in shared memory, fence to the async proxy and
+//     arrive on the stage's "ready" mbarrier; after the last chunk of an item they drain the accumulator
+//     (warps 0-3 / 4-7: the two 128-row tiles) from TMEM straight to global memory and release it ("acc_free");
+//   MMA issuer (warp 9, one lane): waits "ready", issues the 3 x 4 x MT tcgen05.mma of the chunk into one of two
+//     accumulator sets in TMEM, commits them to the stage's "free" mbarrier and, on the last chunk, to "acc_full".
 #define FC_TC_STAGES 3
+#define FC_TC_THREADS 320
 template <int MT /* 128-row tiles of O per pass: 1 or 2 */>
-__global__ void __launch_bounds__(288, 1) fc_tc_gemm_kernel(fc_tc_args a) {
+__global__ void __launch_bounds__(FC_TC_THREADS, 1) fc_tc_gemm_kernel(fc_tc_args a) {
   using namespace fc_tc;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -236,19 +241,26 @@ __global__ void __launch_bounds__(288, 1) fc_tc_gemm_kernel(fc_tc_args a) {
   const int B_BYTES = N * 128;             // one copy of the Bt chunk
   const int stage_bytes = 2 * A_BYTES + 2 * B_BYTES;
   unsigned char* sbase = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bar_full[FC_TC_STAGES];  // bulk copies of the stage have landed
-  __shared__ __align__(8) uint64_t bar_free[FC_TC_STAGES];  // MMAs reading the stage are done
-  __shared__ __align__(8) uint64_t bar_acc;                 // accumulator of the current item complete
+  __shared__ __align__(8) uint64_t bar_full[FC_TC_STAGES];   // bulk copies of the stage have landed      (tx bytes)
+  __shared__ __align__(8) uint64_t bar_ready[FC_TC_STAGES];  // low parts written, stage ready for the MMAs (256 arrivals)
+  __shared__ __align__(8) uint64_t bar_free[FC_TC_STAGES];   // MMAs reading the stage are done             (commit)
+  __shared__ __align__(8) uint64_t bar_acc_full[2];          // accumulator set complete                    (commit)
+  __shared__ __align__(8) uint64_t bar_acc_free[2];          // accumulator set drained                     (256 arrivals)
   __shared__ uint32_t tmem_slot;
   if (tid == 0) {
     for (int s = 0; s < FC_TC_STAGES; ++s) {
       mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_ready[s], 256);
       mbar_init(&bar_free[s], 1);
     }
-    mbar_init(&bar_acc, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_acc_full[s], 1);
+      mbar_init(&bar_acc_free[s], 256);
+    }
     fence_barrier_init();
   }
-  const uint32_t tmem_cols = (MT * N <= 32) ? 32 : (MT * N <= 64 ? 64 : (MT * N <= 128 ? 128 : (MT * N <= 256 ? 256 : 512)));
+  const uint32_t acc_cols = (uint32_t)(MT * N);  // columns of one accumulator set
+  const uint32_t tmem_cols = (2 * acc_cols <= 32) ? 32 : (2 * acc_cols <= 64 ? 64 : (2 * acc_cols <= 128 ? 128 : (2 * acc_cols <= 256 ? 256 : 512)));
   if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -258,7 +270,8 @@ __global__ void __launch_bounds__(288, 1) fc_tc_gemm_kernel(fc_tc_args a) {
 
   const int passes = a.O / (MT * 128);
   const int64_t my_items = (a.n_items > (int64_t)blockIdx.x) ? (a.n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t total = my_items * passes * n_chunks;  // flat chunk sequence q = ((item_local*passes) + pass)*n_chunks + c
+  const int64_t n_acc = my_items * passes;       // accumulator uses (item, pass) of this CTA
+  const int64_t total = n_acc * n_chunks;        // flat chunk sequence q = acc_use * n_chunks + c
 
   if (warp == 8) {
     // ---------------- producer
@@ -277,21 +290,44 @@ __global__ void __launch_bounds__(288, 1) fc_tc_gemm_kernel(fc_tc_args a) {
         bulk_g2s(st + 2 * A_BYTES, a.Bt + ((item * n_chunks + c) * (int64_t)(2 * B_BYTES / 4)), 2 * B_BYTES, &bar_full[s]);
       }
     }
+  } else if (warp == 9) {
+    // ---------------- MMA issuer
+    if (lane == 0) {
+      for (int64_t q = 0; q < total; ++q) {
+        const int c = (int)(q % n_chunks);
+        const int64_t ip = q / n_chunks;  // accumulator use
+        const int buf = (int)(ip & 1);
+        const int s = (int)(q % FC_TC_STAGES);
+        if (c == 0 && ip >= 2) mbar_wait(&bar_acc_free[buf], (uint32_t)(((ip >> 1) - 1) & 1));  // set drained by the epilogue
+        mbar_wait(&bar_ready[s], (uint32_t)((q / FC_TC_STAGES) & 1));
+        tc_fence_after();
+        unsigned char* st = sbase + (size_t)s * stage_bytes;
+        const uint32_t ah = smem_u32(st), al = ah + A_BYTES, bh = ah + 2 * A_BYTES, bl = bh + B_BYTES;
+        const uint64_t dah0 = smem_desc_sw128(ah), dal0 = smem_desc_sw128(al), dbh0 = smem_desc_sw128(bh), dbl0 = smem_desc_sw128(bl);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t d = tmem_base + (uint32_t)buf * acc_cols + (uint32_t)(mt * N);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row; the start address field is in 16-byte units
+            const uint64_t adv_a = (uint64_t)((mt * 16384 + k * 32) >> 4), adv_b = (uint64_t)((k * 32) >> 4);
+            umma_tf32(d, dah0 + adv_a, dbh0 + adv_b, idesc, (c | k) ? 1u : 0u);
+            umma_tf32(d, dal0 + adv_a, dbh0 + adv_b, idesc, 1u);
+            umma_tf32(d, dah0 + adv_a, dbl0 + adv_b, idesc, 1u);
+          }
+        }
+        umma_commit(&bar_free[s]);
+        if (c == n_chunks - 1) umma_commit(&bar_acc_full[buf]);
+      }
+    }
   } else {
-    // ---------------- consumers
+    // ---------------- splitters + epilogue (256 threads)
     const int piece = tid & 7;
-    uint32_t acc_phase = 0;
     for (int64_t q = 0; q < total; ++q) {
       const int c = (int)(q % n_chunks);
-      const int64_t ip = q / n_chunks;
-      const int pass = (int)(ip % passes);
-      const int64_t item = blockIdx.x + (ip / passes) * gridDim.x;
       const int s = (int)(q % FC_TC_STAGES);
       unsigned char* st = sbase + (size_t)s * stage_bytes;
       unsigned char* a_hi = st;
       unsigned char* a_lo = st + A_BYTES;
-      unsigned char* b_hi = st + 2 * A_BYTES;
-      unsigned char* b_lo = b_hi + B_BYTES;
       mbar_wait(&bar_full[s], (uint32_t)((q / FC_TC_STAGES) & 1));
       // low part of A: thread t owns 16-byte piece (t & 7) of rows t>>3 + 32*j (the blob is already swizzled; the
       // low part keeps the same positions)
@@ -303,32 +339,14 @@ __global__ void __launch_bounds__(288, 1) fc_tc_gemm_kernel(fc_tc_args a) {
         *reinterpret_cast<float4*>(a_lo + off) = make_float4(fc_tc_lo(v.x), fc_tc_lo(v.y), fc_tc_lo(v.z), fc_tc_lo(v.w));
       }
       fence_proxy_async();  // generic-proxy writes of a_lo -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      named_bar_sync(1, 256);
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t d = tmem_base + (uint32_t)(mt * N);  // accumulator of this 128-row tile: N columns
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row
-            const uint64_t dah = smem_desc_sw128(ah + mt * 16384 + k * 32);
-            const uint64_t dal = smem_desc_sw128(al + mt * 16384 + k * 32);
-            const uint64_t dbh = smem_desc_sw128(bh + k * 32);
-            const uint64_t dbl = smem_desc_sw128(bl + k * 32);
-            umma_tf32(d, dah, dbh, idesc, (c | k) ? 1u : 0u);
-            umma_tf32(d, dal, dbh, idesc, 1u);
-            umma_tf32(d, dah, dbl, idesc, 1u);
-          }
-        }
-        umma_commit(&bar_free[s]);
-        if (c == n_chunks - 1) umma_commit(&bar_acc);
-      }
+      mbar_arrive(&bar_ready[s]);
       if (c == n_chunks - 1) {
-        // ---- epilogue of this (item, pass): TMEM -> registers -> global; the producer keeps the pipeline filled
-        mbar_wait(&bar_acc, acc_phase);
-        acc_phase ^= 1;
+        // ---- epilogue of this (item, pass): TMEM -> registers -> global
+        const int64_t ip = q / n_chunks;
+        const int buf = (int)(ip & 1);
+        const int pass = (int)(ip % passes);
+        const int64_t item = blockIdx.x + (ip / passes) * gridDim.x;
+        mbar_wait(&bar_acc_full[buf], (uint32_t)((ip >> 1) & 1));
         tc_fence_after();
         const int mt = warp >> 2;  // warps 0-3: tile 0, warps 4-7: tile 1
         if (mt < MT) {
@@ -336,19 +354,20 @@ __global__ void __launch_bounds__(288, 1) fc_tc_gemm_kernel(fc_tc_args a) {
           float* drow = a.D + (item * (int64_t)a.O + (int64_t)pass * MT * 128 + mt * 128 + row) * N;
           for (int c0 = 0; c0 < N; c0 += 32) {
             float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * N + c0), v);
+            tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)(mt * N + c0), v);
 #pragma unroll
             for (int qq = 0; qq < 32; qq += 4)
               if (c0 + qq < N) *reinterpret_cast<float4*>(drow + c0 + qq) = make_float4(v[qq], v[qq + 1], v[qq + 2], v[qq + 3]);
           }
         }
         tc_fence_before();
-        named_bar_sync(1, 256);  // the accumulator may be overwritten by the next item's first MMA
-        tc_fence_after();
+        mbar_arrive(&bar_acc_free[buf]);
       }
     }
   }
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 #endif  // !FC_CPU_EMUL
