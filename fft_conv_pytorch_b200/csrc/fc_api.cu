@@ -435,10 +435,12 @@ int fc_plan_init_const(const fc_plan* plan, void* d_const, void* stream) {
   if (g.x > 64) g.x = 64;
   float2* tw = reinterpret_cast<float2*>(d_const);
   const int len = plan->tw_len;
+  const int len2 = plan->structure == FC_S_1D_SPLIT ? plan->N2 : 0;
+  const double big = plan->structure == FC_S_1D_SPLIT ? (double)plan->N1 * (double)plan->N2 : 1.0;
 #ifdef FC_CPU_EMUL
-  fc_emul_launch(g, b, 0, [=]() { fc_twiddle_kernel(tw, len); });
+  fc_emul_launch(g, b, 0, [=]() { fc_twiddle_kernel(tw, len, len2, big); });
 #else
-  fc_twiddle_kernel<<<g, b, 0, (cudaStream_t)stream>>>(tw, len);
+  fc_twiddle_kernel<<<g, b, 0, (cudaStream_t)stream>>>(tw, len, len2, big);
 #endif
   return check_cuda("twiddle table launch");
 }

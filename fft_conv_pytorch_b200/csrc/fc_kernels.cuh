@@ -182,11 +182,14 @@ FC_DEV float2* fc_fft_forward(float2* a, float2* b, int M, int T, int pitch, con
   return in;
 }
 
-// W_twN^(e) for the four-step twiddle, e already reduced mod twN.
-FC_DEV float2 fc_big_twiddle(int64_t e, int64_t twN) {
-  float s, c;
-  sincospif(-2.0f * (float)((double)e / (double)twN), &s, &c);
-  return make_float2(c, s);
+// Four-step twiddle W_N^(k*r), N = N1*N2 (powers of two), from two small tables: with e = (k*r) mod N = a*N2 + b,
+// W_N^e = W_N1^a * W_N^b. tw holds exp(-2*pi*i*j/tw_len) (tw_len >= N1) followed by exp(-2*pi*i*b/N), b < N2.
+FC_DEV float2 fc_big_twiddle(int64_t k, int64_t r, const fc_pass& p, const float2* tw) {
+  const int64_t e = (k * r) & (p.twN - 1);
+  const int l2 = 31 - __clz(p.tw2_len);
+  const int a = (int)(e >> l2), b = (int)(e & (p.tw2_len - 1));
+  const int n1 = (int)(p.twN >> l2);
+  return fc_mul(__ldg(tw + a * (p.tw_len / n1)), __ldg(tw + p.tw_len + b));
 }
 
 // ------------------------------------------------------------------------------------------------ the axis pass
@@ -335,8 +338,7 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
         if (li.valid) {
           val = __ldg(x + li.in_base + (int64_t)k * p.in_es);
           if (p.twiddle) {
-            const int64_t e = ((int64_t)k * li.r) % p.twN;
-            val = fc_mul(val, fc_conj(fc_big_twiddle(e, p.twN)));
+            val = fc_mul(val, fc_conj(fc_big_twiddle(k, li.r, p, a.tw)));
           }
         }
         bufA[l * pitch + k] = val;
@@ -397,8 +399,7 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
         if (!li.valid) continue;
         float2 val = other[l * pitch + k];
         if (p.twiddle) {
-          const int64_t e = ((int64_t)k * li.r) % p.twN;
-          val = fc_mul(val, fc_big_twiddle(e, p.twN));
+          val = fc_mul(val, fc_big_twiddle(k, li.r, p, a.tw));
         }
         val = fc_scale(val, p.scale);
         if (p.conj_out) val = fc_conj(val);
@@ -556,11 +557,15 @@ __global__ void fc_contract_kernel(fc_contract_args a) {
   }
 }
 
-// Twiddle table: tw[j] = exp(-2*pi*i*j/len), evaluated in double precision.
-__global__ void fc_twiddle_kernel(float2* tw, int len) {
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) {
+// Twiddle tables, evaluated in double precision: tw[j] = exp(-2*pi*i*j/len) for j < len, then (four-step plans)
+// tw[len + b] = exp(-2*pi*i*b/big) for b < len2.
+__global__ void fc_twiddle_kernel(float2* tw, int len, int len2, double big) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len + len2; j += gridDim.x * blockDim.x) {
     double s, c;
-    sincospi(-2.0 * (double)j / (double)len, &s, &c);
+    if (j < len)
+      sincospi(-2.0 * (double)j / (double)len, &s, &c);
+    else
+      sincospi(-2.0 * (double)(j - len) / big, &s, &c);
     tw[j] = make_float2((float)c, (float)s);
   }
 }

@@ -86,6 +86,7 @@ fc_pass blank_pass(int kind, int N, int tw_len) {
   p.kind = kind;
   p.N = N;
   p.tw_len = tw_len;
+  p.tw2_len = 1;
   p.scale = 1.f;
   p.pos_n = 1;
   p.pos_r = 0;
@@ -156,6 +157,7 @@ void build_forward(const fc_plan& pl, const SrcDesc& s, std::vector<fc_step>& ou
     p.out_rfast = 1;
     p.twiddle = 1;
     p.twN = (int64_t)N1 * N2;
+    p.tw2_len = N2;
     finish_pass(p);
     out.push_back({p, FC_BUF_USER_IN, FC_BUF_SA});
     fc_pass q = blank_pass(FC_C2C_FWD, N2, tw);
@@ -313,6 +315,7 @@ void build_inverse(const fc_plan& pl, std::vector<fc_step>& out) {
     p.n_in = Nk1;
     p.twiddle = 1;
     p.twN = (int64_t)N1 * N2;
+    p.tw2_len = N2;
     p.pos_n = N2;
     p.pos_r = 1;
     p.out_os = a.Lout;
@@ -655,7 +658,7 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     }
     I.tensor_core = pl->use_tc;
   }
-  I.const_bytes = (int64_t)tw_len * 8;
+  I.const_bytes = ((int64_t)tw_len + (pl->structure == FC_S_1D_SPLIT ? pl->N2 : 0)) * 8;
   I.n_launches = (int)(pl->sig_fwd.size() + 1 + pl->inv.size());
   I.n_launches_kspec = (int)pl->ker_fwd.size();
   I.fused = 0;

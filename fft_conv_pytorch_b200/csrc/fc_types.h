@@ -56,6 +56,7 @@ struct fc_pass {
   int32_t pos_n;      // dense position on the mapped axis: u = n*pos_n + r*pos_r
   int32_t pos_r;
   int32_t tw_len;     // length of the twiddle table (power of two >= every N of the plan)
+  int32_t tw2_len;    // four-step plans: N2; a second table exp(-2*pi*i*b/(N1*N2)), b < N2, follows the first one
   int32_t cout;       // C2R: bias index = outer % cout
   int32_t has_bias;
   // C2R: lattice on the line (row) index: dense line r owns the output rows j with (j + row_ob) / row_og == r; only
