@@ -279,9 +279,10 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
   a.n_units = (int64_t)P.groups * f.R * a.nbs;
   a.imap = f.imap;
   a.omap = f.omap;
-  const size_t smem = (size_t)f.nb * f.ci * f.N * sizeof(float2);
+  const bool ring = false;  // fc_kb_traits::kRing (see fc_fused.cuh)
+  const size_t smem = (size_t)f.nb * f.ci * f.N * sizeof(float2) + (ring ? (size_t)FC_KB_RING_STAGES * (f.ci / 2) * f.N * sizeof(float2) : 0);
   {  // distance (in units) to the CTA of the next wave on the same SM: what this CTA prefetches into L2
-    int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(smem + 1024);
+    int64_t per_sm = (int64_t)(228 * 1024) / (int64_t)(smem + 1024 + 256);
     const int64_t reg_lim = f.occ;  // launch bounds
     if (per_sm > reg_lim) per_sm = reg_lim;
     if (per_sm < 1) per_sm = 1;
