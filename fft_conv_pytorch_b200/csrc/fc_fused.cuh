@@ -27,14 +27,6 @@ FC_DEV void fc_prefetch_l2(const void*) {}
 FC_DEV void fc_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
 
-// Swizzle of a warp's exchange line. For the three access patterns of the stages (16 consecutive points;
-// stride-8 writes of the first stage; "8 consecutive, jump 64" writes of the second stage) the 16 lanes of a half
-// warp touch 16 distinct 8-byte bank pairs.
-FC_DEV int fc_swz2(int p) {
-  const int h = p >> 4;
-  return p ^ ((h & 7) | (((h >> 2) & 1) << 3));
-}
-
 // Powers w[1..R-1] of a twiddle factor with a shallow dependency tree.
 template <int R>
 FC_DEV void fc_twiddle_powers(float2 w1, float2 (&w)[R]) {

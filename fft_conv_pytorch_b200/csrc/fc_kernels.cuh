@@ -46,9 +46,15 @@ FC_DEV float2 fc_conj(float2 a) { return make_float2(a.x, -a.y); }
 FC_DEV float2 fc_mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 FC_DEV float2 fc_scale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 
-// XOR swizzle of the element index inside a line: makes both the unit-stride reads and the stride-R /
-// stride-Ns writes of a Stockham stage hit 16 distinct 8-byte bank pairs per half warp.
-FC_DEV int fc_swz(int i) { return i ^ ((i >> 4) & 15); }
+// XOR swizzle of the element index inside a line (only bits 4..6 of the index are looked at, only the low 4 bits
+// change). For the access patterns of a Stockham stage — 16 consecutive points; the stride-8 / stride-4 writes of the
+// first stage; the "8 consecutive, jump 64" writes of the second stage — the 16 lanes of a half warp touch 16
+// distinct 8-byte bank pairs.
+FC_DEV int fc_swz2(int p) {
+  const int h = p >> 4;
+  return p ^ ((h & 7) | (((h >> 2) & 1) << 3));
+}
+FC_DEV int fc_swz(int i) { return fc_swz2(i); }
 
 // ------------------------------------------------------------------------------------------------ maps
 // Dense position u -> source index, or -1 for a structural zero. (fc_types.h: fc_imap)

@@ -62,8 +62,13 @@ fc_omap identity_omap(int n) {
 void finish_pass(fc_pass& p) {
   p.M = (p.kind == FC_R2C || p.kind == FC_C2R) ? p.N / 2 : p.N;
   if (p.M < 1) p.M = 1;
+  // tile budget in complex elements: small tiles keep 4-6 CTAs per SM in flight (the pass is a load -> transform ->
+  // store loop per CTA, so resident CTAs are what hides the HBM latency); a transposing side wants >= 16 lines
   const bool rfast = p.in_rfast || p.out_rfast;
-  int budget = (rfast && p.M >= 512) ? 8192 : 4096;
+  int budget = rfast ? 2048 : 4096;
+  if (rfast && 16 * p.M > budget) budget = 16 * p.M;
+  if (budget > 8192) budget = 8192;
+  if (p.M > budget) budget = p.M;
   int T = 1;
   while (T * 2 * p.M <= budget && T * 2 <= 64) T *= 2;
   const int64_t lines_avail = p.flat ? p.n_outer * p.R : p.R;

@@ -104,7 +104,7 @@ def main():
             r["kernels_error"] = repr(e)[:200]
         Fn.clear_caches()
         torch.cuda.empty_cache()
-        if os.environ.get("FFTCONV_B200_CTILE"):
+        if os.environ.get("FFTCONV_B200_CTILE") or os.environ.get("FFTCONV_SKIP_REF"):
             out[name] = r
             print(name, json.dumps(r), flush=True)
             continue
