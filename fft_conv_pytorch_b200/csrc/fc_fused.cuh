@@ -190,29 +190,29 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
   ofs.init(lane);
   // Software pipeline over the tiles of this CTA: the rows of tile t+1 are requested (into the registers the
   // transform has just released) before tile t is stored, so the load latency overlaps the transposed store.
-  auto load_rows = [&](int64_t t, float2 (&v)[NL][E]) {
-    const int64_t o = t / p.tiles_per_outer;
-    const int64_t r0 = (t - o * p.tiles_per_outer) * TR;
-    const int64_t o1 = o / p.o_c2, o2 = o - o1 * p.o_c2;
-    const int64_t base = (o1 / p.o_q) * p.o_sA + (o1 % p.o_q) * p.o_sB + o2 * p.o_sC;
+  // index math in 32 bits (host guarantees n_tiles < 2^31); this kernel only serves the signal tensor, whose outer
+  // items are in_vol apart (o_c2 == o_q == 1)
+  const int tpo = (int)p.tiles_per_outer, n_tiles = (int)p.n_tiles, R = (int)p.R;
+  auto load_rows = [&](int t, float2 (&v)[NL][E]) {
+    const int o = t / tpo;
+    const int r0 = (t - o * tpo) * TR;
+    const float* img = a.x + (int64_t)o * p.o_sA;
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
-      const int64_t r = r0 + NL * w + l;
-      const bool valid = r < p.R;
-      const float* row = a.x + base + (valid ? r : 0) * p.in_rs;
+      const int r = r0 + NL * w + l;
+      const bool valid = r < R;
+      const float2* row = reinterpret_cast<const float2*>(img + (int64_t)(valid ? r : 0) * p.in_rs) + lane;
 #pragma unroll
-      for (int q = 0; q < E; ++q) {
-        const int i0 = 2 * (lane + 32 * q);  // L is even (host check), so the pair (i0, i0 + 1) is in or out together
-        v[l][q] = (valid && i0 < L) ? __ldg(reinterpret_cast<const float2*>(row + i0)) : make_float2(0.f, 0.f);
-      }
+      for (int q = 0; q < E; ++q)  // L is even (host check), so the pair (2m, 2m + 1) is in or out together
+        v[l][q] = (valid && 2 * (lane + 32 * q) < L) ? __ldg(row + 32 * q) : make_float2(0.f, 0.f);
     }
   };
   float2 v[NL][E];
-  if ((int64_t)blockIdx.x < p.n_tiles) load_rows(blockIdx.x, v);
-  for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-    const int64_t o = t / p.tiles_per_outer;
-    const int64_t r0 = (t - o * p.tiles_per_outer) * TR;
-    const int64_t tn = t + gridDim.x;
+  if ((int)blockIdx.x < n_tiles) load_rows(blockIdx.x, v);
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int o = t / tpo;
+    const int r0 = (t - o * tpo) * TR;
+    const int tn = t + gridDim.x;
     if (a.dbg != 1) fc_wfft<M, NL, M>(v, line0, ofs, a.tw, p.tw_len, lane);
     fc_wwrite<M, NL, M>(v, line0, ofs);
     FC_SYNCWARP();
@@ -239,24 +239,27 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
       }
     }
     __syncthreads();
-    if (tn < p.n_tiles) {
+    if (tn < n_tiles) {
       load_rows(tn, v);  // in flight during the store below
       // and pull the tile after that one into L2: its TR rows are one contiguous run of TR*in_rs floats
-      const int64_t t2 = tn + gridDim.x;
-      if (t2 < p.n_tiles) {
-        const int64_t on = t2 / p.tiles_per_outer;
-        const int64_t rn = (t2 - on * p.tiles_per_outer) * TR;
-        const int64_t on1 = on / p.o_c2, on2 = on - on1 * p.o_c2;
-        const int64_t bn = (on1 / p.o_q) * p.o_sA + (on1 % p.o_q) * p.o_sB + on2 * p.o_sC + rn * p.in_rs;
-        int64_t rows = p.R - rn;
-        if (rows > TR) rows = TR;
-        const int64_t span = rows * p.in_rs;  // floats
-        for (int64_t e = (int64_t)tid * 32; e < span; e += FC_FAST_WARPS * 32 * 32) fc_prefetch_l2(a.x + bn + e);
+      const int t2 = tn + gridDim.x;
+      if (t2 < n_tiles) {
+        const int on = t2 / tpo;
+        const int rn = (t2 - on * tpo) * TR;
+        const int rows = (R - rn < TR) ? R - rn : TR;
+        const float* nxt = a.x + (int64_t)on * p.o_sA + (int64_t)rn * p.in_rs;
+        const int span = rows * (int)p.in_rs;  // floats
+        for (int e = tid * 32; e < span; e += FC_FAST_WARPS * 32 * 32) fc_prefetch_l2(nxt + e);
       }
     }
-    for (int idx = tid; idx < (M + 1) * TR; idx += FC_FAST_WARPS * 32) {
-      const int l = idx & (TR - 1), k = idx >> 4;
-      if (r0 + l < p.R && a.dbg != 2) a.out[o * p.out_os + (int64_t)k * p.out_es + r0 + l] = tile[k * TP + l];
+    {  // transposed store: thread (l = tid & 15, k = tid >> 4 + 16 j) writes 16 consecutive rows of one bin = 128 bytes
+      const int l = tid & (TR - 1);
+      if (r0 + l < R && a.dbg != 2) {
+        float2* dst = a.out + (int64_t)o * p.out_os + r0 + l + (int64_t)(tid >> 4) * p.out_es;
+        const float2* src = tile + (tid >> 4) * TP + l;
+        const int64_t dstep = 16 * p.out_es;
+        for (int k = tid >> 4; k <= M; k += 16, dst += dstep, src += 16 * TP) *dst = *src;
+      }
     }
     __syncthreads();
   }
@@ -284,23 +287,29 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
   const bool plain_out = om.os == 1 && om.ob == 0 && om.og == 1 && !(om.Lout & 1) && !(p.out_rs & 1) && !(p.out_os & 1) && p.row_og == 1;
   fc_wofs ofs;
   ofs.init(lane);
-  for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-    const int64_t o = t / p.tiles_per_outer;
-    const int64_t r0 = (t - o * p.tiles_per_outer) * TR;
-    for (int idx = tid; idx < (M + 1) * TR; idx += FC_FAST_WARPS * 32) {
-      const int l = idx & (TR - 1), k = idx >> 4;
-      tile[k * TP + l] = (r0 + l < p.R) ? __ldg(a.in + o * p.in_os + (int64_t)k * p.in_es + r0 + l) : make_float2(0.f, 0.f);
+  const int tpo = (int)p.tiles_per_outer, n_tiles = (int)p.n_tiles, R = (int)p.R;  // 32-bit index math (host: n_tiles < 2^31)
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int o = t / tpo;
+    const int r0 = (t - o * tpo) * TR;
+    {  // transposed load: thread (l = tid & 15, k = tid >> 4 + 16 j) reads 16 consecutive rows of one bin = 128 bytes
+      const int l = tid & (TR - 1);
+      const bool ok = r0 + l < R;
+      const float2* src = a.in + (int64_t)o * p.in_os + r0 + (ok ? l : 0) + (int64_t)(tid >> 4) * p.in_es;
+      float2* dst = tile + (tid >> 4) * TP + l;
+      const int64_t sstep = 16 * p.in_es;
+      for (int k = tid >> 4; k <= M; k += 16, src += sstep, dst += 16 * TP) *dst = ok ? __ldg(src) : make_float2(0.f, 0.f);
     }
     {  // L2 prefetch of the next tile of this CTA: (M+1) segments of TR float2 = 128 bytes
-      const int64_t tn = t + gridDim.x;
-      if (tn < p.n_tiles) {
-        const int64_t on = tn / p.tiles_per_outer;
-        const int64_t rn = (tn - on * p.tiles_per_outer) * TR;
-        for (int k = tid; k <= M; k += FC_FAST_WARPS * 32) fc_prefetch_l2(a.in + on * p.in_os + (int64_t)k * p.in_es + rn);
+      const int tn = t + gridDim.x;
+      if (tn < n_tiles) {
+        const int on = tn / tpo;
+        const int rn = (tn - on * tpo) * TR;
+        const float2* nxt = a.in + (int64_t)on * p.in_os + rn;
+        for (int k = tid; k <= M; k += FC_FAST_WARPS * 32) fc_prefetch_l2(nxt + (int64_t)k * p.in_es);
       }
     }
     __syncthreads();
-    const float b = p.has_bias ? __ldg(a.bias + (int)(o % p.cout)) : 0.f;
+    const float b = p.has_bias ? __ldg(a.bias + (o % p.cout)) : 0.f;
     float2 v[NL][E];
 #pragma unroll
     for (int q = 0; q < E; ++q) {
