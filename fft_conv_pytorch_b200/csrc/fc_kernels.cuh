@@ -283,8 +283,8 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
         const fc_line_info li = lines[l];
         float val = 0.f;
         if (li.valid) {
-          const int64_t u = (int64_t)n * p.pos_n + li.r * p.pos_r;
-          const int s = (u < p.imap.ext) ? fc_imap_src(p.imap, (int)u) : -1;
+          const int u = n * p.pos_n + (int)li.r * p.pos_r;  // dense position < 2^25 (plan limit)
+          const int s = fc_imap_src(p.imap, u);
           if (s >= 0) val = __ldg(x + li.in_base + (int64_t)s * p.in_es);
         }
         dst[2 * (l * pitch + fc_swz(n >> 1)) + (n & 1)] = val;
@@ -446,13 +446,22 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
         if (!li.valid) continue;
         const float2 val = fc_conj(res[l * pitch + fc_swz(n)]);
         // dense index n owns the outputs j with (j*os + ob) / og == n
-        for (int e = 0; e < om.og; ++e) {
-          const int t = n * om.og + e - om.ob;
-          if (t < 0 || (t % om.os)) continue;
-          const int j = t / om.os;
-          if (j >= om.Lout) continue;
-          const bool live = (e == 0) && (n < om.lim);
-          y[li.out_base + (int64_t)j * p.out_es] = live ? val : make_float2(0.f, 0.f);
+        if (om.og == 1 && om.os == 1) {  // plain crop: no division on the common path
+          const int j = n - om.ob;
+          if (j >= 0 && j < om.Lout) y[li.out_base + (int64_t)j * p.out_es] = (n < om.lim) ? val : make_float2(0.f, 0.f);
+        } else {
+          for (int e = 0; e < om.og; ++e) {
+            const int t = n * om.og + e - om.ob;
+            if (t < 0) continue;
+            int j = t;
+            if (om.os != 1) {
+              if (t % om.os) continue;
+              j = t / om.os;
+            }
+            if (j >= om.Lout) continue;
+            const bool live = (e == 0) && (n < om.lim);
+            y[li.out_base + (int64_t)j * p.out_es] = live ? val : make_float2(0.f, 0.f);
+          }
         }
       }
     } else {  // FC_C2R
@@ -473,18 +482,27 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
         const float2 z = res[l * pitch + fc_swz(n >> 1)];
         const float val = (n & 1) ? -z.y : z.x;
         const float b = p.has_bias ? __ldg(a.bias + li.bias_idx) : 0.f;
-        const int64_t u = (int64_t)n * p.pos_n + li.r * p.pos_r;
-        for (int er = 0; er < p.row_og; ++er) {  // output rows owned by this dense line (one unless row lattice)
-          const int64_t jr = li.r * p.row_og + er - p.row_ob;
-          if (p.row_og > 1 && (jr < 0 || jr >= p.row_Lout)) continue;
-          float* yrow = y + li.out_base + (p.row_og > 1 ? (jr - li.r) * p.out_rs : 0);
-          for (int e = 0; e < om.og; ++e) {
-            const int64_t t = u * om.og + e - om.ob;
-            if (t < 0 || (t % om.os)) continue;
-            const int64_t j = t / om.os;
-            if (j >= om.Lout) continue;
-            const bool live = (e == 0) && (er == 0) && (u < om.lim);
-            yrow[j * p.out_es] = (live ? val : 0.f) + b;
+        const int u = n * p.pos_n + (int)li.r * p.pos_r;  // dense position < 2^25 (plan limit)
+        if (p.row_og == 1 && om.og == 1 && om.os == 1) {  // plain crop: no division on the common path
+          const int j = u - om.ob;
+          if (j >= 0 && j < om.Lout) y[li.out_base + (int64_t)j * p.out_es] = ((u < om.lim) ? val : 0.f) + b;
+        } else {
+          for (int er = 0; er < p.row_og; ++er) {  // output rows owned by this dense line (one unless row lattice)
+            const int jr = (int)li.r * p.row_og + er - p.row_ob;
+            if (p.row_og > 1 && (jr < 0 || jr >= p.row_Lout)) continue;
+            float* yrow = y + li.out_base + (p.row_og > 1 ? (int64_t)(jr - (int)li.r) * p.out_rs : 0);
+            for (int e = 0; e < om.og; ++e) {
+              const int t = u * om.og + e - om.ob;
+              if (t < 0) continue;
+              int j = t;
+              if (om.os != 1) {  // strided forward convolution: only every os-th dense sample is an output
+                if (t % om.os) continue;
+                j = t / om.os;
+              }
+              if (j >= om.Lout) continue;
+              const bool live = (e == 0) && (er == 0) && (u < om.lim);
+              yrow[(int64_t)j * p.out_es] = (live ? val : 0.f) + b;
+            }
           }
         }
       }
