@@ -204,6 +204,10 @@ def _run(transposed: bool, signal: Tensor, kernel: Tensor, bias: Optional[Tensor
         return conv_with_grad(transposed, signal, kernel, bias, stride_, padding_, opad_, dilation_, groups, padding_mode)
 
     _require_cuda()
+    if B == 0:  # empty batch: shape algebra only (the plan of a one-sample problem gives the output extents)
+        e1 = get_plan(transposed, 1, cin, cout, groups, tuple(int(s) for s in signal.shape[2:]), tuple(int(s) for s in kernel.shape[2:]),
+                      stride_, padding_, dilation_, opad_, padding_mode, flags)
+        return signal.new_empty((0, cout) + e1.plan.out_size)
     entry = get_plan(transposed, B, cin, cout, groups, tuple(int(s) for s in signal.shape[2:]), tuple(int(s) for s in kernel.shape[2:]),
                      stride_, padding_, dilation_, opad_, padding_mode, flags)
     plan = entry.plan

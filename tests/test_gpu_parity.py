@@ -192,6 +192,24 @@ def test_complex_matmul_matches_einsum():
     assert rel_err(torch.view_as_real(y).cpu().numpy(), torch.view_as_real(ref).cpu().numpy()) < 1e-5
 
 
+def test_empty_batch_noncontiguous_input_and_side_stream():
+    torch.manual_seed(12)
+    w = torch.randn(4, 3, 5, 5, device="cuda")
+    b = torch.randn(4, device="cuda")
+    with torch.no_grad():
+        y = fcp.fft_conv(torch.empty(0, 3, 20, 20, device="cuda"), w, b, padding=1)
+        assert y.shape == (0, 4, 18, 18)
+        x = torch.randn(2, 20, 3, 24, device="cuda").permute(0, 2, 3, 1)  # (2, 3, 24, 20), non-contiguous
+        assert not x.is_contiguous()
+        ref = F.conv2d(x, w, b, stride=2)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            y = fcp.fft_conv(x, w, b, stride=2)
+        torch.cuda.current_stream().wait_stream(s)
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < TOL
+
+
 def test_inputs_are_not_mutated():
     torch.manual_seed(8)
     x = torch.randn(1, 4, 30, device="cuda")
