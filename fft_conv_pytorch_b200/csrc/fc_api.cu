@@ -63,6 +63,10 @@ int g_num_sms = 148;
   X(512, 2, 4, true, 3) X(512, 1, 4, true, 3) X(256, 2, 4, true, 3) \
   X(1024, 1, 8, true, 2) X(1024, 1, 8, false, 2)
 
+// Instantiated variants of the transposing kernels K1 / K4: X(M, lines per warp, warps, CTAs per SM).
+#define FC_FAST_ALL(X) \
+  X(256, 2, 8, 3) X(256, 2, 8, 4) X(256, 1, 16, 2) X(512, 2, 8, 1) X(512, 2, 8, 2) X(512, 2, 8, 3) X(512, 1, 16, 1) X(512, 1, 16, 2) X(1024, 1, 16, 1)
+
 void fused_set_attr() {
 #ifndef FC_CPU_EMUL
 #define FC_FUSED_ATTR(NN, NBB, WW, PL, OC) \
@@ -83,10 +87,11 @@ void init_once() {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
       g_num_sms = sms;
-    cudaFuncSetAttribute(fc_fast_r2c_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(fc_fast_r2c_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(fc_fast_c2r_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(fc_fast_c2r_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+#define FC_FAST_ATTR(MM, NLL, NWW, OC)                                                                                   \
+  cudaFuncSetAttribute(fc_fast_r2c_kernel<MM, NLL, NWW, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); \
+  cudaFuncSetAttribute(fc_fast_c2r_kernel<MM, NLL, NWW, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    FC_FAST_ALL(FC_FAST_ATTR)
+#undef FC_FAST_ATTR
     fused_set_attr();
     cudaFuncSetAttribute(fc_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     cudaFuncSetAttribute(fc_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
@@ -206,6 +211,34 @@ int launch_contract(const float2* X, const float2* K, float2* Y, int64_t bins, i
   return check_cuda("contraction launch");
 }
 
+// Variant of the transposing kernels for a line length: (lines per warp, warps, CTAs per SM). FFTCONV_B200_FAST
+// ("nl,nw,occ") overrides it for timing experiments; unknown combinations fall back to the default.
+struct fast_cfg {
+  int nl, nw, occ;
+};
+fast_cfg fast_config(int M) {
+  fast_cfg c = M == 256 ? fast_cfg{2, 8, 3} : M == 512 ? fast_cfg{2, 8, 2} : fast_cfg{1, 16, 1};
+  static const char* env = std::getenv("FFTCONV_B200_FAST");
+  if (env) {
+    fast_cfg e = c;
+    std::sscanf(env, "%d,%d,%d", &e.nl, &e.nw, &e.occ);
+    bool known = false;
+#define FC_FAST_KNOWN(MM, NLL, NWW, OC) known = known || (M == MM && e.nl == NLL && e.nw == NWW && e.occ == OC);
+    FC_FAST_ALL(FC_FAST_KNOWN)
+#undef FC_FAST_KNOWN
+    if (known) c = e;
+  }
+  return c;
+}
+
+int64_t fast_grid(const fc_pass& p, const fast_cfg& c, size_t smem) {
+  int64_t per_sm = (int64_t)(224 * 1024) / (int64_t)(smem + 1024);
+  if (per_sm > c.occ) per_sm = c.occ;
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)g_num_sms * per_sm;
+  return grid > p.n_tiles ? p.n_tiles : grid;
+}
+
 int launch_fast_r2c(const fc_pass& p, const void* in, void* out, const float2* tw, cudaStream_t st) {
   fc_fast_r2c_args a;
   a.p = p;
@@ -216,19 +249,21 @@ int launch_fast_r2c(const fc_pass& p, const void* in, void* out, const float2* t
     static const int dbg = std::getenv("FFTCONV_B200_DBG") ? std::atoi(std::getenv("FFTCONV_B200_DBG")) : 0;
     a.dbg = dbg;
   }
-  const size_t smem = ((size_t)FC_FAST_TR * p.M + (size_t)(p.M + 1) * (FC_FAST_TR + 1)) * sizeof(float2);
-  int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(smem + 1024);
-  int64_t grid = (int64_t)g_num_sms * (per_sm < 1 ? 1 : per_sm);
-  if (grid > p.n_tiles) grid = p.n_tiles;
+  const fast_cfg c = fast_config(p.M);
+  const size_t smem = (size_t)p.T * (p.M + 1) * sizeof(float2);
+  const int64_t grid = fast_grid(p, c, smem);
   if (grid < 1) return FC_OK;
-  dim3 g((unsigned)grid), b(FC_FAST_WARPS * 32);
-  if (p.M == 256) {
-    auto k = fc_fast_r2c_kernel<256>;
-    FC_LAUNCH(k, g, b, smem, st, a);
-  } else {
-    auto k = fc_fast_r2c_kernel<512>;
-    FC_LAUNCH(k, g, b, smem, st, a);
+  dim3 g((unsigned)grid), b(c.nw * 32);
+  bool done = false;
+#define FC_FAST_LAUNCH(MM, NLL, NWW, OC)                                  \
+  if (!done && p.M == MM && c.nl == NLL && c.nw == NWW && c.occ == OC) { \
+    auto k = fc_fast_r2c_kernel<MM, NLL, NWW, OC>;                       \
+    FC_LAUNCH(k, g, b, smem, st, a);                                     \
+    done = true;                                                         \
   }
+  FC_FAST_ALL(FC_FAST_LAUNCH)
+#undef FC_FAST_LAUNCH
+  if (!done) return set_err(FC_EUNSUPPORTED, "no transposing R2C kernel for this line length");
   rec_mark();
   return check_cuda("fast r2c launch");
 }
@@ -241,19 +276,21 @@ int launch_fast_c2r(const fc_pass& p, const void* in, void* out, const float2* t
   a.out = (float*)out;
   a.tw = tw;
   a.bias = bias;
-  const size_t smem = ((size_t)FC_FAST_TR * p.M + (size_t)(p.M + 1) * (FC_FAST_TR + 1)) * sizeof(float2);
-  int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(smem + 1024);
-  int64_t grid = (int64_t)g_num_sms * (per_sm < 1 ? 1 : per_sm);
-  if (grid > p.n_tiles) grid = p.n_tiles;
+  const fast_cfg c = fast_config(p.M);
+  const size_t smem = (size_t)p.T * (p.M + 1) * sizeof(float2);
+  const int64_t grid = fast_grid(p, c, smem);
   if (grid < 1) return FC_OK;
-  dim3 g((unsigned)grid), b(FC_FAST_WARPS * 32);
-  if (p.M == 256) {
-    auto k = fc_fast_c2r_kernel<256>;
-    FC_LAUNCH(k, g, b, smem, st, a);
-  } else {
-    auto k = fc_fast_c2r_kernel<512>;
-    FC_LAUNCH(k, g, b, smem, st, a);
+  dim3 g((unsigned)grid), b(c.nw * 32);
+  bool done = false;
+#define FC_FAST_LAUNCH(MM, NLL, NWW, OC)                                  \
+  if (!done && p.M == MM && c.nl == NLL && c.nw == NWW && c.occ == OC) { \
+    auto k = fc_fast_c2r_kernel<MM, NLL, NWW, OC>;                       \
+    FC_LAUNCH(k, g, b, smem, st, a);                                     \
+    done = true;                                                         \
   }
+  FC_FAST_ALL(FC_FAST_LAUNCH)
+#undef FC_FAST_LAUNCH
+  if (!done) return set_err(FC_EUNSUPPORTED, "no transposing C2R kernel for this line length");
   rec_mark();
   return check_cuda("fast c2r launch");
 }

@@ -163,8 +163,6 @@ FC_DEV void fc_wfft(float2 (&v)[NL][M / 32], float2* line0, const fc_wofs& o, co
   }
 }
 
-#define FC_FAST_WARPS 8
-#define FC_FAST_TR 16 /* lines per tile of the transposing kernels = 2 per warp */
 
 // ------------------------------------------------------------------------------------------------ K1
 struct fc_fast_r2c_args {
@@ -175,15 +173,18 @@ struct fc_fast_r2c_args {
   int32_t dbg;  // timing experiments only (FFTCONV_B200_DBG): 1 = skip the transform, 2 = skip the global stores
 };
 
-// Shared memory: TR lines of M float2 + a (M+1) x (TR+1) transposition tile.
-template <int M>
-__global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fast_r2c_kernel(fc_fast_r2c_args a) {
-  constexpr int E = M / 32, TR = FC_FAST_TR, TP = TR + 1, NL = 2;
+// Shared memory: TR lines of pitch M + 1 float2. A line is its warp's exchange buffer during the transform, then
+// holds the untangled half spectrum (bin k at the swizzled slot of k, the Nyquist bin in the extra slot M); the odd
+// pitch makes the transposed read of the store phase (16 rows of one bin per half warp) bank-conflict free, so no
+// separate transposition tile is needed and M = 512 leaves room for several CTAs per SM.
+template <int M, int NL, int NW, int OCC>
+__global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_args a) {
+  constexpr int E = M / 32, TR = NL * NW, LP = M + 1, KS = NW * 32 / TR;  // TR lines per tile; KS bins per store sweep
+  static_assert(TR == 16 || TR == 32, "a tile is 16 or 32 lines");
   const fc_pass& p = a.p;
   FC_DYN_SMEM(smem);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  float2* line0 = smem + (NL * w) * M;
-  float2* tile = smem + TR * M;
+  float2* line0 = smem + (NL * w) * LP;
   const int L = p.imap.L;
   const int tstep = p.tw_len / (2 * M);
   fc_wofs ofs;
@@ -213,10 +214,16 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
     const int o = t / tpo;
     const int r0 = (t - o * tpo) * TR;
     const int tn = t + gridDim.x;
-    if (a.dbg != 1) fc_wfft<M, NL, M>(v, line0, ofs, a.tw, p.tw_len, lane);
-    fc_wwrite<M, NL, M>(v, line0, ofs);
+    if (a.dbg != 1) fc_wfft<M, NL, LP>(v, line0, ofs, a.tw, p.tw_len, lane);
+    fc_wwrite<M, NL, LP>(v, line0, ofs);
     FC_SYNCWARP();
-    // untangle the packed real transforms (same algebra as the generic R2C pass)
+    // untangle the packed real transforms (same algebra as the generic R2C pass) into the registers
+    float nyq[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const float2 z0 = line0[l * LP + fc_swz2(0)];
+      nyq[l] = z0.x - z0.y;  // bin k = M: E[0] - O[0]
+    }
 #pragma unroll
     for (int q = 0; q < E; ++q) {
       const int k = lane + 32 * q;
@@ -225,18 +232,17 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
         const float2 zk = v[l][q];
-        const float2 zc = fc_conj(line0[l * M + km]);
+        const float2 zc = fc_conj(line0[l * LP + km]);
         const float2 e = fc_scale(fc_add(zk, zc), 0.5f);
         const float2 od = fc_scale(fc_mul_mi(fc_sub(zk, zc)), 0.5f);
-        tile[k * TP + NL * w + l] = fc_add(e, fc_mul(wk, od));
+        v[l][q] = fc_add(e, fc_mul(wk, od));
       }
     }
-    if (lane == 0) {  // Nyquist bin k = M: E[0] - O[0]
+    FC_SYNCWARP();  // every partner has been read: the lines can take the spectrum
+    fc_wwrite<M, NL, LP>(v, line0, ofs);
+    if (lane == 0) {
 #pragma unroll
-      for (int l = 0; l < NL; ++l) {
-        const float2 z0 = line0[l * M + fc_swz2(0)];
-        tile[M * TP + NL * w + l] = make_float2(z0.x - z0.y, 0.f);
-      }
+      for (int l = 0; l < NL; ++l) line0[l * LP + M] = make_float2(nyq[l], 0.f);
     }
     __syncthreads();
     if (tn < n_tiles) {
@@ -249,16 +255,16 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
         const int rows = (R - rn < TR) ? R - rn : TR;
         const float* nxt = a.x + (int64_t)on * p.o_sA + (int64_t)rn * p.in_rs;
         const int span = rows * (int)p.in_rs;  // floats
-        for (int e = tid * 32; e < span; e += FC_FAST_WARPS * 32 * 32) fc_prefetch_l2(nxt + e);
+        for (int e = tid * 32; e < span; e += NW * 32 * 32) fc_prefetch_l2(nxt + e);
       }
     }
-    {  // transposed store: thread (l = tid & 15, k = tid >> 4 + 16 j) writes 16 consecutive rows of one bin = 128 bytes
+    {  // transposed store: thread (l = tid % TR, k = tid / TR + KS j) writes TR consecutive rows of one bin (128 / 256 bytes)
       const int l = tid & (TR - 1);
       if (r0 + l < R && a.dbg != 2) {
-        float2* dst = a.out + (int64_t)o * p.out_os + r0 + l + (int64_t)(tid >> 4) * p.out_es;
-        const float2* src = tile + (tid >> 4) * TP + l;
-        const int64_t dstep = 16 * p.out_es;
-        for (int k = tid >> 4; k <= M; k += 16, dst += dstep, src += 16 * TP) *dst = *src;
+        float2* dst = a.out + (int64_t)o * p.out_os + r0 + l + (int64_t)(tid / TR) * p.out_es;
+        const float2* src = smem + l * LP;
+        const int64_t dstep = KS * p.out_es;
+        for (int k = tid / TR; k <= M; k += KS, dst += dstep) *dst = src[k < M ? fc_swz2(k) : M];
       }
     }
     __syncthreads();
@@ -274,14 +280,16 @@ struct fc_fast_c2r_args {
   const float* bias;
 };
 
-template <int M>
-__global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fast_c2r_kernel(fc_fast_c2r_args a) {
-  constexpr int E = M / 32, TR = FC_FAST_TR, TP = TR + 1, NL = 2;
+// Shared memory as in K1: the transposed load fills the lines (bin k of row l at l*(M+1) + k), every lane picks up
+// its bins and their Hermitian partners, and the lines then serve as the exchange buffers of the transform.
+template <int M, int NL, int NW, int OCC>
+__global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_args a) {
+  constexpr int E = M / 32, TR = NL * NW, LP = M + 1, KS = NW * 32 / TR;  // TR lines per tile; KS bins per store sweep
+  static_assert(TR == 16 || TR == 32, "a tile is 16 or 32 lines");
   const fc_pass& p = a.p;
   FC_DYN_SMEM(smem);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  float2* line0 = smem + (NL * w) * M;
-  float2* tile = smem + TR * M;
+  float2* line0 = smem + (NL * w) * LP;
   const int tstep = p.tw_len / (2 * M);
   const fc_omap om = p.omap;
   const bool plain_out = om.os == 1 && om.ob == 0 && om.og == 1 && !(om.Lout & 1) && !(p.out_rs & 1) && !(p.out_os & 1) && p.row_og == 1;
@@ -291,13 +299,13 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int o = t / tpo;
     const int r0 = (t - o * tpo) * TR;
-    {  // transposed load: thread (l = tid & 15, k = tid >> 4 + 16 j) reads 16 consecutive rows of one bin = 128 bytes
+    {  // transposed load: thread (l = tid % TR, k = tid / TR + KS j) reads TR consecutive rows of one bin (128 / 256 bytes)
       const int l = tid & (TR - 1);
       const bool ok = r0 + l < R;
-      const float2* src = a.in + (int64_t)o * p.in_os + r0 + (ok ? l : 0) + (int64_t)(tid >> 4) * p.in_es;
-      float2* dst = tile + (tid >> 4) * TP + l;
-      const int64_t sstep = 16 * p.in_es;
-      for (int k = tid >> 4; k <= M; k += 16, src += sstep, dst += 16 * TP) *dst = ok ? __ldg(src) : make_float2(0.f, 0.f);
+      const float2* src = a.in + (int64_t)o * p.in_os + r0 + (ok ? l : 0) + (int64_t)(tid / TR) * p.in_es;
+      float2* dst = smem + l * LP + tid / TR;
+      const int64_t sstep = KS * p.in_es;
+      for (int k = tid / TR; k <= M; k += KS, src += sstep, dst += KS) *dst = ok ? __ldg(src) : make_float2(0.f, 0.f);
     }
     {  // L2 prefetch of the next tile of this CTA: (M+1) segments of TR float2 = 128 bytes
       const int tn = t + gridDim.x;
@@ -305,7 +313,8 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
         const int on = tn / tpo;
         const int rn = (tn - on * tpo) * TR;
         const float2* nxt = a.in + (int64_t)on * p.in_os + rn;
-        for (int k = tid; k <= M; k += FC_FAST_WARPS * 32) fc_prefetch_l2(nxt + (int64_t)k * p.in_es);
+        for (int k = tid; k < (M + 1) * (TR / 16); k += NW * 32)
+          fc_prefetch_l2(nxt + (int64_t)(k / (TR / 16)) * p.in_es + 16 * (k % (TR / 16)));
       }
     }
     __syncthreads();
@@ -317,14 +326,15 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
       const float2 wk = fc_conj(__ldg(a.tw + k * tstep));
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
-        const float2 yk = tile[k * TP + NL * w + l];
-        const float2 ym = fc_conj(tile[(M - k) * TP + NL * w + l]);
+        const float2 yk = line0[l * LP + k];
+        const float2 ym = fc_conj(line0[l * LP + M - k]);
         const float2 s = fc_add(yk, ym);
         const float2 d = fc_mul(fc_sub(yk, ym), wk);
         v[l][q] = make_float2(s.x - d.y, -(s.y + d.x));  // conj(Z[k]), Z = s + i*d
       }
     }
-    fc_wfft<M, NL, M>(v, line0, ofs, a.tw, p.tw_len, lane);
+    FC_SYNCWARP();  // the lines are exchange buffers from here on
+    fc_wfft<M, NL, LP>(v, line0, ofs, a.tw, p.tw_len, lane);
     if (plain_out) {
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
@@ -340,28 +350,28 @@ __global__ void __launch_bounds__(FC_FAST_WARPS * 32, (M <= 256) ? 3 : 1) fc_fas
       }
     } else {
       // general crop / stride / lattice map: stage the real rows in the warp's lines and scatter from there
+      FC_SYNCWARP();
 #pragma unroll
       for (int l = 0; l < NL; ++l)
 #pragma unroll
-        for (int q = 0; q < E; ++q) line0[l * M + lane + 32 * q] = make_float2(v[l][q].x, -v[l][q].y);
+        for (int q = 0; q < E; ++q) line0[l * LP + lane + 32 * q] = make_float2(v[l][q].x, -v[l][q].y);
       FC_SYNCWARP();
       for (int l = 0; l < NL; ++l) {
         const int64_t r = r0 + NL * w + l;
         if (r >= p.R) continue;
-        const float* rl = reinterpret_cast<const float*>(line0 + l * M);
+        const float* rl = reinterpret_cast<const float*>(line0 + l * LP);
         for (int er = 0; er < p.row_og; ++er) {  // output rows owned by this dense line (one unless row lattice)
           const int64_t jr = r * p.row_og + er - p.row_ob;
           if (jr < 0 || jr >= p.row_Lout) continue;
           float* yrow = a.out + o * p.out_os + jr * p.out_rs;
-          for (int n = lane; n < 2 * M; n += 32) {
-            const float val = rl[n];
-            for (int e = 0; e < om.og; ++e) {
-              const int tt = n * om.og + e - om.ob;
-              if (tt < 0 || (tt % om.os)) continue;
-              const int j = tt / om.os;
-              if (j >= om.Lout) continue;
-              yrow[j] = ((e == 0 && er == 0 && n < om.lim) ? val : 0.f) + b;
-            }
+          // output-driven (coalesced stores): output j takes dense sample n = (j*os + ob) / og when the remainder
+          // is 0 and n < lim, else it is bias only
+          for (int j = lane; j < om.Lout; j += 32) {
+            const int tt = j * om.os + om.ob;
+            const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
+            if (n >= 2 * M) continue;
+            const bool live = er == 0 && tt == n * om.og && n < om.lim;
+            yrow[j] = (live ? rl[n] : 0.f) + b;
           }
         }
       }

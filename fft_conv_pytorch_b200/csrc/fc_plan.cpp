@@ -68,6 +68,8 @@ void finish_pass(fc_pass& p) {
   int budget = rfast ? 2048 : 4096;
   if (rfast && 16 * p.M > budget) budget = 16 * p.M;
   if (budget > 8192) budget = 8192;
+  static const int env_flat = std::getenv("FFTCONV_B200_TILE_FLAT") ? std::atoi(std::getenv("FFTCONV_B200_TILE_FLAT")) : 0;  // experiments
+  if (!rfast && env_flat > 0) budget = env_flat;
   if (p.M > budget) budget = p.M;
   int T = 1;
   while (T * 2 * p.M <= budget && T * 2 <= 64) T *= 2;
@@ -459,7 +461,8 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   if (P.padding_mode < 0 || P.padding_mode > 3) return fail(FC_EINVAL, "unknown padding_mode");
   if (P.transposed && P.padding_mode != FC_PAD_CONSTANT) return fail(FC_EINVAL, "fft_conv_transpose has no padding_mode");
   pl->nd = nd;
-  pl->threads = P.threads > 0 ? P.threads : 256;
+  static const int env_threads = std::getenv("FFTCONV_B200_THREADS") ? std::atoi(std::getenv("FFTCONV_B200_THREADS")) : 0;  // experiments
+  pl->threads = P.threads > 0 ? P.threads : env_threads > 0 ? env_threads : 256;
   if (pl->threads % 32 || pl->threads > 1024) return fail(FC_EINVAL, "threads must be a multiple of 32, <= 1024");
   const bool poly = !(P.flags & FC_FLAG_NO_POLYPHASE);
 
@@ -688,9 +691,10 @@ int64_t pass_bytes(const fc_pass& p) {
   return in_b + out_b;
 }
 
-bool fast_line_len(int M) { return M == 256 || M == 512; }
+bool fast_line_len(int M) { return M == 256 || M == 512 || M == 1024; }
 
-// Re-tile a pass for the transposing fast kernels (16 lines per tile, tiles never straddle an outer item).
+// Re-tile a pass for the transposing fast kernels: 16 lines per tile (128-byte segments on the transposed side;
+// 32-line tiles measured the same on B200), tiles never straddle an outer item.
 void retile16(fc_pass& p) {
   p.T = 16;
   p.log2T = 4;

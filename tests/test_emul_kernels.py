@@ -103,6 +103,8 @@ _FAST_SHAPES = [
     ((2, 8, 256, 260), (8, 8, 3, 5), {}),  # full 8x8 channel groups, full lines: the predicate-free instantiation
     ((3, 4, 130, 270), (4, 2, 5, 3), dict(groups=2, padding=(3, 0), stride=(2, 1))),
     ((1, 2, 260, 600), (2, 2, 3, 3), dict(padding=(1, 1), padding_mode="reflect")),
+    ((1, 2, 20, 1100), (2, 2, 3, 5), {}),  # last axis 2048: the one-line-per-warp, 16-warp variant
+    ((1, 2, 18, 1030), (2, 1, 3, 4), dict(groups=2, stride=(1, 3))),  # ... with a strided scatter on store
 ]
 
 
