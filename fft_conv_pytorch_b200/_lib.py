@@ -17,6 +17,7 @@ FC_FLAG_NO_FAST_R2C = 4
 FC_FLAG_NO_FAST_C2R = 8
 FC_FLAG_NO_FUSED_MID = 16
 FC_FLAG_NO_TC = 32
+FC_FLAG_NO_FAST_C2C = 64
 
 _I3 = ctypes.c_int32 * FC_MAX_ND
 

@@ -67,6 +67,9 @@ int g_num_sms = 148;
 #define FC_FAST_ALL(X) \
   X(256, 2, 8, 3) X(256, 2, 8, 4) X(256, 1, 16, 2) X(512, 2, 8, 1) X(512, 2, 8, 2) X(512, 2, 8, 3) X(512, 1, 16, 1) X(512, 1, 16, 2) X(1024, 1, 16, 1)
 
+// ... and of the contiguous complex pass K2 / K3: X(N, lines per warp, warps, CTAs per SM).
+#define FC_FAST_C2C_ALL(X) X(256, 2, 8, 3) X(512, 2, 8, 2) X(1024, 1, 8, 2) X(2048, 1, 8, 1)
+
 void fused_set_attr() {
 #ifndef FC_CPU_EMUL
 #define FC_FUSED_ATTR(NN, NBB, WW, PL, OC) \
@@ -92,6 +95,10 @@ void init_once() {
   cudaFuncSetAttribute(fc_fast_c2r_kernel<MM, NLL, NWW, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     FC_FAST_ALL(FC_FAST_ATTR)
 #undef FC_FAST_ATTR
+#define FC_FAST_C2C_ATTR(NN, NLL, NWW, OC) \
+  cudaFuncSetAttribute(fc_fast_c2c_kernel<NN, NLL, NWW, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    FC_FAST_C2C_ALL(FC_FAST_C2C_ATTR)
+#undef FC_FAST_C2C_ATTR
     fused_set_attr();
     cudaFuncSetAttribute(fc_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     cudaFuncSetAttribute(fc_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
@@ -293,6 +300,33 @@ int launch_fast_c2r(const fc_pass& p, const void* in, void* out, const float2* t
   if (!done) return set_err(FC_EUNSUPPORTED, "no transposing C2R kernel for this line length");
   rec_mark();
   return check_cuda("fast c2r launch");
+}
+
+int launch_fast_c2c(const fc_pass& p, const void* in, void* out, const float2* tw, cudaStream_t st) {
+  fc_fast_c2c_args a;
+  a.p = p;
+  a.in = (const float2*)in;
+  a.out = (float2*)out;
+  a.tw = tw;
+  const int64_t n_lines = p.n_outer * p.R;
+  if (n_lines < 1) return FC_OK;
+  bool done = false;
+#define FC_FAST_C2C_LAUNCH(NN, NLL, NWW, OC)                                                 \
+  if (!done && p.N == NN) {                                                                  \
+    const size_t smem = (size_t)NLL * NWW * NN * sizeof(float2);                             \
+    const int64_t ctas = (n_lines + NLL * NWW - 1) / (NLL * NWW);                            \
+    int64_t grid = (int64_t)g_num_sms * OC;                                                  \
+    if (grid > ctas) grid = ctas;                                                            \
+    dim3 g((unsigned)grid), b(NWW * 32);                                                     \
+    auto k = fc_fast_c2c_kernel<NN, NLL, NWW, OC>;                                           \
+    FC_LAUNCH(k, g, b, smem, st, a);                                                         \
+    done = true;                                                                             \
+  }
+  FC_FAST_C2C_ALL(FC_FAST_C2C_LAUNCH)
+#undef FC_FAST_C2C_LAUNCH
+  if (!done) return set_err(FC_EUNSUPPORTED, "no contiguous complex pass kernel for this line length");
+  rec_mark();
+  return check_cuda("fast c2c launch");
 }
 
 int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, const float2* kspec, void* out, const float2* tw, cudaStream_t st) {
@@ -544,6 +578,9 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
         break;
       case FC_L_FAST_C2R:
         rc = launch_fast_c2r(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, d_bias, st);
+        break;
+      case FC_L_FAST_C2C:
+        rc = launch_fast_c2c(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, st);
         break;
       case FC_L_CONTRACT: {
         const fc_contract_desc& c = plan->contract;

@@ -147,7 +147,7 @@ FC_DEV void fc_wxchg(float2 (&v)[NL][M / 32], float2* line0, int lane) {
 // memory at line0 + l*LS as its exchange buffer.
 template <int M, int NL, int LS>
 FC_DEV void fc_wfft(float2 (&v)[NL][M / 32], float2* line0, const fc_wofs& o, const float2* tw, int tw_len, int lane) {
-  static_assert(M == 256 || M == 512 || M == 1024, "unsupported warp FFT length");
+  static_assert(M == 256 || M == 512 || M == 1024 || M == 2048, "unsupported warp FFT length");
   fc_wstage<M, NL, 8, 1>(v, tw, tw_len, lane);
   fc_wxchg8<M, NL, LS, 1>(v, line0, o);
   fc_wstage<M, NL, 8, 8>(v, tw, tw_len, lane);
@@ -159,7 +159,7 @@ FC_DEV void fc_wfft(float2 (&v)[NL][M / 32], float2* line0, const fc_wofs& o, co
   } else {
     fc_wstage<M, NL, 8, 64>(v, tw, tw_len, lane);
     fc_wxchg<M, NL, LS, 8, 64>(v, line0, lane);
-    fc_wstage<M, NL, 2, 512>(v, tw, tw_len, lane);
+    fc_wstage<M, NL, (M == 2048 ? 4 : 2), 512>(v, tw, tw_len, lane);  // radix 2 (M = 1024) or 4 (M = 2048)
   }
 }
 
@@ -377,6 +377,126 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
       }
     }
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2 / K3
+struct fc_fast_c2c_args {
+  fc_pass p;  // FC_C2C_FWD or FC_C2C_INV with contiguous lines on both sides (in_es == out_es == 1)
+  const float2* in;
+  float2* out;
+  const float2* tw;
+};
+
+// One axis pass over contiguous complex lines on the warp engine: a warp owns NL lines from load to store (coalesced
+// 256-byte requests straight between HBM and registers; shared memory only carries the exchanges between the
+// radix stages), so there is no block-wide barrier and no staging tile. Forward passes apply the gather map on load
+// and scale / conjugation on store; inverse passes the crop / stride / lattice map on store.
+template <int N, int NL, int NW, int OCC>
+__global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2c_kernel(fc_fast_c2c_args a) {
+  constexpr int E = N / 32;
+  const fc_pass& p = a.p;
+  FC_DYN_SMEM(smem);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float2* line0 = smem + (size_t)(NL * w) * N;
+  fc_wofs ofs;
+  ofs.init(lane);
+  const bool inv = p.kind == FC_C2C_INV;
+  const fc_imap im = p.imap;
+  const fc_omap om = p.omap;
+  const bool plain_in = inv || (im.mode == FC_PAD_CONSTANT && im.pad == 0 && im.up == 1 && im.sub == 1);
+  const int in_lim = inv ? N : (im.ext < im.L ? im.ext : im.L);  // plain_in: positions >= in_lim are zero
+  const bool plain_out = om.og == 1 && om.os == 1;
+  const int64_t n_lines = p.n_outer * p.R;
+  const int64_t n_groups = (n_lines + NL - 1) / NL;
+  const int64_t gstep = (int64_t)gridDim.x * NW;
+  for (int64_t g = (int64_t)blockIdx.x * NW + w; g < n_groups; g += gstep) {
+    float2 v[NL][E];
+    int64_t obase[NL];
+    bool ok[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const int64_t line = g * NL + l;
+      ok[l] = line < n_lines;
+      const int64_t o = ok[l] ? line / p.R : 0;
+      const int64_t r = ok[l] ? line - o * p.R : 0;
+      obase[l] = o * p.out_os + r * p.out_rs;
+      const float2* src = a.in + o * p.in_os + r * p.in_rs;
+      if (plain_in) {
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const int n = lane + 32 * q;
+          v[l][q] = (ok[l] && n < in_lim) ? __ldg(src + n) : make_float2(0.f, 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const int sidx = fc_imap_src(im, lane + 32 * q);
+          v[l][q] = (ok[l] && sidx >= 0) ? __ldg(src + sidx) : make_float2(0.f, 0.f);
+        }
+      }
+      if (inv) {
+#pragma unroll
+        for (int q = 0; q < E; ++q) v[l][q] = fc_conj(v[l][q]);
+      }
+    }
+    {  // pull the lines this warp takes next into L2 while these are transformed
+      const int64_t gn = g + gstep;
+      if (gn < n_groups) {
+        const int span = plain_in ? in_lim : im.L;  // stored elements of a line
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+          const int64_t line = gn * NL + l;
+          if (line >= n_lines) break;
+          const int64_t o = line / p.R, r = line - o * p.R;
+          const float2* nxt = a.in + o * p.in_os + r * p.in_rs;
+          for (int e = lane * 16; e < span; e += 32 * 16) fc_prefetch_l2(nxt + e);
+        }
+      }
+    }
+    fc_wfft<N, NL, N>(v, line0, ofs, a.tw, p.tw_len, lane);
+    if (!inv) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        if (!ok[l]) continue;
+        float2* dst = a.out + obase[l];
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          float2 val = fc_scale(v[l][q], p.scale);
+          if (p.conj_out) val = fc_conj(val);
+          dst[lane + 32 * q] = val;
+        }
+      }
+    } else if (plain_out) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        if (!ok[l]) continue;
+        float2* dst = a.out + obase[l];
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const int n = lane + 32 * q, j = n - om.ob;
+          if (j >= 0 && j < om.Lout) dst[j] = (n < om.lim) ? fc_conj(v[l][q]) : make_float2(0.f, 0.f);
+        }
+      }
+    } else {
+      // general stride / lattice map: stage the lines in the exchange buffers, then output-driven coalesced stores
+#pragma unroll
+      for (int l = 0; l < NL; ++l)
+#pragma unroll
+        for (int q = 0; q < E; ++q) line0[l * N + lane + 32 * q] = fc_conj(v[l][q]);
+      FC_SYNCWARP();
+      for (int l = 0; l < NL; ++l) {
+        if (!ok[l]) continue;
+        float2* dst = a.out + obase[l];
+        for (int j = lane; j < om.Lout; j += 32) {
+          const int tt = j * om.os + om.ob;
+          const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
+          if (n >= N) continue;
+          dst[j] = (tt == n * om.og && n < om.lim) ? line0[l * N + n] : make_float2(0.f, 0.f);
+        }
+      }
+      FC_SYNCWARP();
+    }
   }
 }
 

@@ -693,6 +693,12 @@ int64_t pass_bytes(const fc_pass& p) {
 
 bool fast_line_len(int M) { return M == 256 || M == 512 || M == 1024; }
 
+// Contiguous complex lines on both sides, a length the warp engine has: the pass can run on fc_fast_c2c_kernel.
+bool fast_c2c_ok(const fc_pass& p) {
+  return (p.kind == FC_C2C_FWD || p.kind == FC_C2C_INV) && !p.in_rfast && !p.out_rfast && p.in_es == 1 && p.out_es == 1 && !p.twiddle &&
+         p.pos_n == 1 && p.pos_r == 0 && (p.N == 256 || p.N == 512 || p.N == 1024 || p.N == 2048);
+}
+
 // Re-tile a pass for the transposing fast kernels: 16 lines per tile (128-byte segments on the transposed side;
 // 32-line tiles measured the same on B200), tiles never straddle an outer item.
 void retile16(fc_pass& p) {
@@ -736,9 +742,12 @@ void fc_plan_build_program(fc_plan* pl) {
         !(p.o_sA & 1) && !(p.o_sB & 1) && !(p.o_sC & 1) && p.scale == 1.f && !p.conj_out && p.pos_n == 1 && p.pos_r == 0) {
       L.type = FC_L_FAST_R2C;
       retile16(L.pass);
+    } else if (allow && !(flags & FC_FLAG_NO_FAST_C2C) && fast_c2c_ok(p)) {
+      L.type = FC_L_FAST_C2C;
     }
-    L.name = std::string(L.type == FC_L_FAST_R2C ? "fast_r2c_N" : "fwd_") + (L.type == FC_L_FAST_R2C ? "" : kKindName[p.kind]) +
-             (L.type == FC_L_FAST_R2C ? "" : "_N") + std::to_string(p.N);
+    L.name = L.type == FC_L_FAST_R2C   ? "fast_r2c_N" + std::to_string(p.N)
+             : L.type == FC_L_FAST_C2C ? "fast_c2c_fwd_N" + std::to_string(p.N)
+                                       : std::string("fwd_") + kKindName[p.kind] + "_N" + std::to_string(p.N);
     L.bytes = pass_bytes(p);
     pl->prog.push_back(L);
   }
@@ -822,8 +831,12 @@ void fc_plan_build_program(fc_plan* pl) {
         p.pos_n == 1 && p.pos_r == 0 && p.out_es == 1) {
       L.type = FC_L_FAST_C2R;
       retile16(L.pass);
+    } else if (allow && !(flags & FC_FLAG_NO_FAST_C2C) && fast_c2c_ok(p)) {
+      L.type = FC_L_FAST_C2C;
     }
-    L.name = (L.type == FC_L_FAST_C2R ? std::string("fast_c2r_N") : std::string("inv_") + kKindName[p.kind] + "_N") + std::to_string(p.N);
+    L.name = L.type == FC_L_FAST_C2R   ? "fast_c2r_N" + std::to_string(p.N)
+             : L.type == FC_L_FAST_C2C ? "fast_c2c_inv_N" + std::to_string(p.N)
+                                       : std::string("inv_") + kKindName[p.kind] + "_N" + std::to_string(p.N);
     L.bytes = pass_bytes(p);
     pl->prog.push_back(L);
   }

@@ -77,7 +77,8 @@ enum {
   FC_FLAG_NO_FAST_R2C = 4,  /* the three below switch the specialised kernels off one by one (tests, A/B timing) */
   FC_FLAG_NO_FAST_C2R = 8,
   FC_FLAG_NO_FUSED_MID = 16,
-  FC_FLAG_NO_TC = 32        /* keep the contraction on the SIMT kernel even when the tensor-core path qualifies */
+  FC_FLAG_NO_TC = 32,       /* keep the contraction on the SIMT kernel even when the tensor-core path qualifies */
+  FC_FLAG_NO_FAST_C2C = 64  /* keep contiguous complex axis passes on the generic block-level kernel */
 };
 
 typedef struct fc_plan fc_plan; /* opaque */

@@ -156,6 +156,38 @@ def test_fast_kernels_transposed_row_lattice():
     assert rel_err(y2, ref) < 1e-5
 
 
+_C2C_SHAPES = [
+    # first axis 256 .. 2048 with the fused middle switched off: the contiguous complex passes run on fc_fast_c2c_kernel
+    ((1, 2, 200, 40), (2, 2, 9, 3), {}, False),
+    ((2, 3, 300, 40), (3, 3, 5, 3), dict(padding=(2, 1), padding_mode="reflect"), False),  # non-trivial gather map
+    ((1, 2, 600, 36), (2, 1, 4, 3), dict(groups=2, stride=(3, 1), padding=(5, 0)), False),  # strided scatter on store
+    ((1, 1, 1100, 34), (1, 1, 3, 3), {}, False),  # N = 2048: 64 points per lane
+    ((1, 2, 150, 40), (2, 2, 3, 3), dict(stride=2, padding=1, output_padding=1), True),  # zero-stuffed signal
+    ((1, 2, 140, 40), (2, 1, 5, 3), dict(stride=2, dilation=2, groups=2), True),  # polyphase lattice on store
+]
+
+
+@pytest.mark.parametrize("xs,ws,kw,tr", _C2C_SHAPES)
+def test_fast_c2c_pass_matches_generic_and_oracle(xs, ws, kw, tr):
+    from oracle import fftconv_oracle as O
+
+    rng = np.random.RandomState(21)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = rng.standard_normal(ws).astype(np.float32)
+    cout = ws[1] * kw.get("groups", 1) if tr else ws[0]
+    b = rng.standard_normal(cout).astype(np.float32)
+    ofn = O.fft_conv_transpose if tr else O.fft_conv
+    ref = ofn(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), **kw)
+    y, p = emul.conv(x, w, b, transposed=tr, threads=256, flags=L.FC_FLAG_NO_FUSED_MID, **kw)
+    d = p.describe()
+    assert "fast_c2c_fwd" in d and "fast_c2c_inv" in d, d
+    assert y.shape == ref.shape and not np.isnan(y).any()
+    assert rel_err(y, ref) < 1e-5
+    y2, p2 = emul.conv(x, w, b, transposed=tr, threads=256, flags=L.FC_FLAG_NO_FUSED_MID | L.FC_FLAG_NO_FAST_C2C, **kw)
+    assert "fast_c2c" not in p2.describe()
+    assert rel_err(y2, ref) < 1e-5
+
+
 @pytest.mark.parametrize("xs,ws,groups", [((10, 40, 70), (36, 40, 5), 1), ((17, 70, 40), (66, 35, 3), 2)])
 def test_wide_channel_contraction_tiling(xs, ws, groups):
     """>= 32 output channels per group select the layout with several output tiles per CTA (BASELINE c4's
