@@ -179,6 +179,9 @@ int launch_contract(const float2* X, const float2* K, float2* Y, int64_t bins, i
     } else if (tb == 16 && to == 2) {
       auto k = fc_contract_kernel<16, 2>;
       FC_LAUNCH(k, g, b, 0, st, a);
+    } else if (tb == 4 && to == 8) {
+      auto k = fc_contract_kernel<4, 8>;
+      FC_LAUNCH(k, g, b, 0, st, a);
     } else {
       auto k = fc_contract_kernel<4, 4>;
       FC_LAUNCH(k, g, b, 0, st, a);
@@ -190,6 +193,15 @@ int launch_contract(const float2* X, const float2* K, float2* Y, int64_t bins, i
     const int oy = 4;
     dim3 b(32, oy), g((unsigned)((bins + 31) / 32), (unsigned)(a.btiles * ((a.otiles + oy - 1) / oy)), (unsigned)groups);
     auto k = fc_contract_kernel<8, 8>;
+    FC_LAUNCH(k, g, b, 0, st, a);
+  } else if (batch >= 3 && batch <= 4 && Og >= 8) {
+    // small batch, 8+ output channels per group (BASELINE c3, c5): the kernel spectrum is the dominant stream; a 4 x 8
+    // tile reads it once per thread and two output tiles per CTA share the signal spectrum through L1
+    a.btiles = 1;
+    a.otiles = (Og + 7) / 8;
+    const int oy = a.otiles >= 2 ? 2 : 1, bx = oy == 2 ? 32 : 128;
+    dim3 b(bx, oy), g((unsigned)((bins + bx - 1) / bx), (unsigned)((a.otiles + oy - 1) / oy), (unsigned)groups);
+    auto k = fc_contract_kernel<4, 8>;
     FC_LAUNCH(k, g, b, 0, st, a);
   } else {
     const int threads = 128;
@@ -350,8 +362,7 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
   a.n_units = (int64_t)P.groups * f.R * a.nbs;
   a.imap = f.imap;
   a.omap = f.omap;
-  const bool ring = false;  // fc_kb_traits::kRing (see fc_fused.cuh)
-  const size_t smem = (size_t)f.nb * f.ci * f.N * sizeof(float2) + (ring ? (size_t)FC_KB_RING_STAGES * (f.ci / 2) * f.N * sizeof(float2) : 0);
+  const size_t smem = (size_t)f.nb * f.ci * f.N * sizeof(float2);
   {  // distance (in units) to the CTA of the next wave on the same SM: what this CTA prefetches into L2
     int64_t per_sm = (int64_t)(228 * 1024) / (int64_t)(smem + 1024 + 256);
     const int64_t reg_lim = f.occ;  // launch bounds

@@ -516,86 +516,48 @@ struct fc_fused_args {
   fc_omap omap;
 };
 
-// N: transform length of the fused axis. CI: bound on channels per group (in and out). NB: batches per CTA
-// (= lines per warp: a warp transforms one channel of all NB batches together). W: compute warps per CTA. PLAIN: the
-// axis has an identity gather map with all N points stored, full channel groups (Ig == Og == CI) and a plain crop
-// on store (compiled without the general map / predication code).
-// Shared memory: NB*CI lines of N float2 (each line doubles as its warp's exchange buffer) and, for PLAIN with
-// N <= 512, a 3-stage ring of kernel-spectrum half-sets (CI/2 lines each) filled with bulk async copies (one
-// thread issues them; completion is tracked by mbarriers): the first half-sets stream in during phase 1, the
-// following ones while the previous output channel is accumulated, and phase 2 reads the kernel spectrum from
-// shared memory instead of waiting on L2 / HBM.
-#define FC_KB_RING_STAGES 3
-template <int N, int CI, int NB, bool PLAIN>
-struct fc_kb_traits {
-  // Measured on B200 (profiles/README.md): the ring (84 us at c2) loses to the register-pipelined loads (74 us) because
-  // three 16 KB stages per CTA do not cover the L2 latency of the kernel-spectrum stream; kept for larger rings.
-  static constexpr bool kRing = false && PLAIN && N <= 512;
-};
-
+// N: transform length of the fused axis. CI: bound on channels per group (in and out). NB: batches per CTA; a warp
+// transforms NL = min(NB, 2) lines (one channel, two batches) at a time. W: compute warps per CTA. PLAIN: the axis has
+// an identity gather map with all N points stored, full channel groups (Ig == Og == CI) and a plain crop on store
+// (compiled without the general map / predication code).
+// Shared memory: NB*CI lines of N float2; each line doubles as its warp's exchange buffer.
+// Measured alternatives that lost at BASELINE c2 (74 us) and were removed: staging the kernel spectrum through a ring
+// of bulk-copy stages (84 us), and 16-warp CTAs with NB = 4 whose batch pairs share kernel-spectrum reads (87 us).
 template <int N, int CI, int NB, int W, bool PLAIN, int OCC>
 __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_args a) {
   constexpr int E = N / 32, LS = CI * N;  // line (b, c) at xy + (b*CI + c)*N
-  constexpr bool RING = fc_kb_traits<N, CI, NB, PLAIN>::kRing;
+  constexpr int NL = NB < 2 ? NB : 2;     // lines per warp = batches per contraction thread
+  constexpr int NBG = NB / NL;            // batch groups of a CTA
   constexpr int H = CI / 2;               // input channels per kernel-spectrum half-set
+  static_assert(NB == NL * NBG, "NB is 1, 2 or a multiple of 2");
   FC_DYN_SMEM(xy);
-  float2* ring = xy + (size_t)NB * CI * N;  // [stage][H][N]
-  __shared__ fc_mbar kfull[FC_KB_RING_STAGES], kfree[FC_KB_RING_STAGES];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int Ig = a.Ig, Og = a.Og;
   const int64_t kstride = a.R * N;  // kernel-spectrum stride between input channels
-  if (RING) {
-    if (tid == 0) {
-      for (int s = 0; s < FC_KB_RING_STAGES; ++s) {
-        fc_mbar_init(&kfull[s], 1);
-        fc_mbar_init(&kfree[s], W * 32);
-      }
-      fc_mbar_init_fence();
-    }
-    __syncthreads();
-  }
-  // Thread 0 feeds the ring: stage number qi (running over all units of this CTA) holds the half-set h = qi mod 2*Og
-  // of its unit; before refilling a stage it waits until every thread has released the previous contents.
-  int64_t qi = 0;
-  auto issue_stage = [&](const float2* kl, int h) {
-    const int s = (int)(qi % FC_KB_RING_STAGES);
-    if (qi >= FC_KB_RING_STAGES) fc_mbar_wait(&kfree[s], (unsigned)((qi / FC_KB_RING_STAGES - 1) & 1));
-    fc_mbar_expect_tx(&kfull[s], (unsigned)(H * N * sizeof(float2)));
-#pragma unroll
-    for (int i = 0; i < H; ++i)  // lines (o = h/2, i = (h&1)*H + i) are consecutive: line index h*H + i
-      fc_bulk_g2s(ring + ((size_t)s * H + i) * N, kl + (int64_t)(h * H + i) * kstride, (unsigned)(N * sizeof(float2)), &kfull[s]);
-    ++qi;
-  };
   fc_wofs ofs;
   ofs.init(lane);
   const fc_omap om = a.omap;
   const bool plain_in = PLAIN;   // host guarantees: constant mode, no pad / zero-stuffing / subsampling, N stored points
   const bool plain_out = PLAIN;  // host guarantees: og == 1, os == 1, ob == 0, Lout <= lim
   const int out_lim = om.Lout < om.lim ? om.Lout : om.lim;
-  int64_t kq = 0;  // running count of ring stages consumed by this CTA
-  (void)kq;
   for (int64_t unit = blockIdx.x; unit < a.n_units; unit += gridDim.x) {
     const int bs = (int)(unit % a.nbs);
     const int64_t gr = unit / a.nbs;
     const int64_t r = gr % a.R;
     const int g = (int)(gr / a.R);
     const int b0 = bs * NB;
-    const float2* kl0 = a.kspec + (((int64_t)(g * Og) * Ig) * a.R + r) * N;  // kernel-spectrum line (o = 0, i = 0) of this bin
-    if (RING && tid == 0) {  // the first half-sets stream in during phase 1
-      for (int h = 0; h < FC_KB_RING_STAGES && h < 2 * Og; ++h) issue_stage(kl0, h);
-    }
     // ---- phase 1: forward transform of every (batch, input channel) line of this bin
-    const int n_it1 = (Ig + W - 1) / W;
+    const int n_task1 = Ig * NBG;
 #pragma unroll 1
-    for (int it = 0; it < n_it1; ++it) {
-      const int i = w + W * it;
-      if (i >= Ig) continue;  // warp-uniform
-      float2* line0 = xy + (size_t)i * N;
-      float2 v[NB][E];
+    for (int tk = w; tk < n_task1; tk += W) {  // warp-uniform
+      const int bg = tk / Ig, i = tk - bg * Ig;
+      float2* line0 = xy + (size_t)(bg * NL * CI + i) * N;
+      float2 v[NL][E];
 #pragma unroll
-      for (int bl = 0; bl < NB; ++bl) {
-        const bool active = b0 + bl < a.B;
-        const float2* src = a.xin + (((int64_t)(b0 + (active ? bl : 0)) * a.Cin + g * Ig + i) * a.R + r) * a.n_in;
+      for (int bl = 0; bl < NL; ++bl) {
+        const int bb = b0 + bg * NL + bl;
+        const bool active = bb < a.B;
+        const float2* src = a.xin + (((int64_t)(active ? bb : b0) * a.Cin + g * Ig + i) * a.R + r) * a.n_in;
         if (plain_in) {
 #pragma unroll
           for (int q = 0; q < E; ++q) {
@@ -610,9 +572,9 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
           }
         }
       }
-      fc_wfft<N, NB, LS>(v, line0, ofs, a.tw, a.tw_len, lane);  // the lines themselves are the exchange buffers
+      fc_wfft<N, NL, LS>(v, line0, ofs, a.tw, a.tw_len, lane);  // the lines themselves are the exchange buffers
 #pragma unroll
-      for (int bl = 0; bl < NB; ++bl)
+      for (int bl = 0; bl < NL; ++bl)
 #pragma unroll
         for (int q = 0; q < E; ++q) line0[bl * LS + lane + 32 * q] = v[bl][q];
     }
@@ -632,7 +594,7 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
           if (bsn * NB + bl < a.B)
             fc_prefetch_l2(a.xin + (((int64_t)(bsn * NB + bl) * a.Cin + gn * Ig + i) * a.R + rn) * a.n_in + seg * 16);
         }
-        if (!RING && bsn == 0) {  // and, once per bin, its slice of the kernel spectrum
+        if (bsn == 0) {  // and, once per bin, its slice of the kernel spectrum
           constexpr int kper = N * 8 / 128;
           for (int idx = tid; idx < Og * Ig * kper; idx += W * 32) {
             const int ln = idx / kper, seg = idx - ln * kper;
@@ -641,160 +603,112 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
         }
       }
     }
-    // ---- phase 2: per-bin contraction over the input channels of the group, in place (X -> Y); two adjacent bins
-    // per thread (16-byte accesses)
-    if (RING) {
-      const int u = tid;  // N/2 <= W*32 bin pairs: one per thread (threads beyond only keep the ring protocol)
-      const bool work = u < N / 2;
-      float4 xr[NB][CI];
-      if (work) {
+    // ---- phase 2: per-bin contraction over the input channels of the group, in place (X -> Y); a thread takes two
+    // adjacent bins (16-byte accesses) of one batch group. The kernel-spectrum loads run in two half-sets, one always
+    // in flight.
+    for (int idx = tid; idx < (N / 2) * NBG; idx += W * 32) {
+      const int u = idx & (N / 2 - 1), bg = idx / (N / 2);
+      float2* xb = xy + (size_t)(bg * NL * CI) * N + 2 * u;  // line (bl, c) of this batch group at xb + (bl*CI + c)*N
+      float4 xr[NL][CI];
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
+      for (int b = 0; b < NL; ++b)
 #pragma unroll
-          for (int i = 0; i < CI; ++i) xr[b][i] = *reinterpret_cast<const float4*>(xy + (size_t)(b * CI + i) * N + 2 * u);
-      }
+        for (int i = 0; i < CI; ++i) xr[b][i] = *reinterpret_cast<const float4*>(xb + (size_t)(b * CI + i) * N);
+      // one running pointer over the (o, i) lines of this bin: consecutive lines are kstride apart
+      const char* kp = reinterpret_cast<const char*>(a.kspec + (((int64_t)(g * Og) * Ig) * a.R + r) * N + 2 * u);
+      const int64_t ksb = kstride * (int64_t)sizeof(float2);
       const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 acc[NB];
-#pragma unroll 1
-      for (int h = 0; h < 2 * Og; ++h, ++kq) {
-        const int s = (int)(kq % FC_KB_RING_STAGES);
-        const int half = h & 1;
-        if (!half) {
+      float4 ka[H], kb[H];
 #pragma unroll
-          for (int b = 0; b < NB; ++b) acc[b] = zero4;
-        }
-        fc_mbar_wait(&kfull[s], (unsigned)((kq / FC_KB_RING_STAGES) & 1));
-        if (work) {
-          float4 kv[H];
-#pragma unroll
-          for (int i = 0; i < H; ++i) kv[i] = *reinterpret_cast<const float4*>(ring + ((size_t)s * H + i) * N + 2 * u);
-#pragma unroll
-          for (int i = 0; i < H; ++i) {
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-              const float4 x = half ? xr[b][i + H] : xr[b][i];
-              acc[b].x = fmaf(x.x, kv[i].x, acc[b].x);
-              acc[b].y = fmaf(x.x, kv[i].y, acc[b].y);
-              acc[b].z = fmaf(x.z, kv[i].z, acc[b].z);
-              acc[b].w = fmaf(x.z, kv[i].w, acc[b].w);
-              acc[b].x = fmaf(-x.y, kv[i].y, acc[b].x);
-              acc[b].y = fmaf(x.y, kv[i].x, acc[b].y);
-              acc[b].z = fmaf(-x.w, kv[i].w, acc[b].z);
-              acc[b].w = fmaf(x.w, kv[i].z, acc[b].w);
-            }
-          }
-        }
-        fc_mbar_arrive(&kfree[s]);  // this thread is done with the stage
-        if (tid == 0 && h >= 1 && h + FC_KB_RING_STAGES - 1 < 2 * Og) issue_stage(kl0, h + FC_KB_RING_STAGES - 1);  // refill the stage of h-1
-        if (half && work) {
-#pragma unroll
-          for (int b = 0; b < NB; ++b) *reinterpret_cast<float4*>(xy + (size_t)(b * CI + (h >> 1)) * N + 2 * u) = acc[b];
-        }
+      for (int i = 0; i < H; ++i) {
+        const bool on = PLAIN || i < Ig;  // PLAIN implies Ig == CI
+        ka[i] = on ? __ldg(reinterpret_cast<const float4*>(kp)) : zero4;
+        if (on) kp += ksb;
       }
-    } else {
-      // register-pipelined variant: the kernel-spectrum loads run in two half-sets, one always in flight
-      for (int u = tid; u < N / 2; u += W * 32) {
-        float4 xr[NB][CI];
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
-#pragma unroll
-          for (int i = 0; i < CI; ++i) xr[b][i] = *reinterpret_cast<const float4*>(xy + (size_t)(b * CI + i) * N + 2 * u);
-        // one running pointer over the (o, i) lines of this bin: consecutive lines are kstride apart
-        const char* kp = reinterpret_cast<const char*>(a.kspec + (((int64_t)(g * Og) * Ig) * a.R + r) * N + 2 * u);
-        const int64_t ksb = kstride * (int64_t)sizeof(float2);
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 ka[H], kb[H];
-#pragma unroll
-        for (int i = 0; i < H; ++i) {
-          const bool on = PLAIN || i < Ig;  // PLAIN implies Ig == CI
-          ka[i] = on ? __ldg(reinterpret_cast<const float4*>(kp)) : zero4;
-          if (on) kp += ksb;
-        }
-#pragma unroll
-        for (int i = 0; i < H; ++i) {
-          const bool on = PLAIN || i + H < Ig;
-          kb[i] = on ? __ldg(reinterpret_cast<const float4*>(kp)) : zero4;
-          if (on) kp += ksb;
-        }
+      for (int i = 0; i < H; ++i) {
+        const bool on = PLAIN || i + H < Ig;
+        kb[i] = on ? __ldg(reinterpret_cast<const float4*>(kp)) : zero4;
+        if (on) kp += ksb;
+      }
 #pragma unroll 1
-        for (int o = 0; o < Og; ++o) {
-          const bool more = o + 1 < Og;
-          float4 acc[NB];
+      for (int o = 0; o < Og; ++o) {
+        const bool more = o + 1 < Og;
+        float4 acc[NL];
 #pragma unroll
-          for (int b = 0; b < NB; ++b) acc[b] = zero4;
+        for (int b = 0; b < NL; ++b) acc[b] = zero4;
 #pragma unroll
-          for (int i = 0; i < H; ++i) {
+        for (int i = 0; i < H; ++i) {
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-              acc[b].x = fmaf(xr[b][i].x, ka[i].x, acc[b].x);
-              acc[b].y = fmaf(xr[b][i].x, ka[i].y, acc[b].y);
-              acc[b].z = fmaf(xr[b][i].z, ka[i].z, acc[b].z);
-              acc[b].w = fmaf(xr[b][i].z, ka[i].w, acc[b].w);
-              acc[b].x = fmaf(-xr[b][i].y, ka[i].y, acc[b].x);
-              acc[b].y = fmaf(xr[b][i].y, ka[i].x, acc[b].y);
-              acc[b].z = fmaf(-xr[b][i].w, ka[i].w, acc[b].z);
-              acc[b].w = fmaf(xr[b][i].w, ka[i].z, acc[b].w);
-            }
+          for (int b = 0; b < NL; ++b) {
+            acc[b].x = fmaf(xr[b][i].x, ka[i].x, acc[b].x);
+            acc[b].y = fmaf(xr[b][i].x, ka[i].y, acc[b].y);
+            acc[b].z = fmaf(xr[b][i].z, ka[i].z, acc[b].z);
+            acc[b].w = fmaf(xr[b][i].z, ka[i].w, acc[b].w);
+            acc[b].x = fmaf(-xr[b][i].y, ka[i].y, acc[b].x);
+            acc[b].y = fmaf(xr[b][i].y, ka[i].x, acc[b].y);
+            acc[b].z = fmaf(-xr[b][i].w, ka[i].w, acc[b].z);
+            acc[b].w = fmaf(xr[b][i].w, ka[i].z, acc[b].w);
           }
-          if (more) {
-#pragma unroll
-            for (int i = 0; i < H; ++i) {
-              const bool on = PLAIN || i < Ig;
-              if (on) {
-                ka[i] = __ldg(reinterpret_cast<const float4*>(kp));
-                kp += ksb;
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < H; ++i) {
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-              acc[b].x = fmaf(xr[b][i + H].x, kb[i].x, acc[b].x);
-              acc[b].y = fmaf(xr[b][i + H].x, kb[i].y, acc[b].y);
-              acc[b].z = fmaf(xr[b][i + H].z, kb[i].z, acc[b].z);
-              acc[b].w = fmaf(xr[b][i + H].z, kb[i].w, acc[b].w);
-              acc[b].x = fmaf(-xr[b][i + H].y, kb[i].y, acc[b].x);
-              acc[b].y = fmaf(xr[b][i + H].y, kb[i].x, acc[b].y);
-              acc[b].z = fmaf(-xr[b][i + H].w, kb[i].w, acc[b].z);
-              acc[b].w = fmaf(xr[b][i + H].w, kb[i].z, acc[b].w);
-            }
-          }
-          if (more) {
-#pragma unroll
-            for (int i = 0; i < H; ++i) {
-              const bool on = PLAIN || i + H < Ig;
-              if (on) {
-                kb[i] = __ldg(reinterpret_cast<const float4*>(kp));
-                kp += ksb;
-              }
-            }
-          }
-#pragma unroll
-          for (int b = 0; b < NB; ++b) *reinterpret_cast<float4*>(xy + (size_t)(b * CI + o) * N + 2 * u) = acc[b];
         }
+        if (more) {
+#pragma unroll
+          for (int i = 0; i < H; ++i) {
+            const bool on = PLAIN || i < Ig;
+            if (on) {
+              ka[i] = __ldg(reinterpret_cast<const float4*>(kp));
+              kp += ksb;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+#pragma unroll
+          for (int b = 0; b < NL; ++b) {
+            acc[b].x = fmaf(xr[b][i + H].x, kb[i].x, acc[b].x);
+            acc[b].y = fmaf(xr[b][i + H].x, kb[i].y, acc[b].y);
+            acc[b].z = fmaf(xr[b][i + H].z, kb[i].z, acc[b].z);
+            acc[b].w = fmaf(xr[b][i + H].z, kb[i].w, acc[b].w);
+            acc[b].x = fmaf(-xr[b][i + H].y, kb[i].y, acc[b].x);
+            acc[b].y = fmaf(xr[b][i + H].y, kb[i].x, acc[b].y);
+            acc[b].z = fmaf(-xr[b][i + H].w, kb[i].w, acc[b].z);
+            acc[b].w = fmaf(xr[b][i + H].w, kb[i].z, acc[b].w);
+          }
+        }
+        if (more) {
+#pragma unroll
+          for (int i = 0; i < H; ++i) {
+            const bool on = PLAIN || i + H < Ig;
+            if (on) {
+              kb[i] = __ldg(reinterpret_cast<const float4*>(kp));
+              kp += ksb;
+            }
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < NL; ++b) *reinterpret_cast<float4*>(xb + (size_t)(b * CI + o) * N) = acc[b];
       }
     }
     fc_named_bar_sync(1, W * 32);
     // ---- phase 3: inverse transform of every (batch, output channel) line, crop / stride on store
-    const int n_it3 = (Og + W - 1) / W;
+    const int n_task3 = Og * NBG;
 #pragma unroll 1
-    for (int it = 0; it < n_it3; ++it) {
-      const int o = w + W * it;
-      if (o >= Og) continue;  // warp-uniform
-      float2* line0 = xy + (size_t)o * N;
-      float2 v[NB][E];
+    for (int tk = w; tk < n_task3; tk += W) {  // warp-uniform
+      const int bg = tk / Og, o = tk - bg * Og;
+      const int bb0 = b0 + bg * NL;
+      float2* line0 = xy + (size_t)(bg * NL * CI + o) * N;
+      float2 v[NL][E];
 #pragma unroll
-      for (int bl = 0; bl < NB; ++bl)
+      for (int bl = 0; bl < NL; ++bl)
 #pragma unroll
         for (int q = 0; q < E; ++q) v[bl][q] = fc_conj(line0[bl * LS + lane + 32 * q]);
       FC_SYNCWARP();  // the lines become the exchange buffers: every lane must have read its inputs
-      fc_wfft<N, NB, LS>(v, line0, ofs, a.tw, a.tw_len, lane);
+      fc_wfft<N, NL, LS>(v, line0, ofs, a.tw, a.tw_len, lane);
       if (plain_out) {
 #pragma unroll
-        for (int bl = 0; bl < NB; ++bl) {
-          if (b0 + bl >= a.B) continue;
-          float2* dst = a.yout + (((int64_t)(b0 + bl) * a.Cout + g * Og + o) * a.R + r) * a.n_out;
+        for (int bl = 0; bl < NL; ++bl) {
+          if (bb0 + bl >= a.B) continue;
+          float2* dst = a.yout + (((int64_t)(bb0 + bl) * a.Cout + g * Og + o) * a.R + r) * a.n_out;
 #pragma unroll
           for (int q = 0; q < E; ++q) {
             const int n = lane + 32 * q;
@@ -802,24 +716,20 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
           }
         }
       } else {
-        // general crop / stride / lattice map: stage the lines in shared memory and scatter from there
+        // general crop / stride / lattice map: stage the lines in shared memory, then output-driven coalesced stores
 #pragma unroll
-        for (int bl = 0; bl < NB; ++bl)
+        for (int bl = 0; bl < NL; ++bl)
 #pragma unroll
           for (int q = 0; q < E; ++q) line0[bl * LS + lane + 32 * q] = fc_conj(v[bl][q]);
         FC_SYNCWARP();
-        for (int bl = 0; bl < NB; ++bl) {
-          if (b0 + bl >= a.B) continue;
-          float2* dst = a.yout + (((int64_t)(b0 + bl) * a.Cout + g * Og + o) * a.R + r) * a.n_out;
-          for (int n = lane; n < N; n += 32) {
-            const float2 val = line0[bl * LS + n];
-            for (int e = 0; e < om.og; ++e) {
-              const int tt = n * om.og + e - om.ob;
-              if (tt < 0 || (tt % om.os)) continue;
-              const int j = tt / om.os;
-              if (j >= om.Lout) continue;
-              dst[j] = (e == 0 && n < om.lim) ? val : make_float2(0.f, 0.f);
-            }
+        for (int bl = 0; bl < NL; ++bl) {
+          if (bb0 + bl >= a.B) continue;
+          float2* dst = a.yout + (((int64_t)(bb0 + bl) * a.Cout + g * Og + o) * a.R + r) * a.n_out;
+          for (int j = lane; j < om.Lout; j += 32) {
+            const int tt = j * om.os + om.ob;
+            const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
+            if (n >= N) continue;
+            dst[j] = (tt == n * om.og && n < om.lim) ? line0[bl * LS + n] : make_float2(0.f, 0.f);
           }
         }
       }
