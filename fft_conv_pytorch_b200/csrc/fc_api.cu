@@ -10,6 +10,7 @@
 
 #include "fc_kernels.cuh"
 #include "fc_fused.cuh"
+#include "fc_column.cuh"
 #include "fc_tc.cuh"
 #include "fc_plan.h"
 
@@ -314,6 +315,34 @@ int launch_fast_c2r(const fc_pass& p, const void* in, void* out, const float2* t
   return check_cuda("fast c2r launch");
 }
 
+int launch_column(const fc_pass& p, const void* in, void* out, const float2* tw, const float* bias, cudaStream_t st) {
+  fc_col_args a;
+  a.p = p;
+  a.in = in;
+  a.out = out;
+  a.tw = tw;
+  a.bias = bias;
+  if (p.kind == FC_C2R) a.p.has_bias = bias ? 1 : 0;
+  const int64_t cols = p.n_outer * p.R;
+  if (cols < 1) return FC_OK;
+  const int bt = cols >= (int64_t)g_num_sms * 256 ? 128 : 32;  // few columns: one warp per CTA spreads them over the SMs
+  dim3 g((unsigned)((cols + bt - 1) / bt)), b(bt);
+  if (p.kind == FC_R2C) {
+    if (p.imap.mode == FC_PAD_CONSTANT && p.imap.up == 1 && p.imap.sub == 1) {
+      auto k = fc_col_r2c_kernel<true>;
+      FC_LAUNCH(k, g, b, 0, st, a);
+    } else {
+      auto k = fc_col_r2c_kernel<false>;
+      FC_LAUNCH(k, g, b, 0, st, a);
+    }
+  } else {
+    auto k = fc_col_c2r_kernel;
+    FC_LAUNCH(k, g, b, 0, st, a);
+  }
+  rec_mark();
+  return check_cuda("column pass launch");
+}
+
 int launch_fast_c2c(const fc_pass& p, const void* in, void* out, const float2* tw, cudaStream_t st) {
   fc_fast_c2c_args a;
   a.p = p;
@@ -592,6 +621,10 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
         break;
       case FC_L_FAST_C2C:
         rc = launch_fast_c2c(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, st);
+        break;
+      case FC_L_COL_R2C:
+      case FC_L_COL_C2R:
+        rc = launch_column(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, d_bias, st);
         break;
       case FC_L_CONTRACT: {
         const fc_contract_desc& c = plan->contract;

@@ -70,6 +70,8 @@ void finish_pass(fc_pass& p) {
   if (budget > 8192) budget = 8192;
   static const int env_flat = std::getenv("FFTCONV_B200_TILE_FLAT") ? std::atoi(std::getenv("FFTCONV_B200_TILE_FLAT")) : 0;  // experiments
   if (!rfast && env_flat > 0) budget = env_flat;
+  static const int env_rfast = std::getenv("FFTCONV_B200_TILE_RFAST") ? std::atoi(std::getenv("FFTCONV_B200_TILE_RFAST")) : 0;  // experiments
+  if (rfast && env_rfast > 0) budget = env_rfast;
   if (p.M > budget) budget = p.M;
   int T = 1;
   while (T * 2 * p.M <= budget && T * 2 <= 64) T *= 2;
@@ -551,9 +553,12 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
       pl->structure = FC_S_1D;
     } else {
       pl->structure = FC_S_1D_SPLIT;
-      const int l2 = ilog2(pl->ax[0].N);
-      pl->N1 = 1 << ((l2 + 1) / 2);
-      pl->N2 = pl->ax[0].N / pl->N1;
+      // Four-step split N = N1 * N2. Up to N = 64 * 2048 the strided pass is 64 points long: it then runs one thread
+      // per column entirely in registers (fc_column.cuh) and the contiguous pass on the warp engine (N2 = 256..2048).
+      // Longer lines fall back to a balanced split on the generic kernels.
+      const int N = pl->ax[0].N, l2 = ilog2(N);
+      pl->N1 = (N / 64 >= 256 && N / 64 <= 2048) ? 64 : 1 << ((l2 + 1) / 2);
+      pl->N2 = N / pl->N1;
       pl->ax[0].Nk = 0;  // bins are (N1/2+1) x N2 for the split layout
     }
   } else {
@@ -699,6 +704,13 @@ bool fast_c2c_ok(const fc_pass& p) {
          p.pos_n == 1 && p.pos_r == 0 && (p.N == 256 || p.N == 512 || p.N == 1024 || p.N == 2048);
 }
 
+// The strided pass of the four-step split with 64-point columns: one thread per column (fc_column.cuh).
+bool column_pass_ok(const fc_pass& p) {
+  if (p.N != 64 || !p.twiddle || !p.in_rfast || !p.out_rfast || p.pos_r != 1 || p.row_og > 1) return false;
+  if (p.kind == FC_R2C) return p.in_rs == 0 && p.in_es == 1 && p.out_rs == 1;
+  return p.kind == FC_C2R && p.in_rs == 1 && p.out_rs == 0 && p.out_es == 1;
+}
+
 // Re-tile a pass for the transposing fast kernels: 16 lines per tile (128-byte segments on the transposed side;
 // 32-line tiles measured the same on B200), tiles never straddle an outer item.
 void retile16(fc_pass& p) {
@@ -744,8 +756,11 @@ void fc_plan_build_program(fc_plan* pl) {
       retile16(L.pass);
     } else if (allow && !(flags & FC_FLAG_NO_FAST_C2C) && fast_c2c_ok(p)) {
       L.type = FC_L_FAST_C2C;
+    } else if (allow && !(flags & FC_FLAG_NO_FAST_R2C) && p.kind == FC_R2C && column_pass_ok(p)) {
+      L.type = FC_L_COL_R2C;
     }
     L.name = L.type == FC_L_FAST_R2C   ? "fast_r2c_N" + std::to_string(p.N)
+             : L.type == FC_L_COL_R2C  ? "col_r2c_N" + std::to_string(p.N)
              : L.type == FC_L_FAST_C2C ? "fast_c2c_fwd_N" + std::to_string(p.N)
                                        : std::string("fwd_") + kKindName[p.kind] + "_N" + std::to_string(p.N);
     L.bytes = pass_bytes(p);
@@ -833,8 +848,11 @@ void fc_plan_build_program(fc_plan* pl) {
       retile16(L.pass);
     } else if (allow && !(flags & FC_FLAG_NO_FAST_C2C) && fast_c2c_ok(p)) {
       L.type = FC_L_FAST_C2C;
+    } else if (allow && !(flags & FC_FLAG_NO_FAST_C2R) && p.kind == FC_C2R && column_pass_ok(p)) {
+      L.type = FC_L_COL_C2R;
     }
     L.name = L.type == FC_L_FAST_C2R   ? "fast_c2r_N" + std::to_string(p.N)
+             : L.type == FC_L_COL_C2R  ? "col_c2r_N" + std::to_string(p.N)
              : L.type == FC_L_FAST_C2C ? "fast_c2c_inv_N" + std::to_string(p.N)
                                        : std::string("inv_") + kKindName[p.kind] + "_N" + std::to_string(p.N);
     L.bytes = pass_bytes(p);

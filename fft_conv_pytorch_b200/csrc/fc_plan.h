@@ -22,7 +22,7 @@ struct fc_step {
 };
 
 // One kernel launch of fc_conv.
-enum { FC_L_PASS = 0, FC_L_FAST_R2C = 1, FC_L_FAST_C2R = 2, FC_L_CONTRACT = 3, FC_L_FUSED = 4, FC_L_TC_X = 5, FC_L_TC_GEMM = 6, FC_L_TC_Y = 7, FC_L_FAST_C2C = 8 };
+enum { FC_L_PASS = 0, FC_L_FAST_R2C = 1, FC_L_FAST_C2R = 2, FC_L_CONTRACT = 3, FC_L_FUSED = 4, FC_L_TC_X = 5, FC_L_TC_GEMM = 6, FC_L_TC_Y = 7, FC_L_FAST_C2C = 8, FC_L_COL_R2C = 9, FC_L_COL_C2R = 10 };
 
 // Geometry of the fused "last forward axis -> contraction -> first inverse axis" kernel (fc_fused.cuh).
 struct fc_fused_desc {

@@ -50,56 +50,11 @@ void fc_emul_launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bo
   fc_emul_smem = nullptr;
 }
 
-// ---- mbarrier / named barrier stand-ins (see fc_async.cuh): blocking, condition-variable based
+// ---- named barrier stand-in (see fc_async.cuh)
 namespace {
-struct MbarImpl {
-  std::mutex m;
-  std::condition_variable cv;
-  unsigned count = 0, pending = 0, phase = 0;
-  long tx = 0;
-  void maybe_complete() {
-    if (pending == 0 && tx == 0) {
-      pending = count;
-      phase ^= 1;
-      cv.notify_all();
-    }
-  }
-};
 std::mutex g_named_m;
 std::map<std::pair<int, int>, std::unique_ptr<std::barrier<>>> g_named;
 }  // namespace
-struct fc_mbar {
-  void* impl;
-};
-void fc_emul_mbar_init(fc_mbar* b, unsigned count) {
-  auto* i = new MbarImpl();  // leaked on purpose: test infrastructure, a handful per launch
-  i->count = i->pending = count;
-  b->impl = i;
-}
-void fc_emul_mbar_arrive(fc_mbar* b) {
-  auto* i = (MbarImpl*)b->impl;
-  std::lock_guard<std::mutex> l(i->m);
-  --i->pending;
-  i->maybe_complete();
-}
-void fc_emul_mbar_expect_tx(fc_mbar* b, unsigned bytes) {
-  auto* i = (MbarImpl*)b->impl;
-  std::lock_guard<std::mutex> l(i->m);
-  i->tx += bytes;
-  --i->pending;
-  i->maybe_complete();
-}
-void fc_emul_mbar_complete_tx(fc_mbar* b, unsigned bytes) {
-  auto* i = (MbarImpl*)b->impl;
-  std::lock_guard<std::mutex> l(i->m);
-  i->tx -= bytes;
-  i->maybe_complete();
-}
-void fc_emul_mbar_wait(fc_mbar* b, unsigned parity) {
-  auto* i = (MbarImpl*)b->impl;
-  std::unique_lock<std::mutex> l(i->m);
-  i->cv.wait(l, [&] { return i->phase != parity; });
-}
 void fc_emul_named_barrier(int id, int count) {
   std::barrier<>* bar;
   {
