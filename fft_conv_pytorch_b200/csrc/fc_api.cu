@@ -237,7 +237,7 @@ struct fast_cfg {
   int nl, nw, occ;
 };
 fast_cfg fast_config(int M) {
-  fast_cfg c = M == 256 ? fast_cfg{2, 8, 3} : M == 512 ? fast_cfg{2, 8, 2} : fast_cfg{1, 16, 1};
+  fast_cfg c = M == 256 ? fast_cfg{2, 8, 4} : M == 512 ? fast_cfg{2, 8, 2} : fast_cfg{1, 16, 1};
   static const char* env = std::getenv("FFTCONV_B200_FAST");
   if (env) {
     fast_cfg e = c;

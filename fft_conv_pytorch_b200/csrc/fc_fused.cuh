@@ -305,7 +305,14 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
       const float2* src = a.in + (int64_t)o * p.in_os + r0 + (ok ? l : 0) + (int64_t)(tid / TR) * p.in_es;
       float2* dst = smem + l * LP + tid / TR;
       const int64_t sstep = KS * p.in_es;
-      for (int k = tid / TR; k <= M; k += KS, src += sstep, dst += KS) *dst = ok ? __ldg(src) : make_float2(0.f, 0.f);
+      // all loads of a thread are issued before the first shared-memory store (NIT requests in flight per thread)
+      constexpr int NIT = (M + KS) / KS;  // ceil((M + 1) / KS)
+      float2 t[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) t[it] = (ok && tid / TR + it * KS <= M) ? __ldg(src + it * sstep) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int it = 0; it < NIT; ++it)
+        if (tid / TR + it * KS <= M) dst[it * KS] = t[it];
     }
     {  // L2 prefetch of the next tile of this CTA: (M+1) segments of TR float2 = 128 bytes
       const int tn = t + gridDim.x;
@@ -366,6 +373,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
           float* yrow = a.out + o * p.out_os + jr * p.out_rs;
           // output-driven (coalesced stores): output j takes dense sample n = (j*os + ob) / og when the remainder
           // is 0 and n < lim, else it is bias only
+#pragma unroll 8
           for (int j = lane; j < om.Lout; j += 32) {
             const int tt = j * om.os + om.ob;
             const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
@@ -488,6 +496,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2c_kernel(fc_fast_c2c_a
       for (int l = 0; l < NL; ++l) {
         if (!ok[l]) continue;
         float2* dst = a.out + obase[l];
+#pragma unroll 8
         for (int j = lane; j < om.Lout; j += 32) {
           const int tt = j * om.os + om.ob;
           const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
@@ -725,6 +734,7 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
         for (int bl = 0; bl < NL; ++bl) {
           if (bb0 + bl >= a.B) continue;
           float2* dst = a.yout + (((int64_t)(bb0 + bl) * a.Cout + g * Og + o) * a.R + r) * a.n_out;
+#pragma unroll 8
           for (int j = lane; j < om.Lout; j += 32) {
             const int tt = j * om.os + om.ob;
             const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
