@@ -100,10 +100,12 @@ def get_plan(
         return e
 
 
-def clear_caches() -> None:
+def clear_caches(plans: bool = True) -> None:
+    """Drop the cached kernel spectra and (unless plans=False) the plans."""
     global _kspec_cache_bytes
     with _lock:
-        _plans.clear()
+        if plans:
+            _plans.clear()
         _kspec_cache.clear()
         _kspec_cache_bytes = 0
 
