@@ -69,7 +69,7 @@ int g_num_sms = 148;
   X(256, 2, 8, 3) X(256, 2, 8, 4) X(256, 1, 16, 2) X(512, 2, 8, 1) X(512, 2, 8, 2) X(512, 2, 8, 3) X(512, 1, 16, 1) X(512, 1, 16, 2) X(1024, 1, 16, 1)
 
 // ... and of the contiguous complex pass K2 / K3: X(N, lines per warp, warps, CTAs per SM).
-#define FC_FAST_C2C_ALL(X) X(256, 2, 8, 3) X(512, 2, 8, 2) X(1024, 1, 8, 2) X(2048, 1, 8, 1)
+#define FC_FAST_C2C_ALL(X) X(32, 2, 8, 4) X(64, 2, 8, 4) X(128, 2, 8, 4) X(256, 2, 8, 3) X(512, 2, 8, 2) X(1024, 1, 8, 2) X(2048, 1, 8, 1)
 
 void fused_set_attr() {
 #ifndef FC_CPU_EMUL
@@ -354,8 +354,9 @@ int launch_fast_c2c(const fc_pass& p, const void* in, void* out, const float2* t
   bool done = false;
 #define FC_FAST_C2C_LAUNCH(NN, NLL, NWW, OC)                                                 \
   if (!done && p.N == NN) {                                                                  \
-    const size_t smem = (size_t)NLL * NWW * NN * sizeof(float2);                             \
-    const int64_t ctas = (n_lines + NLL * NWW - 1) / (NLL * NWW);                            \
+    const int gpw = NN >= 256 ? 1 : 256 / NN; /* line groups per warp */                     \
+    const size_t smem = (size_t)NLL * NWW * gpw * (NN >= 256 ? NN : NN + 2) * sizeof(float2); \
+    const int64_t ctas = (n_lines + NLL * NWW * gpw - 1) / (NLL * NWW * gpw);                \
     int64_t grid = (int64_t)g_num_sms * OC;                                                  \
     if (grid > ctas) grid = ctas;                                                            \
     dim3 g((unsigned)grid), b(NWW * 32);                                                     \

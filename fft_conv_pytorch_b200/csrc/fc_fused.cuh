@@ -164,6 +164,72 @@ FC_DEV void fc_wfft(float2 (&v)[NL][M / 32], float2* line0, const fc_wofs& o, co
 }
 
 
+// ---- short lines (M = 32, 64, 128): a group of G = M/8 lanes owns a line (8 points per lane, layout gl + G*q), so a
+// warp transforms 32/G lines at once. Same Stockham stages as above with the lane index replaced by the lane's
+// position in its group; the exchanges use the generic swizzled pattern.
+template <int M, int G, int NL, int R, int Ns>
+FC_DEV void fc_gstage(float2 (&v)[NL][M / G], const float2* tw, int tw_len, int gl) {
+  constexpr int E = M / G, NBF = E / R;
+  float2 w[R];
+  if (Ns > 1 && Ns <= G) fc_twiddle_powers<R>(__ldg(tw + (gl & (Ns - 1)) * (tw_len / (Ns * R))), w);  // same for every t
+#pragma unroll
+  for (int t = 0; t < NBF; ++t) {
+    if (Ns > G) fc_twiddle_powers<R>(__ldg(tw + ((gl + G * t) & (Ns - 1)) * (tw_len / (Ns * R))), w);
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      float2 a[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r] = v[l][t + NBF * r];
+      if (Ns > 1) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) a[r] = fc_mul(a[r], w[r]);
+      }
+      fc_butterfly<R>(a);
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[l][t + NBF * r] = a[r];
+    }
+  }
+}
+
+template <int M, int G, int NL, int LS, int R, int Ns>
+FC_DEV void fc_gxchg(float2 (&v)[NL][M / G], float2* line0, int gl) {
+  constexpr int E = M / G, NBF = E / R;
+#pragma unroll
+  for (int l = 0; l < NL; ++l)
+#pragma unroll
+    for (int t = 0; t < NBF; ++t) {
+      const int j = gl + G * t;
+      const int k = j & (Ns - 1);
+      const int j0 = (j - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) line0[l * LS + fc_swz2(j0 + r * Ns)] = v[l][t + NBF * r];
+    }
+  FC_SYNCWARP();
+#pragma unroll
+  for (int l = 0; l < NL; ++l)
+#pragma unroll
+    for (int q = 0; q < E; ++q) v[l][q] = line0[l * LS + fc_swz2(gl + G * q)];
+  FC_SYNCWARP();
+}
+
+// Forward FFT of NL lines of M points held by a group of G = M/8 lanes; line l of the group exchanges through
+// line0 + l*LS (M float2, private to the group). Every lane of the warp must call it (warp-wide __syncwarp).
+template <int M, int G, int NL, int LS>
+FC_DEV void fc_gfft(float2 (&v)[NL][M / G], float2* line0, const float2* tw, int tw_len, int gl) {
+  static_assert((M == 32 || M == 64 || M == 128) && G * 8 == M, "group FFT: 8 points per lane");
+  fc_gstage<M, G, NL, 8, 1>(v, tw, tw_len, gl);
+  fc_gxchg<M, G, NL, LS, 8, 1>(v, line0, gl);
+  if (M == 32) {
+    fc_gstage<M, G, NL, 4, 8>(v, tw, tw_len, gl);
+  } else {
+    fc_gstage<M, G, NL, 8, 8>(v, tw, tw_len, gl);
+    if (M == 128) {
+      fc_gxchg<M, G, NL, LS, 8, 8>(v, line0, gl);
+      fc_gstage<M, G, NL, 2, 64>(v, tw, tw_len, gl);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K1
 struct fc_fast_r2c_args {
   fc_pass p;
@@ -402,13 +468,16 @@ struct fc_fast_c2c_args {
 // and scale / conjugation on store; inverse passes the crop / stride / lattice map on store.
 template <int N, int NL, int NW, int OCC>
 __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2c_kernel(fc_fast_c2c_args a) {
-  constexpr int E = N / 32;
+  constexpr int G = N >= 256 ? 32 : N / 8;  // lanes per line: the whole warp, or a group of N/8 lanes for short lines
+  constexpr int E = N / G, GPW = 32 / G;    // points per lane; line groups per warp
+  constexpr int LP = G == 32 ? N : N + 2;   // line pitch (short lines: the groups of a warp start on different banks)
   const fc_pass& p = a.p;
   FC_DYN_SMEM(smem);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  float2* line0 = smem + (size_t)(NL * w) * N;
+  const int gl = lane % G, gid = lane / G;
+  float2* line0 = smem + (size_t)((w * GPW + gid) * NL) * LP;
   fc_wofs ofs;
-  ofs.init(lane);
+  if (G == 32) ofs.init(lane);
   const bool inv = p.kind == FC_C2C_INV;
   const fc_imap im = p.imap;
   const fc_omap om = p.omap;
@@ -416,9 +485,11 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2c_kernel(fc_fast_c2c_a
   const int in_lim = inv ? N : (im.ext < im.L ? im.ext : im.L);  // plain_in: positions >= in_lim are zero
   const bool plain_out = om.og == 1 && om.os == 1;
   const int64_t n_lines = p.n_outer * p.R;
-  const int64_t n_groups = (n_lines + NL - 1) / NL;
-  const int64_t gstep = (int64_t)gridDim.x * NW;
-  for (int64_t g = (int64_t)blockIdx.x * NW + w; g < n_groups; g += gstep) {
+  const int64_t n_groups = (n_lines + NL - 1) / NL;  // a group of G lanes takes NL lines at a time
+  const int64_t gstep = (int64_t)gridDim.x * NW * GPW;
+  // the loop is warp-uniform (the exchanges synchronise the whole warp); lane groups past the end carry zeros
+  for (int64_t g0 = ((int64_t)blockIdx.x * NW + w) * GPW; g0 < n_groups; g0 += gstep) {
+    const int64_t g = g0 + gid;
     float2 v[NL][E];
     int64_t obase[NL];
     bool ok[NL];
@@ -433,13 +504,13 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2c_kernel(fc_fast_c2c_a
       if (plain_in) {
 #pragma unroll
         for (int q = 0; q < E; ++q) {
-          const int n = lane + 32 * q;
+          const int n = gl + G * q;
           v[l][q] = (ok[l] && n < in_lim) ? __ldg(src + n) : make_float2(0.f, 0.f);
         }
       } else {
 #pragma unroll
         for (int q = 0; q < E; ++q) {
-          const int sidx = fc_imap_src(im, lane + 32 * q);
+          const int sidx = fc_imap_src(im, gl + G * q);
           v[l][q] = (ok[l] && sidx >= 0) ? __ldg(src + sidx) : make_float2(0.f, 0.f);
         }
       }
@@ -448,7 +519,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2c_kernel(fc_fast_c2c_a
         for (int q = 0; q < E; ++q) v[l][q] = fc_conj(v[l][q]);
       }
     }
-    {  // pull the lines this warp takes next into L2 while these are transformed
+    {  // pull the lines this lane group takes next into L2 while these are transformed
       const int64_t gn = g + gstep;
       if (gn < n_groups) {
         const int span = plain_in ? in_lim : im.L;  // stored elements of a line
@@ -458,11 +529,14 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2c_kernel(fc_fast_c2c_a
           if (line >= n_lines) break;
           const int64_t o = line / p.R, r = line - o * p.R;
           const float2* nxt = a.in + o * p.in_os + r * p.in_rs;
-          for (int e = lane * 16; e < span; e += 32 * 16) fc_prefetch_l2(nxt + e);
+          for (int e = gl * 16; e < span; e += G * 16) fc_prefetch_l2(nxt + e);
         }
       }
     }
-    fc_wfft<N, NL, N>(v, line0, ofs, a.tw, p.tw_len, lane);
+    if constexpr (G == 32)
+      fc_wfft<N, NL, LP>(v, line0, ofs, a.tw, p.tw_len, lane);
+    else
+      fc_gfft<N, G, NL, LP>(v, line0, a.tw, p.tw_len, gl);
     if (!inv) {
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
@@ -472,7 +546,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2c_kernel(fc_fast_c2c_a
         for (int q = 0; q < E; ++q) {
           float2 val = fc_scale(v[l][q], p.scale);
           if (p.conj_out) val = fc_conj(val);
-          dst[lane + 32 * q] = val;
+          dst[gl + G * q] = val;
         }
       }
     } else if (plain_out) {
@@ -482,7 +556,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2c_kernel(fc_fast_c2c_a
         float2* dst = a.out + obase[l];
 #pragma unroll
         for (int q = 0; q < E; ++q) {
-          const int n = lane + 32 * q, j = n - om.ob;
+          const int n = gl + G * q, j = n - om.ob;
           if (j >= 0 && j < om.Lout) dst[j] = (n < om.lim) ? fc_conj(v[l][q]) : make_float2(0.f, 0.f);
         }
       }
@@ -491,17 +565,18 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2c_kernel(fc_fast_c2c_a
 #pragma unroll
       for (int l = 0; l < NL; ++l)
 #pragma unroll
-        for (int q = 0; q < E; ++q) line0[l * N + lane + 32 * q] = fc_conj(v[l][q]);
+        for (int q = 0; q < E; ++q) line0[l * LP + gl + G * q] = fc_conj(v[l][q]);
       FC_SYNCWARP();
+#pragma unroll
       for (int l = 0; l < NL; ++l) {
         if (!ok[l]) continue;
         float2* dst = a.out + obase[l];
-#pragma unroll 8
-        for (int j = lane; j < om.Lout; j += 32) {
+#pragma unroll 4
+        for (int j = gl; j < om.Lout; j += G) {
           const int tt = j * om.os + om.ob;
           const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
           if (n >= N) continue;
-          dst[j] = (tt == n * om.og && n < om.lim) ? line0[l * N + n] : make_float2(0.f, 0.f);
+          dst[j] = (tt == n * om.og && n < om.lim) ? line0[l * LP + n] : make_float2(0.f, 0.f);
         }
       }
       FC_SYNCWARP();

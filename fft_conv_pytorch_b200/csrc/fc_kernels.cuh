@@ -217,6 +217,7 @@ struct fc_line_info {
 };
 
 #define FC_MAX_T 128
+#define FC_LD_BATCH 8 /* global loads a thread of the generic pass keeps in flight */
 
 template <int KIND>
 __global__ void fc_pass_kernel(fc_pass_args a) {
@@ -266,88 +267,99 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
     }
     __syncthreads();
 
-    // ---- load tile into bufA
+    // ---- load tile into bufA. Each thread first issues FC_LD_BATCH independent global loads, then stores them to
+    // shared memory: the pass is a load -> transform -> store loop per CTA, so the loads in flight per thread are
+    // what hides the HBM latency.
     if (KIND == FC_R2C) {
       const float* x = reinterpret_cast<const float*>(a.in);
       float* dst = reinterpret_cast<float*>(bufA);
       const int total = T * N;
-      for (int idx = tid; idx < total; idx += nth) {
-        int l, n;
-        if (p.in_rfast) {
-          l = idx & (T - 1);
-          n = idx >> p.log2T;
-        } else {
-          l = idx >> lN;
-          n = idx & (N - 1);
-        }
-        const fc_line_info li = lines[l];
-        float val = 0.f;
-        if (li.valid) {
-          const int u = n * p.pos_n + (int)li.r * p.pos_r;  // dense position < 2^25 (plan limit)
-          const int s = fc_imap_src(p.imap, u);
-          if (s >= 0) val = __ldg(x + li.in_base + (int64_t)s * p.in_es);
-        }
-        dst[2 * (l * pitch + fc_swz(n >> 1)) + (n & 1)] = val;
-      }
-    } else if (KIND == FC_C2C_FWD) {
-      const float2* x = reinterpret_cast<const float2*>(a.in);
-      const int total = T * N;
-      for (int idx = tid; idx < total; idx += nth) {
-        int l, n;
-        if (p.in_rfast) {
-          l = idx & (T - 1);
-          n = idx >> p.log2T;
-        } else {
-          l = idx >> lN;
-          n = idx & (N - 1);
-        }
-        const fc_line_info li = lines[l];
-        float2 val = make_float2(0.f, 0.f);
-        if (li.valid) {
-          const int s = fc_imap_src(p.imap, n);
-          if (s >= 0) val = __ldg(x + li.in_base + (int64_t)s * p.in_es);
-        }
-        bufA[l * pitch + fc_swz(n)] = val;
-      }
-    } else if (KIND == FC_C2C_INV) {
-      const float2* x = reinterpret_cast<const float2*>(a.in);
-      const int total = T * N;
-      for (int idx = tid; idx < total; idx += nth) {
-        int l, n;
-        if (p.in_rfast) {
-          l = idx & (T - 1);
-          n = idx >> p.log2T;
-        } else {
-          l = idx >> lN;
-          n = idx & (N - 1);
-        }
-        const fc_line_info li = lines[l];
-        float2 val = make_float2(0.f, 0.f);
-        if (li.valid) val = fc_conj(__ldg(x + li.in_base + (int64_t)n * p.in_es));
-        bufA[l * pitch + fc_swz(n)] = val;
-      }
-    } else {  // FC_C2R: bins 0..M, plain layout
-      const float2* x = reinterpret_cast<const float2*>(a.in);
-      const int W = M + 1;
-      const int total = T * W;
-      for (int idx = tid; idx < total; idx += nth) {
-        int l, k;
-        if (p.in_rfast) {
-          l = idx & (T - 1);
-          k = idx >> p.log2T;
-        } else {
-          l = (int)__umulhi((unsigned)idx, rW);
-          k = idx - l * W;
-        }
-        const fc_line_info li = lines[l];
-        float2 val = make_float2(0.f, 0.f);
-        if (li.valid) {
-          val = __ldg(x + li.in_base + (int64_t)k * p.in_es);
-          if (p.twiddle) {
-            val = fc_mul(val, fc_conj(fc_big_twiddle(k, li.r, p, a.tw)));
+      for (int base = tid; base < total; base += nth * FC_LD_BATCH) {
+        float val[FC_LD_BATCH];
+        int off[FC_LD_BATCH];
+#pragma unroll
+        for (int u = 0; u < FC_LD_BATCH; ++u) {
+          const int idx = base + u * nth;
+          val[u] = 0.f;
+          off[u] = -1;
+          if (idx < total) {
+            int l, n;
+            if (p.in_rfast) {
+              l = idx & (T - 1);
+              n = idx >> p.log2T;
+            } else {
+              l = idx >> lN;
+              n = idx & (N - 1);
+            }
+            const fc_line_info li = lines[l];
+            off[u] = 2 * (l * pitch + fc_swz(n >> 1)) + (n & 1);
+            if (li.valid) {
+              const int pos = n * p.pos_n + (int)li.r * p.pos_r;  // dense position < 2^25 (plan limit)
+              const int s = fc_imap_src(p.imap, pos);
+              if (s >= 0) val[u] = __ldg(x + li.in_base + (int64_t)s * p.in_es);
+            }
           }
         }
-        bufA[l * pitch + k] = val;
+#pragma unroll
+        for (int u = 0; u < FC_LD_BATCH; ++u)
+          if (off[u] >= 0) dst[off[u]] = val[u];
+      }
+    } else {
+      // complex kinds: C2C_FWD (gather map), C2C_INV (conjugate), C2R (bins 0..M, plain layout, four-step twiddle)
+      const float2* x = reinterpret_cast<const float2*>(a.in);
+      const int W = M + 1;
+      const int total = (KIND == FC_C2R) ? T * W : T * N;
+      for (int base = tid; base < total; base += nth * FC_LD_BATCH) {
+        float2 val[FC_LD_BATCH];
+        int off[FC_LD_BATCH];
+#pragma unroll
+        for (int u = 0; u < FC_LD_BATCH; ++u) {
+          const int idx = base + u * nth;
+          val[u] = make_float2(0.f, 0.f);
+          off[u] = -1;
+          if (idx < total) {
+            int l, n;
+            if (p.in_rfast) {
+              l = idx & (T - 1);
+              n = idx >> p.log2T;
+            } else if (KIND == FC_C2R) {
+              l = (int)__umulhi((unsigned)idx, rW);
+              n = idx - l * W;
+            } else {
+              l = idx >> lN;
+              n = idx & (N - 1);
+            }
+            const fc_line_info li = lines[l];
+            off[u] = l * pitch + (KIND == FC_C2R ? n : fc_swz(n));
+            if (li.valid) {
+              if (KIND == FC_C2C_FWD) {
+                const int s = fc_imap_src(p.imap, n);
+                if (s >= 0) val[u] = __ldg(x + li.in_base + (int64_t)s * p.in_es);
+              } else if (KIND == FC_C2C_INV) {
+                val[u] = fc_conj(__ldg(x + li.in_base + (int64_t)n * p.in_es));
+              } else {
+                val[u] = __ldg(x + li.in_base + (int64_t)n * p.in_es);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < FC_LD_BATCH; ++u) {
+          if (off[u] < 0) continue;
+          if (KIND == FC_C2R && p.twiddle) {  // four-step twiddle, applied once the loads have been issued
+            const int idx = base + u * nth;
+            int l, n;
+            if (p.in_rfast) {
+              l = idx & (T - 1);
+              n = idx >> p.log2T;
+            } else {
+              l = (int)__umulhi((unsigned)idx, rW);
+              n = idx - l * W;
+            }
+            val[u] = fc_mul(val[u], fc_conj(fc_big_twiddle(n, lines[l].r, p, a.tw)));
+          }
+          bufA[off[u]] = val[u];
+        }
       }
     }
     __syncthreads();

@@ -701,7 +701,7 @@ bool fast_line_len(int M) { return M == 256 || M == 512 || M == 1024; }
 // Contiguous complex lines on both sides, a length the warp engine has: the pass can run on fc_fast_c2c_kernel.
 bool fast_c2c_ok(const fc_pass& p) {
   return (p.kind == FC_C2C_FWD || p.kind == FC_C2C_INV) && !p.in_rfast && !p.out_rfast && p.in_es == 1 && p.out_es == 1 && !p.twiddle &&
-         p.pos_n == 1 && p.pos_r == 0 && (p.N == 256 || p.N == 512 || p.N == 1024 || p.N == 2048);
+         p.pos_n == 1 && p.pos_r == 0 && p.N >= 32 && p.N <= 2048;
 }
 
 // The strided pass of the four-step split with 64-point columns: one thread per column (fc_column.cuh).

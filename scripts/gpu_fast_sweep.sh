@@ -1,10 +1,6 @@
 mkdir -p gpurun_out
 L=gpurun_out/fast_sweep.log; : > $L
-echo "== write" >> $L
-python bench.py --no-cpu-baseline --flush write >> $L 2>&1
-echo "== write+read" >> $L
-python bench.py --no-cpu-baseline --flush write+read >> $L 2>&1
-echo "== write+read c1" >> $L
-python bench.py --no-cpu-baseline --config c1 >> $L 2>&1
-echo "== write+read c3" >> $L
-python bench.py --no-cpu-baseline --config c3 >> $L 2>&1
+for v in "X=0" "FFTCONV_B200_KB_L1PF=1" "X=1" "FFTCONV_B200_KB_L1PF=1"; do
+  echo "== c2 $v" >> $L
+  env $v FFTCONV_SKIP_REF=1 python scripts/time_configs.py c2 >> $L 2>&1
+done

@@ -204,6 +204,13 @@ _C2C_SHAPES = [
     ((1, 1, 1100, 34), (1, 1, 3, 3), {}, False),  # N = 2048: 64 points per lane
     ((1, 2, 150, 40), (2, 2, 3, 3), dict(stride=2, padding=1, output_padding=1), True),  # zero-stuffed signal
     ((1, 2, 140, 40), (2, 1, 5, 3), dict(stride=2, dilation=2, groups=2), True),  # polyphase lattice on store
+    # short lines: a group of N/8 lanes per line (N = 32, 64, 128), several lines per warp, ragged line counts
+    ((3, 2, 30, 20), (2, 2, 3, 3), {}, False),
+    ((2, 3, 50, 36), (3, 3, 5, 3), dict(padding=(2, 1), padding_mode="circular"), False),
+    ((1, 2, 100, 20), (2, 1, 4, 3), dict(groups=2, stride=(3, 1), padding=(5, 0)), False),
+    ((1, 2, 40, 20), (2, 2, 3, 3), dict(stride=2, padding=1, output_padding=1), True),
+    ((2, 2, 20, 20, 20), (2, 2, 3, 3, 3), {}, False),  # 3-d: the z passes
+    ((1, 2, 40, 12, 10), (2, 2, 5, 3, 3), dict(stride=(2, 1, 1), dilation=(2, 1, 1)), True),
 ]
 
 
