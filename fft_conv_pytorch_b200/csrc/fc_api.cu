@@ -11,6 +11,7 @@
 #include "fc_kernels.cuh"
 #include "fc_fused.cuh"
 #include "fc_column.cuh"
+#include "fc_plane.cuh"
 #include "fc_tc.cuh"
 #include "fc_plan.h"
 
@@ -71,6 +72,9 @@ int g_num_sms = 148;
 // ... and of the contiguous complex pass K2 / K3: X(N, lines per warp, warps, CTAs per SM).
 #define FC_FAST_C2C_ALL(X) X(32, 2, 8, 4) X(64, 2, 8, 4) X(128, 2, 8, 4) X(256, 2, 8, 3) X(512, 2, 8, 2) X(1024, 1, 8, 2) X(2048, 1, 8, 1)
 
+// ... and of the two-axis plane kernels: X(NY, NZ).
+#define FC_PLANE_ALL(X) X(32, 32) X(32, 64) X(64, 32) X(64, 64)
+
 void fused_set_attr() {
 #ifndef FC_CPU_EMUL
 #define FC_FUSED_ATTR(NN, NBB, WW, PL, OC) \
@@ -100,6 +104,11 @@ void init_once() {
   cudaFuncSetAttribute(fc_fast_c2c_kernel<NN, NLL, NWW, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     FC_FAST_C2C_ALL(FC_FAST_C2C_ATTR)
 #undef FC_FAST_C2C_ATTR
+#define FC_PLANE_ATTR(NY, NZ)                                                                                  \
+  cudaFuncSetAttribute(fc_plane_fwd_kernel<NY, NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); \
+  cudaFuncSetAttribute(fc_plane_inv_kernel<NY, NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    FC_PLANE_ALL(FC_PLANE_ATTR)
+#undef FC_PLANE_ATTR
     fused_set_attr();
     cudaFuncSetAttribute(fc_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     cudaFuncSetAttribute(fc_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
@@ -341,6 +350,50 @@ int launch_column(const fc_pass& p, const void* in, void* out, const float2* tw,
   }
   rec_mark();
   return check_cuda("column pass launch");
+}
+
+int launch_plane(bool inverse, const fc_plane_desc& d, const void* in, void* out, const float2* tw, int tw_len, cudaStream_t st) {
+  fc_plane_args a;
+  std::memset(&a, 0, sizeof(a));
+  a.in = (const float2*)in;
+  a.out = (float2*)out;
+  a.tw = tw;
+  a.tw_len = tw_len;
+  a.nkx = d.nkx;
+  a.n_units = d.n_outer * d.nkx;
+  a.in_os = d.in_os;
+  a.out_os = d.out_os;
+  a.imy = d.imy;
+  a.imz = d.imz;
+  a.conj_out = d.conj_out;
+  a.scale = d.scale;
+  a.omy = d.omy;
+  a.omz = d.omz;
+  if (a.n_units < 1) return FC_OK;
+  // rows of the first pass live in the plane (pitch + 1); one exchange line (pitch + 2) per line of the second pass
+  const int n1 = inverse ? d.nz : d.ny, n2 = inverse ? d.ny : d.nz;  // first-pass / second-pass line lengths
+  const int rows = inverse ? d.ny : d.nz;
+  const size_t smem = ((size_t)rows * (n1 + 1) + (size_t)FC_PLANE_WARPS * (256 / n2) * 2 * (n2 + 2)) * sizeof(float2);
+  int64_t grid = (int64_t)g_num_sms * 3;
+  if (grid > a.n_units) grid = a.n_units;
+  dim3 g((unsigned)grid), b(FC_PLANE_WARPS * 32);
+  bool done = false;
+#define FC_PLANE_LAUNCH(NY, NZ)                     \
+  if (!done && d.ny == NY && d.nz == NZ) {          \
+    if (inverse) {                                  \
+      auto k = fc_plane_inv_kernel<NY, NZ>;         \
+      FC_LAUNCH(k, g, b, smem, st, a);              \
+    } else {                                        \
+      auto k = fc_plane_fwd_kernel<NY, NZ>;         \
+      FC_LAUNCH(k, g, b, smem, st, a);              \
+    }                                               \
+    done = true;                                    \
+  }
+  FC_PLANE_ALL(FC_PLANE_LAUNCH)
+#undef FC_PLANE_LAUNCH
+  if (!done) return set_err(FC_EUNSUPPORTED, "no plane kernel for these extents");
+  rec_mark();
+  return check_cuda("plane pass launch");
 }
 
 int launch_fast_c2c(const fc_pass& p, const void* in, void* out, const float2* tw, cudaStream_t st) {
@@ -622,6 +675,10 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
         break;
       case FC_L_FAST_C2C:
         rc = launch_fast_c2c(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, st);
+        break;
+      case FC_L_PLANE_FWD:
+      case FC_L_PLANE_INV:
+        rc = launch_plane(L.type == FC_L_PLANE_INV, L.plane, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, plan->tw_len, st);
         break;
       case FC_L_COL_R2C:
       case FC_L_COL_C2R:

@@ -711,6 +711,56 @@ bool column_pass_ok(const fc_pass& p) {
   return p.kind == FC_C2R && p.in_rs == 1 && p.out_rs == 0 && p.out_es == 1;
 }
 
+bool plane_len(int n) { return n == 32 || n == 64; }
+bool plain_gather(const fc_imap& m) { return m.mode == FC_PAD_CONSTANT && m.up == 1 && m.sub == 1; }
+bool plain_crop(const fc_omap& m) { return m.og == 1 && m.os == 1 && m.ob >= 0; }
+
+// 3-d program: the y pass (contiguous lines in, transposing store) and the z pass (contiguous) of the forward
+// transform can run as one plane kernel when both extents are 32 or 64 and the gather maps are plain.
+bool plane_fwd_ok(const fc_pass& a, const fc_pass& b, fc_plane_desc& d) {
+  if (a.kind != FC_C2C_FWD || b.kind != FC_C2C_FWD || a.in_rfast || !a.out_rfast || b.in_rfast || b.out_rfast) return false;
+  if (!plane_len(a.N) || !plane_len(b.N) || a.in_es != 1 || b.in_es != 1 || b.out_es != 1 || a.twiddle || b.twiddle) return false;
+  if (!plain_gather(a.imap) || !plain_gather(b.imap) || a.pos_n != 1 || a.pos_r != 0 || b.pos_n != 1 || b.pos_r != 0) return false;
+  const int Ly = a.imap.L, Lz = b.imap.L;
+  if (b.R % a.N || a.in_rs != Ly || b.out_rs != b.N || a.n_outer != b.n_outer) return false;
+  const int64_t nkx = b.R / a.N;
+  if (a.R != nkx * Lz || a.in_os != nkx * Lz * Ly || a.scale != 1.f || a.conj_out) return false;
+  std::memset(&d, 0, sizeof(d));
+  d.ny = a.N;
+  d.nz = b.N;
+  d.nkx = (int32_t)nkx;
+  d.conj_out = b.conj_out;
+  d.scale = b.scale;
+  d.n_outer = a.n_outer;
+  d.in_os = a.in_os;
+  d.out_os = b.out_os;
+  d.imy = a.imap;
+  d.imz = b.imap;
+  return true;
+}
+
+// ... and likewise the z pass (contiguous) and the y pass (transposing load, contiguous cropped store) of the inverse.
+bool plane_inv_ok(const fc_pass& c, const fc_pass& e, fc_plane_desc& d) {
+  if (c.kind != FC_C2C_INV || e.kind != FC_C2C_INV || c.in_rfast || c.out_rfast || !e.in_rfast || e.out_rfast) return false;
+  if (!plane_len(c.N) || !plane_len(e.N) || c.in_es != 1 || c.out_es != 1 || e.out_es != 1 || c.twiddle || e.twiddle) return false;
+  if (!plain_crop(c.omap) || !plain_crop(e.omap) || c.pos_n != 1 || c.pos_r != 0 || e.pos_n != 1 || e.pos_r != 0) return false;
+  const int Oy = e.omap.Lout, Oz = c.omap.Lout;
+  if (c.R % e.N || c.in_rs != c.N || e.out_rs != Oy || c.n_outer != e.n_outer) return false;
+  const int64_t nkx = c.R / e.N;
+  if (e.R != nkx * Oz || e.out_os != nkx * Oz * Oy) return false;
+  std::memset(&d, 0, sizeof(d));
+  d.ny = e.N;
+  d.nz = c.N;
+  d.nkx = (int32_t)nkx;
+  d.scale = 1.f;
+  d.n_outer = c.n_outer;
+  d.in_os = c.in_os;
+  d.out_os = e.out_os;
+  d.omy = e.omap;
+  d.omz = c.omap;
+  return true;
+}
+
 // Re-tile a pass for the transposing fast kernels: 16 lines per tile (128-byte segments on the transposed side;
 // 32-line tiles measured the same on B200), tiles never straddle an outer item.
 void retile16(fc_pass& p) {
@@ -739,9 +789,23 @@ void fc_plan_build_program(fc_plan* pl) {
     fuse_mid = f.kind == FC_C2C_FWD && b.kind == FC_C2C_INV && !f.in_rfast && !f.out_rfast && !b.in_rfast && !b.out_rfast && f.N == b.N &&
                (f.N == 256 || f.N == 512 || f.N == 1024) && Ig <= 8 && Og <= 8 && f.R == b.R && f.in_es == 1 && b.out_es == 1;
   }
+  const bool allow_plane = allow && !(flags & FC_FLAG_NO_FAST_C2C) && !fuse_mid && pl->structure == FC_S_3D && nf == 3 && ni == 3;
   for (int i = 0; i < nf; ++i) {
     if (fuse_mid && i == nf - 1) break;
     fc_launch L;
+    std::memset(&L.plane, 0, sizeof(L.plane));
+    if (allow_plane && i == 1 && plane_fwd_ok(pl->sig_fwd[1].pass, pl->sig_fwd[2].pass, L.plane)) {
+      L.type = FC_L_PLANE_FWD;
+      L.pass = pl->sig_fwd[1].pass;
+      L.src = pl->sig_fwd[1].src;
+      L.dst = pl->sig_fwd[2].dst;
+      L.spec_is_y = 0;
+      std::memset(&L.fused, 0, sizeof(L.fused));
+      L.name = "plane_fwd_" + std::to_string(L.plane.ny) + "x" + std::to_string(L.plane.nz);
+      L.bytes = 8 * (pl->sig_fwd[1].pass.R * pl->sig_fwd[1].pass.n_in + pl->sig_fwd[2].pass.R * pl->sig_fwd[2].pass.n_out) * L.plane.n_outer;
+      pl->prog.push_back(L);
+      break;
+    }
     L.type = FC_L_PASS;
     L.pass = pl->sig_fwd[i].pass;
     L.src = pl->sig_fwd[i].src;
@@ -835,6 +899,20 @@ void fc_plan_build_program(fc_plan* pl) {
   }
   for (int i = fuse_mid ? 1 : 0; i < ni; ++i) {
     fc_launch L;
+    std::memset(&L.plane, 0, sizeof(L.plane));
+    if (allow_plane && i == 0 && plane_inv_ok(pl->inv[0].pass, pl->inv[1].pass, L.plane)) {
+      L.type = FC_L_PLANE_INV;
+      L.pass = pl->inv[0].pass;
+      L.src = pl->inv[0].src;
+      L.dst = pl->inv[1].dst;
+      L.spec_is_y = 1;
+      std::memset(&L.fused, 0, sizeof(L.fused));
+      L.name = "plane_inv_" + std::to_string(L.plane.ny) + "x" + std::to_string(L.plane.nz);
+      L.bytes = 8 * (pl->inv[0].pass.R * pl->inv[0].pass.n_in + pl->inv[1].pass.R * pl->inv[1].pass.n_out) * L.plane.n_outer;
+      pl->prog.push_back(L);
+      ++i;  // the y pass is part of the plane kernel
+      continue;
+    }
     L.type = FC_L_PASS;
     L.pass = pl->inv[i].pass;
     L.src = (fuse_mid && i == 1) ? FC_BUF_SPEC : pl->inv[i].src;

@@ -22,7 +22,7 @@ struct fc_step {
 };
 
 // One kernel launch of fc_conv.
-enum { FC_L_PASS = 0, FC_L_FAST_R2C = 1, FC_L_FAST_C2R = 2, FC_L_CONTRACT = 3, FC_L_FUSED = 4, FC_L_TC_X = 5, FC_L_TC_GEMM = 6, FC_L_TC_Y = 7, FC_L_FAST_C2C = 8, FC_L_COL_R2C = 9, FC_L_COL_C2R = 10 };
+enum { FC_L_PASS = 0, FC_L_FAST_R2C = 1, FC_L_FAST_C2R = 2, FC_L_CONTRACT = 3, FC_L_FUSED = 4, FC_L_TC_X = 5, FC_L_TC_GEMM = 6, FC_L_TC_Y = 7, FC_L_FAST_C2C = 8, FC_L_COL_R2C = 9, FC_L_COL_C2R = 10, FC_L_PLANE_FWD = 11, FC_L_PLANE_INV = 12 };
 
 // Geometry of the fused "last forward axis -> contraction -> first inverse axis" kernel (fc_fused.cuh).
 struct fc_fused_desc {
@@ -39,10 +39,21 @@ struct fc_fused_desc {
   fc_omap omap;
 };
 
+// Geometry of the two-axis plane kernels of the 3-d program (fc_plane.cuh).
+struct fc_plane_desc {
+  int32_t ny, nz, nkx;
+  int32_t conj_out;
+  float scale;
+  int64_t n_outer, in_os, out_os;
+  fc_imap imy, imz;
+  fc_omap omy, omz;
+};
+
 struct fc_launch {
   int type;
   fc_pass pass;  // FC_L_PASS / FC_L_FAST_*
   fc_fused_desc fused;
+  fc_plane_desc plane;
   int src, dst;  // FC_BUF_* (FC_BUF_SPEC as src of an inverse step = product spectrum; as dst of a forward step = signal spectrum)
   int spec_is_y; // which spectrum buffer FC_BUF_SPEC means for this launch: 0 = xspec, 1 = yspec
   std::string name;

@@ -209,8 +209,8 @@ _C2C_SHAPES = [
     ((2, 3, 50, 36), (3, 3, 5, 3), dict(padding=(2, 1), padding_mode="circular"), False),
     ((1, 2, 100, 20), (2, 1, 4, 3), dict(groups=2, stride=(3, 1), padding=(5, 0)), False),
     ((1, 2, 40, 20), (2, 2, 3, 3), dict(stride=2, padding=1, output_padding=1), True),
-    ((2, 2, 20, 20, 20), (2, 2, 3, 3, 3), {}, False),  # 3-d: the z passes
-    ((1, 2, 40, 12, 10), (2, 2, 5, 3, 3), dict(stride=(2, 1, 1), dilation=(2, 1, 1)), True),
+    ((2, 2, 20, 70, 12), (2, 2, 3, 3, 3), {}, False),  # 3-d: the z passes (y extent 128, so no plane kernel)
+    ((1, 2, 40, 66, 10), (2, 2, 5, 3, 3), dict(stride=(2, 1, 1), dilation=(2, 1, 1)), True),
 ]
 
 
@@ -232,6 +232,37 @@ def test_fast_c2c_pass_matches_generic_and_oracle(xs, ws, kw, tr):
     assert rel_err(y, ref) < 1e-5
     y2, p2 = emul.conv(x, w, b, transposed=tr, threads=256, flags=L.FC_FLAG_NO_FUSED_MID | L.FC_FLAG_NO_FAST_C2C, **kw)
     assert "fast_c2c" not in p2.describe()
+    assert rel_err(y2, ref) < 1e-5
+
+
+_PLANE_SHAPES = [
+    # 3-d problems whose y and z transform extents are 32 or 64: the two middle passes run as one plane kernel
+    ((2, 2, 20, 20, 20), (2, 2, 3, 3, 3), {}, False),
+    ((1, 3, 40, 20, 18), (2, 3, 5, 3, 3), dict(padding=(2, 1, 0)), False),  # 64 x 32 plane, zero padding on load
+    ((1, 2, 24, 50, 12), (2, 2, 3, 7, 3), dict(padding=(0, 3, 1)), False),  # 32 x 64 plane
+    ((1, 2, 60, 60, 10), (2, 1, 17, 17, 3), dict(groups=2), False),  # 64 x 64 plane
+    ((1, 2, 20, 20, 20), (2, 2, 3, 3, 3), dict(padding=1), True),  # transposed, stride 1: crop offset on store
+]
+
+
+@pytest.mark.parametrize("xs,ws,kw,tr", _PLANE_SHAPES)
+def test_plane_kernels_match_generic_and_oracle(xs, ws, kw, tr):
+    from oracle import fftconv_oracle as O
+
+    rng = np.random.RandomState(41)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = rng.standard_normal(ws).astype(np.float32)
+    cout = ws[1] * kw.get("groups", 1) if tr else ws[0]
+    b = rng.standard_normal(cout).astype(np.float32)
+    ofn = O.fft_conv_transpose if tr else O.fft_conv
+    ref = ofn(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), **kw)
+    y, p = emul.conv(x, w, b, transposed=tr, threads=256, **kw)
+    d = p.describe()
+    assert "plane_fwd" in d and "plane_inv" in d and p.info.n_launches == 5, d
+    assert y.shape == ref.shape and not np.isnan(y).any()
+    assert rel_err(y, ref) < 1e-5
+    y2, p2 = emul.conv(x, w, b, transposed=tr, threads=256, flags=L.FC_FLAG_NO_FAST_C2C, **kw)
+    assert "plane" not in p2.describe()
     assert rel_err(y2, ref) < 1e-5
 
 
