@@ -67,6 +67,7 @@ int g_num_sms = 148;
 
 // Instantiated variants of the transposing kernels K1 / K4: X(M, lines per warp, warps, CTAs per SM).
 #define FC_FAST_ALL(X) \
+  X(32, 2, 8, 4) X(64, 2, 8, 4) X(128, 2, 8, 4) \
   X(256, 2, 8, 3) X(256, 2, 8, 4) X(256, 1, 16, 2) X(512, 2, 8, 1) X(512, 2, 8, 2) X(512, 2, 8, 3) X(512, 1, 16, 1) X(512, 1, 16, 2) X(1024, 1, 16, 1)
 
 // ... and of the contiguous complex pass K2 / K3: X(N, lines per warp, warps, CTAs per SM).
@@ -246,7 +247,7 @@ struct fast_cfg {
   int nl, nw, occ;
 };
 fast_cfg fast_config(int M) {
-  fast_cfg c = M == 256 ? fast_cfg{2, 8, 4} : M == 512 ? fast_cfg{2, 8, 2} : fast_cfg{1, 16, 1};
+  fast_cfg c = M <= 256 ? fast_cfg{2, 8, 4} : M == 512 ? fast_cfg{2, 8, 2} : fast_cfg{1, 16, 1};
   static const char* env = std::getenv("FFTCONV_B200_FAST");
   if (env) {
     fast_cfg e = c;

@@ -230,6 +230,19 @@ FC_DEV void fc_gfft(float2 (&v)[NL][M / G], float2* line0, const float2* tw, int
   }
 }
 
+// Write the registers of a lane (layout gl + G*q) to the swizzled slots of its lines.
+template <int M, int G, int NL, int LS>
+FC_DEV void fc_lwrite(const float2 (&v)[NL][M / G], float2* line0, const fc_wofs& o, int gl) {
+  if constexpr (G == 32) {
+    fc_wwrite<M, NL, LS>(v, line0, o);
+  } else {
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+#pragma unroll
+      for (int q = 0; q < M / G; ++q) line0[l * LS + fc_swz2(gl + G * q)] = v[l][q];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K1
 struct fc_fast_r2c_args {
   fc_pass p;
@@ -245,16 +258,20 @@ struct fc_fast_r2c_args {
 // separate transposition tile is needed and M = 512 leaves room for several CTAs per SM.
 template <int M, int NL, int NW, int OCC>
 __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_args a) {
-  constexpr int E = M / 32, TR = NL * NW, LP = M + 1, KS = NW * 32 / TR;  // TR lines per tile; KS bins per store sweep
-  static_assert(TR == 16 || TR == 32, "a tile is 16 or 32 lines");
+  constexpr int G = M >= 256 ? 32 : M / 8;  // lanes per line (short lines: a group of M/8 lanes, 32/G lines per warp pass)
+  constexpr int E = M / G, GPW = 32 / G;
+  constexpr int TR = NL * NW * GPW, LP = M + 1, KS = NW * 32 / TR;  // TR lines per tile; KS bins per store sweep
+  static_assert(TR >= 16 && (TR & (TR - 1)) == 0 && TR <= NW * 32, "a tile is a power-of-two number of lines");
   const fc_pass& p = a.p;
   FC_DYN_SMEM(smem);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  float2* line0 = smem + (NL * w) * LP;
+  const int gl = lane % G, gid = lane / G;
+  const int lrow = (w * GPW + gid) * NL;  // first tile line of this lane's group
+  float2* line0 = smem + lrow * LP;
   const int L = p.imap.L;
   const int tstep = p.tw_len / (2 * M);
   fc_wofs ofs;
-  ofs.init(lane);
+  if (G == 32) ofs.init(lane);
   // Software pipeline over the tiles of this CTA: the rows of tile t+1 are requested (into the registers the
   // transform has just released) before tile t is stored, so the load latency overlaps the transposed store.
   // index math in 32 bits (host guarantees n_tiles < 2^31); this kernel only serves the signal tensor, whose outer
@@ -266,12 +283,12 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
     const float* img = a.x + (int64_t)o * p.o_sA;
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
-      const int r = r0 + NL * w + l;
+      const int r = r0 + lrow + l;
       const bool valid = r < R;
-      const float2* row = reinterpret_cast<const float2*>(img + (int64_t)(valid ? r : 0) * p.in_rs) + lane;
+      const float2* row = reinterpret_cast<const float2*>(img + (int64_t)(valid ? r : 0) * p.in_rs) + gl;
 #pragma unroll
       for (int q = 0; q < E; ++q)  // L is even (host check), so the pair (2m, 2m + 1) is in or out together
-        v[l][q] = (valid && 2 * (lane + 32 * q) < L) ? __ldg(row + 32 * q) : make_float2(0.f, 0.f);
+        v[l][q] = (valid && 2 * (gl + G * q) < L) ? __ldg(row + G * q) : make_float2(0.f, 0.f);
     }
   };
   float2 v[NL][E];
@@ -280,8 +297,13 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
     const int o = t / tpo;
     const int r0 = (t - o * tpo) * TR;
     const int tn = t + gridDim.x;
-    if (a.dbg != 1) fc_wfft<M, NL, LP>(v, line0, ofs, a.tw, p.tw_len, lane);
-    fc_wwrite<M, NL, LP>(v, line0, ofs);
+    if (a.dbg != 1) {
+      if constexpr (G == 32)
+        fc_wfft<M, NL, LP>(v, line0, ofs, a.tw, p.tw_len, lane);
+      else
+        fc_gfft<M, G, NL, LP>(v, line0, a.tw, p.tw_len, gl);
+    }
+    fc_lwrite<M, G, NL, LP>(v, line0, ofs, gl);
     FC_SYNCWARP();
     // untangle the packed real transforms (same algebra as the generic R2C pass) into the registers
     float nyq[NL];
@@ -292,7 +314,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
     }
 #pragma unroll
     for (int q = 0; q < E; ++q) {
-      const int k = lane + 32 * q;
+      const int k = gl + G * q;
       const float2 wk = __ldg(a.tw + k * tstep);
       const int km = fc_swz2((M - k) & (M - 1));
 #pragma unroll
@@ -305,8 +327,8 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
       }
     }
     FC_SYNCWARP();  // every partner has been read: the lines can take the spectrum
-    fc_wwrite<M, NL, LP>(v, line0, ofs);
-    if (lane == 0) {
+    fc_lwrite<M, G, NL, LP>(v, line0, ofs, gl);
+    if (gl == 0) {
 #pragma unroll
       for (int l = 0; l < NL; ++l) line0[l * LP + M] = make_float2(nyq[l], 0.f);
     }
@@ -325,7 +347,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
       }
     }
     {  // transposed store: thread (l = tid % TR, k = tid / TR + KS j) writes TR consecutive rows of one bin (128 / 256 bytes)
-      const int l = tid & (TR - 1);
+      const int l = tid & (TR - 1);  // tile line l lives at smem + l*LP (see lrow)
       if (r0 + l < R && a.dbg != 2) {
         float2* dst = a.out + (int64_t)o * p.out_os + r0 + l + (int64_t)(tid / TR) * p.out_es;
         const float2* src = smem + l * LP;
@@ -350,17 +372,21 @@ struct fc_fast_c2r_args {
 // its bins and their Hermitian partners, and the lines then serve as the exchange buffers of the transform.
 template <int M, int NL, int NW, int OCC>
 __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_args a) {
-  constexpr int E = M / 32, TR = NL * NW, LP = M + 1, KS = NW * 32 / TR;  // TR lines per tile; KS bins per store sweep
-  static_assert(TR == 16 || TR == 32, "a tile is 16 or 32 lines");
+  constexpr int G = M >= 256 ? 32 : M / 8;  // lanes per line (short lines: a group of M/8 lanes, 32/G lines per warp pass)
+  constexpr int E = M / G, GPW = 32 / G;
+  constexpr int TR = NL * NW * GPW, LP = M + 1, KS = NW * 32 / TR;  // TR lines per tile; KS bins per load sweep
+  static_assert(TR >= 16 && (TR & (TR - 1)) == 0 && TR <= NW * 32, "a tile is a power-of-two number of lines");
   const fc_pass& p = a.p;
   FC_DYN_SMEM(smem);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  float2* line0 = smem + (NL * w) * LP;
+  const int gl = lane % G, gid = lane / G;
+  const int lrow = (w * GPW + gid) * NL;  // first tile line of this lane's group
+  float2* line0 = smem + lrow * LP;
   const int tstep = p.tw_len / (2 * M);
   const fc_omap om = p.omap;
   const bool plain_out = om.os == 1 && om.ob == 0 && om.og == 1 && !(om.Lout & 1) && !(p.out_rs & 1) && !(p.out_os & 1) && p.row_og == 1;
   fc_wofs ofs;
-  ofs.init(lane);
+  if (G == 32) ofs.init(lane);
   const int tpo = (int)p.tiles_per_outer, n_tiles = (int)p.n_tiles, R = (int)p.R;  // 32-bit index math (host: n_tiles < 2^31)
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int o = t / tpo;
@@ -395,7 +421,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
     float2 v[NL][E];
 #pragma unroll
     for (int q = 0; q < E; ++q) {
-      const int k = lane + 32 * q;
+      const int k = gl + G * q;
       const float2 wk = fc_conj(__ldg(a.tw + k * tstep));
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
@@ -407,16 +433,19 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
       }
     }
     FC_SYNCWARP();  // the lines are exchange buffers from here on
-    fc_wfft<M, NL, LP>(v, line0, ofs, a.tw, p.tw_len, lane);
+    if constexpr (G == 32)
+      fc_wfft<M, NL, LP>(v, line0, ofs, a.tw, p.tw_len, lane);
+    else
+      fc_gfft<M, G, NL, LP>(v, line0, a.tw, p.tw_len, gl);
     if (plain_out) {
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
-        const int64_t r = r0 + NL * w + l;
+        const int64_t r = r0 + lrow + l;
         if (r < p.R) {
           float* yrow = a.out + o * p.out_os + r * p.out_rs;
 #pragma unroll
           for (int q = 0; q < E; ++q) {
-            const int n0 = 2 * (lane + 32 * q);
+            const int n0 = 2 * (gl + G * q);
             if (n0 < om.Lout) *reinterpret_cast<float2*>(yrow + n0) = make_float2(v[l][q].x + b, -v[l][q].y + b);
           }
         }
@@ -427,10 +456,10 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
 #pragma unroll
       for (int l = 0; l < NL; ++l)
 #pragma unroll
-        for (int q = 0; q < E; ++q) line0[l * LP + lane + 32 * q] = make_float2(v[l][q].x, -v[l][q].y);
+        for (int q = 0; q < E; ++q) line0[l * LP + gl + G * q] = make_float2(v[l][q].x, -v[l][q].y);
       FC_SYNCWARP();
       for (int l = 0; l < NL; ++l) {
-        const int64_t r = r0 + NL * w + l;
+        const int64_t r = r0 + lrow + l;
         if (r >= p.R) continue;
         const float* rl = reinterpret_cast<const float*>(line0 + l * LP);
         for (int er = 0; er < p.row_og; ++er) {  // output rows owned by this dense line (one unless row lattice)
@@ -440,7 +469,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
           // output-driven (coalesced stores): output j takes dense sample n = (j*os + ob) / og when the remainder
           // is 0 and n < lim, else it is bias only
 #pragma unroll 8
-          for (int j = lane; j < om.Lout; j += 32) {
+          for (int j = gl; j < om.Lout; j += G) {
             const int tt = j * om.os + om.ob;
             const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
             if (n >= 2 * M) continue;

@@ -696,7 +696,7 @@ int64_t pass_bytes(const fc_pass& p) {
   return in_b + out_b;
 }
 
-bool fast_line_len(int M) { return M == 256 || M == 512 || M == 1024; }
+bool fast_line_len(int M) { return M == 32 || M == 64 || M == 128 || M == 256 || M == 512 || M == 1024; }
 
 // Contiguous complex lines on both sides, a length the warp engine has: the pass can run on fc_fast_c2c_kernel.
 bool fast_c2c_ok(const fc_pass& p) {
@@ -762,12 +762,14 @@ bool plane_inv_ok(const fc_pass& c, const fc_pass& e, fc_plane_desc& d) {
 }
 
 // Re-tile a pass for the transposing fast kernels: 16 lines per tile (128-byte segments on the transposed side;
-// 32-line tiles measured the same on B200), tiles never straddle an outer item.
+// 32-line tiles measured the same on B200) for M >= 256; shorter lines are handled by groups of M/8 lanes, 2 lines per
+// group and 8 warps, i.e. 4096/M lines per tile (fc_fast_tile_lines). Tiles never straddle an outer item.
 void retile16(fc_pass& p) {
-  p.T = 16;
-  p.log2T = 4;
+  const int T = fc_fast_tile_lines(p.M);
+  p.T = T;
+  p.log2T = ilog2(T);
   p.flat = 0;
-  p.tiles_per_outer = (p.R + 15) / 16;
+  p.tiles_per_outer = (p.R + T - 1) / T;
   p.n_tiles = p.tiles_per_outer * p.n_outer;
 }
 

@@ -15,6 +15,9 @@ enum {
   FC_S_3D = 4
 };
 
+// Lines per tile of the transposing fast kernels K1 / K4 (must match the instantiations in fc_api.cu).
+inline int fc_fast_tile_lines(int M) { return M >= 256 ? 16 : 4096 / M; }
+
 struct fc_step {
   fc_pass pass;
   int src;  // FC_BUF_*

@@ -19,6 +19,9 @@ CFG = {
     "c2": dict(x=(8, 8, 512, 512), w=(8, 8, 65, 65), tr=False, kw={}),
     "c3": dict(x=(4, 8, 64, 64, 64), w=(8, 8, 17, 17, 17), tr=False, kw={}),
     "c4": dict(x=(16, 256, 65536), w=(256, 256, 4097), tr=False, kw={}),
+    # not BASELINE configs: common image sizes, to watch the short-line kernels
+    "img128": dict(x=(32, 8, 128, 128), w=(8, 8, 15, 15), tr=False, kw={}),
+    "img256": dict(x=(16, 8, 256, 256), w=(8, 8, 31, 31), tr=False, kw={}),
     "c5_shard": dict(x=(4, 64, 1024, 1024), w=(64, 16, 31, 31), tr=True, kw=dict(stride=2, dilation=2, groups=4)),
 }
 

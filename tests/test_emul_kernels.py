@@ -160,6 +160,38 @@ def test_fast_kernels_transposed_row_lattice():
     assert rel_err(y2, ref) < 1e-5
 
 
+_SHORT_ROW_SHAPES = [
+    # last axis 64 / 128 / 256 real points: K1 / K4 with a group of M/8 lanes per row (M = 32, 64, 128)
+    ((2, 2, 70, 60), (2, 2, 5, 7), {}, False),
+    ((1, 3, 40, 100), (2, 3, 3, 9), {}, False),
+    ((2, 2, 30, 200), (3, 2, 3, 11), dict(groups=1), False),
+    ((1, 2, 50, 64), (2, 1, 3, 5), dict(groups=2, stride=(1, 2)), False),  # strided scatter in K4
+    ((1, 2, 20, 20, 60), (2, 2, 3, 3, 5), {}, False),  # 3-d, x extent 64
+    ((1, 2, 33, 50), (2, 2, 3, 4), dict(stride=(1, 2), dilation=(1, 2)), True),  # lattice on the last axis (K4 general path)
+]
+
+
+@pytest.mark.parametrize("xs,ws,kw,tr", _SHORT_ROW_SHAPES)
+def test_short_row_kernels_match_generic_and_oracle(xs, ws, kw, tr):
+    from oracle import fftconv_oracle as O
+
+    rng = np.random.RandomState(51)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = rng.standard_normal(ws).astype(np.float32)
+    cout = ws[1] * kw.get("groups", 1) if tr else ws[0]
+    b = rng.standard_normal(cout).astype(np.float32)
+    ofn = O.fft_conv_transpose if tr else O.fft_conv
+    ref = ofn(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), **kw)
+    y, p = emul.conv(x, w, b, transposed=tr, threads=256, **kw)
+    d = p.describe()
+    assert "fast_c2r" in d and (tr or "fast_r2c" in d), d
+    assert y.shape == ref.shape and not np.isnan(y).any()
+    assert rel_err(y, ref) < 1e-5
+    y2, p2 = emul.conv(x, w, b, transposed=tr, threads=256, flags=L.FC_FLAG_NO_FAST_R2C | L.FC_FLAG_NO_FAST_C2R, **kw)
+    assert "fast_r2c" not in p2.describe() and "fast_c2r" not in p2.describe()
+    assert rel_err(y2, ref) < 1e-5
+
+
 _COLUMN_SHAPES = [
     # 1-d lines long enough for the four-step split (transform length 16384 .. 65536 = 64 x N2)
     ((1, 2, 9000), (2, 2, 33), {}, False),
