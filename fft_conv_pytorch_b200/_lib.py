@@ -18,6 +18,7 @@ FC_FLAG_NO_FAST_C2R = 8
 FC_FLAG_NO_FUSED_MID = 16
 FC_FLAG_NO_TC = 32
 FC_FLAG_NO_FAST_C2C = 64
+FC_FLAG_NO_SEGMENT = 128
 
 _I3 = ctypes.c_int32 * FC_MAX_ND
 
@@ -51,7 +52,7 @@ class FcPlanInfo(ctypes.Structure):
         ("n_launches", ctypes.c_int32),
         ("n_launches_kspec", ctypes.c_int32),
         ("fused", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("segments", ctypes.c_int32),
         ("bins", ctypes.c_int64),
         ("out_elems", ctypes.c_int64),
         ("xspec_bytes", ctypes.c_int64),

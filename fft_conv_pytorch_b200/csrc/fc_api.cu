@@ -55,15 +55,20 @@ int check_cuda(const char* what) {
 }
 
 const int kMaxSmem = 200 * 1024;
+const char* const kSegMsg =
+    "this plan splits the first axis into overlap-save segments and runs through fc_conv only; create the plan with FC_FLAG_NO_SEGMENT "
+    "for the stage calls";
 int g_num_sms = 148;
 
-// every instantiation of the fused kernel: (N, NB, warps, plain)
+// every instantiation of the fused kernel: (N, CI, NB, warps, plain, CTAs per SM)
 #define FC_FUSED_ALL(X) \
-  X(256, 2, 8, true, 2) X(256, 2, 8, false, 2) X(256, 1, 8, true, 2) X(256, 1, 8, false, 2) \
-  X(512, 2, 8, true, 2) X(512, 2, 8, false, 2) X(512, 1, 8, true, 2) X(512, 1, 8, false, 2) \
-  X(512, 2, 8, true, 3) X(512, 1, 8, true, 3) X(512, 1, 8, true, 4) \
-  X(512, 2, 4, true, 3) X(512, 1, 4, true, 3) X(256, 2, 4, true, 3) \
-  X(1024, 1, 8, true, 2) X(1024, 1, 8, false, 2)
+  X(256, 8, 2, 8, true, 2) X(256, 8, 2, 8, false, 2) X(256, 8, 1, 8, true, 2) X(256, 8, 1, 8, false, 2) \
+  X(512, 8, 2, 8, true, 2) X(512, 8, 2, 8, false, 2) X(512, 8, 1, 8, true, 2) X(512, 8, 1, 8, false, 2) \
+  X(512, 8, 2, 8, true, 3) X(512, 8, 1, 8, true, 3) X(512, 8, 1, 8, true, 4) \
+  X(512, 8, 2, 4, true, 3) X(512, 8, 1, 4, true, 3) X(256, 8, 2, 4, true, 3) \
+  X(1024, 8, 1, 8, true, 2) X(1024, 8, 1, 8, false, 2) \
+  X(256, 16, 2, 8, true, 2) X(256, 16, 2, 8, false, 2) X(256, 16, 1, 8, true, 2) X(256, 16, 1, 8, false, 2) \
+  X(512, 16, 1, 8, true, 2) X(512, 16, 1, 8, false, 2) X(1024, 16, 1, 8, true, 1) X(1024, 16, 1, 8, false, 1)
 
 // Instantiated variants of the transposing kernels K1 / K4: X(M, lines per warp, warps, CTAs per SM).
 #define FC_FAST_ALL(X) \
@@ -78,8 +83,8 @@ int g_num_sms = 148;
 
 void fused_set_attr() {
 #ifndef FC_CPU_EMUL
-#define FC_FUSED_ATTR(NN, NBB, WW, PL, OC) \
-  cudaFuncSetAttribute(fc_fused_axis_kernel<NN, 8, NBB, WW, PL, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+#define FC_FUSED_ATTR(NN, CC, NBB, WW, PL, OC) \
+  cudaFuncSetAttribute(fc_fused_axis_kernel<NN, CC, NBB, WW, PL, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   FC_FUSED_ALL(FC_FUSED_ATTR)
 #undef FC_FUSED_ATTR
 #endif
@@ -441,7 +446,11 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
   a.Og = P.cout / P.groups;
   a.n_in = f.n_in;
   a.n_out = f.n_out;
-  a.nbs = (P.batch + f.nb - 1) / f.nb;
+  a.n_seg = f.n_seg > 1 ? f.n_seg : 1;
+  a.seg_V = f.n_seg > 1 ? f.seg_V : f.N;
+  a.seg_off = f.n_seg > 1 ? f.seg_off : 0;
+  a.n_items = P.batch * a.n_seg;
+  a.nbs = (a.n_items + f.nb - 1) / f.nb;
   a.R = f.R;
   a.n_units = (int64_t)P.groups * f.R * a.nbs;
   a.imap = f.imap;
@@ -459,9 +468,9 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
   if (grid > cap) grid = cap;
   dim3 g((unsigned)grid), b((unsigned)f.warps * 32);
   bool ok = false;
-#define FC_FUSED_CASE(NN, NBB, WW, PL, OC)                                   \
-  if (!ok && f.N == NN && f.nb == NBB && f.warps == WW && (f.plain != 0) == PL && f.occ == OC) { \
-    auto k = fc_fused_axis_kernel<NN, 8, NBB, WW, PL, OC>;                   \
+#define FC_FUSED_CASE(NN, CC, NBB, WW, PL, OC)                                   \
+  if (!ok && f.N == NN && f.ci == CC && f.nb == NBB && f.warps == WW && (f.plain != 0) == PL && f.occ == OC) { \
+    auto k = fc_fused_axis_kernel<NN, CC, NBB, WW, PL, OC>;                   \
     FC_LAUNCH(k, g, b, smem, st, a);                                     \
     ok = true;                                                           \
   }
@@ -614,6 +623,7 @@ int fc_plan_init_const(const fc_plan* plan, void* d_const, void* stream) {
 
 int fc_signal_spectrum(const fc_plan* plan, const void* d_const, const float* d_x, float* d_xspec, void* d_ws, void* stream) {
   if (!plan || !d_const || !d_x || !d_xspec || !d_ws) return set_err(FC_ENULL, "fc_signal_spectrum: NULL argument");
+  if (plan->info.segments > 1) return set_err(FC_EUNSUPPORTED, kSegMsg);
   init_once();
   Bufs b{d_x, d_xspec, (char*)d_ws + plan->off_sA, (char*)d_ws + plan->off_sB, nullptr};
   return run_steps(plan, plan->sig_fwd, b, (const float2*)d_const, nullptr, (cudaStream_t)stream);
@@ -638,6 +648,7 @@ int fc_kernel_spectrum(const fc_plan* plan, const void* d_const, const float* d_
 
 int fc_contract(const fc_plan* plan, const float* d_xspec, const float* d_kspec, float* d_yspec, void* stream) {
   if (!plan || !d_xspec || !d_kspec || !d_yspec) return set_err(FC_ENULL, "fc_contract: NULL argument");
+  if (plan->info.segments > 1) return set_err(FC_EUNSUPPORTED, kSegMsg);
   init_once();
   if (plan->use_tc) return set_err(FC_EUNSUPPORTED, "fc_contract: this plan keeps the kernel spectrum in the tensor-core layout; use fc_conv");
   const fc_contract_desc& c = plan->contract;
@@ -647,6 +658,7 @@ int fc_contract(const fc_plan* plan, const float* d_xspec, const float* d_kspec,
 
 int fc_inverse(const fc_plan* plan, const void* d_const, const float* d_yspec, const float* d_bias, float* d_y, void* d_ws, void* stream) {
   if (!plan || !d_const || !d_yspec || !d_y || !d_ws) return set_err(FC_ENULL, "fc_inverse: NULL argument");
+  if (plan->info.segments > 1) return set_err(FC_EUNSUPPORTED, kSegMsg);
   init_once();
   Bufs b{nullptr, const_cast<float*>(d_yspec), (char*)d_ws + plan->off_sA, (char*)d_ws + plan->off_sB, d_y};
   return run_steps(plan, plan->inv, b, (const float2*)d_const, d_bias, (cudaStream_t)stream);

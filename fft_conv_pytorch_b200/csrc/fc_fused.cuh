@@ -622,6 +622,8 @@ struct fc_fused_args {
   int32_t tw_len;
   int32_t B, Cin, Cout, G, Ig, Og;
   int32_t n_in, n_out, nbs;
+  int32_t n_items;        // B * n_seg: (batch, segment) pairs per (group, bin); NB of them per unit
+  int32_t n_seg, seg_V, seg_off;  // overlap-save segments of the fused axis (fc_fused_desc)
   int32_t prefetch_dist;  // units between a CTA and the one whose operands it pulls into L2 (0 = off)
   int64_t R;
   int64_t n_units;
@@ -629,10 +631,13 @@ struct fc_fused_args {
   fc_omap omap;
 };
 
-// N: transform length of the fused axis. CI: bound on channels per group (in and out). NB: batches per CTA; a warp
-// transforms NL = min(NB, 2) lines (one channel, two batches) at a time. W: compute warps per CTA. PLAIN: the axis has
-// an identity gather map with all N points stored, full channel groups (Ig == Og == CI) and a plain crop on store
-// (compiled without the general map / predication code).
+// N: transform length of the fused axis. CI: bound on channels per group (in and out; 8 or 16). NB: items per CTA, an
+// item being a (batch, overlap-save segment) pair; a warp transforms NL = min(NB, 2) lines (one channel, two items) at a
+// time. W: compute warps per CTA. PLAIN: the axis has an identity gather map with all N points stored, full channel
+// groups (Ig == Og == CI), a plain crop on store and a single segment (compiled without the general map / predication
+// code).
+// Segments (reference-free tiling): item (b, s) loads the dense positions s*V - off + [0, N) of line b through
+// the gather map, and after the inverse transform owns the dense outputs s*V + [0, V), found at local index off + [0, V).
 // Shared memory: NB*CI lines of N float2; each line doubles as its warp's exchange buffer.
 // Measured alternatives that lost at BASELINE c2 (74 us) and were removed: staging the kernel spectrum through a ring
 // of bulk-copy stages (84 us), and 16-warp CTAs with NB = 4 whose batch pairs share kernel-spectrum reads (87 us).
@@ -651,8 +656,16 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
   ofs.init(lane);
   const fc_omap om = a.omap;
   const bool plain_in = PLAIN;   // host guarantees: constant mode, no pad / zero-stuffing / subsampling, N stored points
-  const bool plain_out = PLAIN;  // host guarantees: og == 1, os == 1, ob == 0, Lout <= lim
+  const bool plain_out = PLAIN;  // host guarantees: og == 1, os == 1, ob == 0, Lout <= lim, one segment
   const int out_lim = om.Lout < om.lim ? om.Lout : om.lim;
+  // zero padding without zero-stuffing / subsampling: dense position u holds source u - pad for u in [u_lo, u_hi)
+  const bool simple_in = a.imap.mode == FC_PAD_CONSTANT && a.imap.up == 1 && a.imap.sub == 1;
+  const int u_lo = a.imap.pad > 0 ? a.imap.pad : 0;
+  const int u_hi = a.imap.ext < a.imap.L + a.imap.pad ? a.imap.ext : a.imap.L + a.imap.pad;
+  if (!PLAIN && Ig < CI) {  // channel lines the forward phase never writes are read (times a zero kernel value) by the contraction
+    for (int e = tid; e < NB * CI * N; e += W * 32) xy[e] = make_float2(0.f, 0.f);
+    fc_named_bar_sync(1, W * 32);
+  }
   for (int64_t unit = blockIdx.x; unit < a.n_units; unit += gridDim.x) {
     const int bs = (int)(unit % a.nbs);
     const int64_t gr = unit / a.nbs;
@@ -668,19 +681,30 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
       float2 v[NL][E];
 #pragma unroll
       for (int bl = 0; bl < NL; ++bl) {
-        const int bb = b0 + bg * NL + bl;
-        const bool active = bb < a.B;
-        const float2* src = a.xin + (((int64_t)(active ? bb : b0) * a.Cin + g * Ig + i) * a.R + r) * a.n_in;
+        const int bb = b0 + bg * NL + bl;  // item = (batch bt, segment sg)
+        const bool active = bb < a.n_items;
+        const int it = active ? bb : b0;
+        const int bt = PLAIN ? it : it / a.n_seg, sg = PLAIN ? 0 : it - bt * a.n_seg;
+        const float2* src = a.xin + (((int64_t)bt * a.Cin + g * Ig + i) * a.R + r) * a.n_in;
         if (plain_in) {
 #pragma unroll
           for (int q = 0; q < E; ++q) {
             const int n = lane + 32 * q;
             v[bl][q] = active ? __ldg(src + n) : make_float2(0.f, 0.f);
           }
-        } else {
+        } else if (simple_in) {
+          const int ub = sg * a.seg_V - a.seg_off + lane;
+          src -= a.imap.pad;
 #pragma unroll
           for (int q = 0; q < E; ++q) {
-            const int s = fc_imap_src(a.imap, lane + 32 * q);
+            const int u = ub + 32 * q;
+            v[bl][q] = (active && u >= u_lo && u < u_hi) ? __ldg(src + u) : make_float2(0.f, 0.f);
+          }
+        } else {
+          const int ub = sg * a.seg_V - a.seg_off + lane;
+#pragma unroll
+          for (int q = 0; q < E; ++q) {
+            const int s = fc_imap_src(a.imap, ub + 32 * q);
             v[bl][q] = (active && s >= 0) ? __ldg(src + s) : make_float2(0.f, 0.f);
           }
         }
@@ -700,12 +724,14 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
         const int64_t grn = un / a.nbs;
         const int64_t rn = grn % a.R;
         const int gn = (int)(grn / a.R);
-        const int per_line = (a.n_in * 8 + 127) / 128;  // 128-byte lines per input line
-        for (int idx = tid; idx < NB * Ig * per_line; idx += W * 32) {
-          const int ln = idx / per_line, seg = idx - ln * per_line;
-          const int bl = ln / Ig, i = ln - bl * Ig;
-          if (bsn * NB + bl < a.B)
-            fc_prefetch_l2(a.xin + (((int64_t)(bsn * NB + bl) * a.Cin + gn * Ig + i) * a.R + rn) * a.n_in + seg * 16);
+        if (a.n_seg == 1) {  // (segments of one batch share their input line: nothing to pull ahead)
+          const int per_line = (a.n_in * 8 + 127) / 128;  // 128-byte lines per input line
+          for (int idx = tid; idx < NB * Ig * per_line; idx += W * 32) {
+            const int ln = idx / per_line, seg = idx - ln * per_line;
+            const int bl = ln / Ig, i = ln - bl * Ig;
+            if (bsn * NB + bl < a.B)
+              fc_prefetch_l2(a.xin + (((int64_t)(bsn * NB + bl) * a.Cin + gn * Ig + i) * a.R + rn) * a.n_in + seg * 16);
+          }
         }
         if (bsn == 0) {  // and, once per bin, its slice of the kernel spectrum
           constexpr int kper = N * 8 / 128;
@@ -719,6 +745,7 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
     // ---- phase 2: per-bin contraction over the input channels of the group, in place (X -> Y); a thread takes two
     // adjacent bins (16-byte accesses) of one batch group. The kernel-spectrum loads run in two half-sets, one always
     // in flight.
+    if constexpr (CI <= 8) {
     for (int idx = tid; idx < (N / 2) * NBG; idx += W * 32) {
       const int u = idx & (N / 2 - 1), bg = idx / (N / 2);
       float2* xb = xy + (size_t)(bg * NL * CI) * N + 2 * u;  // line (bl, c) of this batch group at xb + (bl*CI + c)*N
@@ -802,13 +829,90 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
         for (int b = 0; b < NL; ++b) *reinterpret_cast<float4*>(xb + (size_t)(b * CI + o) * N) = acc[b];
       }
     }
+    } else {
+    // 9..16 channels per group: one bin per thread (8-byte accesses) keeps the signal values of both items in registers
+    for (int idx = tid; idx < N * NBG; idx += W * 32) {
+      const int u = idx & (N - 1), bg = idx / N;
+      float2* xb = xy + (size_t)(bg * NL * CI) * N + u;
+      float2 xr[NL][CI];
+#pragma unroll
+      for (int b = 0; b < NL; ++b)
+#pragma unroll
+        for (int i = 0; i < CI; ++i) xr[b][i] = xb[(size_t)(b * CI + i) * N];
+      const char* kp = reinterpret_cast<const char*>(a.kspec + (((int64_t)(g * Og) * Ig) * a.R + r) * N + u);
+      const int64_t ksb = kstride * (int64_t)sizeof(float2);
+      const float2 zero2 = make_float2(0.f, 0.f);
+      float2 ka[H], kb[H];
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const bool on = PLAIN || i < Ig;
+        ka[i] = on ? __ldg(reinterpret_cast<const float2*>(kp)) : zero2;
+        if (on) kp += ksb;
+      }
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const bool on = PLAIN || i + H < Ig;
+        kb[i] = on ? __ldg(reinterpret_cast<const float2*>(kp)) : zero2;
+        if (on) kp += ksb;
+      }
+#pragma unroll 1
+      for (int o = 0; o < Og; ++o) {
+        const bool more = o + 1 < Og;
+        float2 acc[NL];
+#pragma unroll
+        for (int b = 0; b < NL; ++b) acc[b] = zero2;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+#pragma unroll
+          for (int b = 0; b < NL; ++b) {
+            acc[b].x = fmaf(xr[b][i].x, ka[i].x, acc[b].x);
+            acc[b].y = fmaf(xr[b][i].x, ka[i].y, acc[b].y);
+            acc[b].x = fmaf(-xr[b][i].y, ka[i].y, acc[b].x);
+            acc[b].y = fmaf(xr[b][i].y, ka[i].x, acc[b].y);
+          }
+        }
+        if (more) {
+#pragma unroll
+          for (int i = 0; i < H; ++i) {
+            const bool on = PLAIN || i < Ig;
+            if (on) {
+              ka[i] = __ldg(reinterpret_cast<const float2*>(kp));
+              kp += ksb;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+#pragma unroll
+          for (int b = 0; b < NL; ++b) {
+            acc[b].x = fmaf(xr[b][i + H].x, kb[i].x, acc[b].x);
+            acc[b].y = fmaf(xr[b][i + H].x, kb[i].y, acc[b].y);
+            acc[b].x = fmaf(-xr[b][i + H].y, kb[i].y, acc[b].x);
+            acc[b].y = fmaf(xr[b][i + H].y, kb[i].x, acc[b].y);
+          }
+        }
+        if (more) {
+#pragma unroll
+          for (int i = 0; i < H; ++i) {
+            const bool on = PLAIN || i + H < Ig;
+            if (on) {
+              kb[i] = __ldg(reinterpret_cast<const float2*>(kp));
+              kp += ksb;
+            }
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < NL; ++b) xb[(size_t)(b * CI + o) * N] = acc[b];
+      }
+    }
+    }
     fc_named_bar_sync(1, W * 32);
     // ---- phase 3: inverse transform of every (batch, output channel) line, crop / stride on store
     const int n_task3 = Og * NBG;
 #pragma unroll 1
     for (int tk = w; tk < n_task3; tk += W) {  // warp-uniform
       const int bg = tk / Og, o = tk - bg * Og;
-      const int bb0 = b0 + bg * NL;
+      const int bb0 = b0 + bg * NL;  // first item of this task
       float2* line0 = xy + (size_t)(bg * NL * CI + o) * N;
       float2 v[NL][E];
 #pragma unroll
@@ -820,7 +924,7 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
       if (plain_out) {
 #pragma unroll
         for (int bl = 0; bl < NL; ++bl) {
-          if (bb0 + bl >= a.B) continue;
+          if (bb0 + bl >= a.n_items) continue;  // PLAIN: items are batches
           float2* dst = a.yout + (((int64_t)(bb0 + bl) * a.Cout + g * Og + o) * a.R + r) * a.n_out;
 #pragma unroll
           for (int q = 0; q < E; ++q) {
@@ -836,14 +940,23 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
           for (int q = 0; q < E; ++q) line0[bl * LS + lane + 32 * q] = fc_conj(v[bl][q]);
         FC_SYNCWARP();
         for (int bl = 0; bl < NL; ++bl) {
-          if (bb0 + bl >= a.B) continue;
-          float2* dst = a.yout + (((int64_t)(bb0 + bl) * a.Cout + g * Og + o) * a.R + r) * a.n_out;
+          const int it = bb0 + bl;
+          if (it >= a.n_items) continue;
+          const int bt = it / a.n_seg, sg = it - bt * a.n_seg;
+          float2* dst = a.yout + (((int64_t)bt * a.Cout + g * Og + o) * a.R + r) * a.n_out;
+          // this item owns the dense outputs n in [n_lo, n_hi), i.e. the outputs j with n(j) = (j*os + ob) / og in that
+          // range: a contiguous run of j because n(j) is monotone
+          const int n_lo = sg * a.seg_V, n_hi = n_lo + a.seg_V;
+          const int c_lo = n_lo * om.og - om.ob, c_hi = n_hi * om.og - om.ob;
+          int j_lo = c_lo > 0 ? (c_lo + om.os - 1) / om.os : 0;
+          int j_hi = c_hi > 0 ? (c_hi + om.os - 1) / om.os : 0;
+          if (j_hi > om.Lout) j_hi = om.Lout;
+          const float2* ln = line0 + bl * LS + (a.seg_off - n_lo);
 #pragma unroll 8
-          for (int j = lane; j < om.Lout; j += 32) {
+          for (int j = j_lo + lane; j < j_hi; j += 32) {
             const int tt = j * om.os + om.ob;
             const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
-            if (n >= N) continue;
-            dst[j] = (tt == n * om.og && n < om.lim) ? line0[bl * LS + n] : make_float2(0.f, 0.f);
+            dst[j] = (tt == n * om.og && n < om.lim) ? ln[n] : make_float2(0.f, 0.f);
           }
         }
       }

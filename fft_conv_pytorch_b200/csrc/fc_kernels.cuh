@@ -59,7 +59,7 @@ FC_DEV int fc_swz(int i) { return fc_swz2(i); }
 // ------------------------------------------------------------------------------------------------ maps
 // Dense position u -> source index, or -1 for a structural zero. (fc_types.h: fc_imap)
 FC_DEV int fc_imap_src(const fc_imap& m, int u) {
-  if (u >= m.ext) return -1;
+  if (u < 0 || u >= m.ext) return -1;
   int w = u;
   if (m.up > 1) {
     if (u % m.up) return -1;

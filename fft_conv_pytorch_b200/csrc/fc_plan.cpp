@@ -467,6 +467,9 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   pl->threads = P.threads > 0 ? P.threads : env_threads > 0 ? env_threads : 256;
   if (pl->threads % 32 || pl->threads > 1024) return fail(FC_EINVAL, "threads must be a multiple of 32, <= 1024");
   const bool poly = !(P.flags & FC_FLAG_NO_POLYPHASE);
+  const int Ig_ = P.cin / P.groups, Og_ = P.cout / P.groups;
+  // segments need the fused axis kernel (fc_plan_build_program: fuse_mid)
+  const bool seg_ok = !(P.flags & (FC_FLAG_NO_SEGMENT | FC_FLAG_NO_FUSED | FC_FLAG_NO_FUSED_MID)) && Ig_ <= 16 && Og_ <= 16;
 
   int64_t bins = 1, out_vol = 1, in_vol = 1, k_vol = 1;
   double inv_scale = 1.0;
@@ -531,14 +534,46 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     a.imap_ker.up = d2;
     a.imap_ker.sub = 1;
     a.imap_ker.ext = (a.K - 1) * d2 + 1;
-    const int64_t N = next_pow2(std::max<int64_t>(need, 2));
+    int64_t N = next_pow2(std::max<int64_t>(need, 2));
     const bool last = (i == nd - 1);
+    a.N_full = (int)std::min<int64_t>(N, int64_t(1) << 30);
+    a.seg_n = 1;
+    a.seg_V = 0;
+    a.seg_off = 0;
+    if (nd == 2 && i == 0 && seg_ok) {
+      // Overlap-save along y: the fused axis kernel transforms segments of Ns points, of which
+      // V = Ns - (Kd - 1) outputs are alias-free, so the kernel spectrum is Ns instead of N bins long on this axis
+      // (BASELINE c5: 2048 -> 256, 17.2 GB -> 2.1 GB) and a long axis stays inside the fused kernel's line lengths.
+      // Cost model: elements moved through the fused kernel, signal + product lines plus the kernel spectrum.
+      const int64_t Kd2 = (int64_t)(a.K - 1) * d2 + 1;
+      const int64_t n_need = ((int64_t)(a.Lout - 1) * a.omap.os + a.omap.ob) / a.omap.og + 1;  // dense outputs to produce
+      const double io = (double)P.batch * (P.cin + P.cout), kio = (double)P.cout * Ig_;
+      double best = (N >= 256 && N <= 1024) ? (double)N * io + (double)N * kio : 1e300;  // unsegmented and fusable
+      int best_ns = 0;
+      for (int Ns = 256; Ns <= 1024 && Ns < N; Ns *= 2) {
+        const int64_t V = Ns - Kd2 + 1;
+        if (V < Ns / 2) continue;
+        const int64_t ns = (n_need + V - 1) / V;
+        const double c = (double)ns * Ns * io + (double)Ns * kio;
+        if (c < best) {
+          best = c;
+          best_ns = Ns;
+        }
+      }
+      if (best_ns) {
+        a.seg_V = (int)(best_ns - Kd2 + 1);
+        a.seg_n = (int)((n_need + a.seg_V - 1) / a.seg_V);
+        a.seg_off = P.transposed ? (int)(Kd2 - 1) : 0;
+        a.omap.lim = P.transposed ? a.omap.lim : a.seg_n * a.seg_V;
+        N = best_ns;
+      }
+    }
     if (nd > 1 && N > (last ? kMaxRealLine : kMaxComplexLine))
       return fail(FC_EUNSUPPORTED, ax_s + "transform extent " + std::to_string(N) + " exceeds the per-axis limit");
     if (nd == 1 && N > (int64_t)kMaxRealLine * kMaxComplexLine)
       return fail(FC_EUNSUPPORTED, ax_s + "transform extent " + std::to_string(N) + " exceeds the 1-d limit");
     a.N = (int)N;
-    if (!P.transposed) a.omap.lim = a.N;
+    if (!P.transposed && a.seg_n == 1) a.omap.lim = a.N;
     a.Nk = last ? a.N / 2 + 1 : a.N;
     out_vol *= a.Lout;
     in_vol *= a.L;
@@ -633,6 +668,9 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   I.xspec_bytes = (int64_t)P.batch * P.cin * bins * 8;
   I.kspec_bytes = (int64_t)P.cout * Ig * bins * 8;
   I.yspec_bytes = (int64_t)P.batch * P.cout * bins * 8;
+  I.segments = (nd == 2) ? pl->ax[0].seg_n : 1;
+  if (I.segments > 1)  // the fused kernel writes all dense rows of the first axis into the product-spectrum buffer
+    I.yspec_bytes = std::max<int64_t>(I.yspec_bytes, (int64_t)P.batch * P.cout * pl->inv[0].pass.R * pl->inv[0].pass.n_out * 8);
   int64_t sA = 0, sB = 0;
   auto scan = [&](const std::vector<fc_step>& v) {
     for (const fc_step& s : v) {
@@ -680,6 +718,7 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   I.algo_bytes_s3 = I.xspec_bytes + I.kspec_bytes + I.yspec_bytes;
   I.algo_bytes_s4 = I.yspec_bytes + 4 * I.out_elems + 4 * (int64_t)P.cout;
   fc_plan_build_program(pl);
+  if (I.segments > 1 && !I.fused) return fail(FC_EUNSUPPORTED, "internal: segmented plan without the fused axis kernel");
   return FC_OK;
 }
 
@@ -789,8 +828,9 @@ void fc_plan_build_program(fc_plan* pl) {
     const fc_pass& f = pl->sig_fwd[nf - 1].pass;
     const fc_pass& b = pl->inv[0].pass;
     fuse_mid = f.kind == FC_C2C_FWD && b.kind == FC_C2C_INV && !f.in_rfast && !f.out_rfast && !b.in_rfast && !b.out_rfast && f.N == b.N &&
-               (f.N == 256 || f.N == 512 || f.N == 1024) && Ig <= 8 && Og <= 8 && f.R == b.R && f.in_es == 1 && b.out_es == 1;
+               (f.N == 256 || f.N == 512 || f.N == 1024) && Ig <= 16 && Og <= 16 && f.R == b.R && f.in_es == 1 && b.out_es == 1;
   }
+  const fc_axis* seg_ax = (pl->structure == FC_S_2D && pl->ax[0].seg_n > 1) ? &pl->ax[0] : nullptr;
   const bool allow_plane = allow && !(flags & FC_FLAG_NO_FAST_C2C) && !fuse_mid && pl->structure == FC_S_3D && nf == 3 && ni == 3;
   for (int i = 0; i < nf; ++i) {
     if (fuse_mid && i == nf - 1) break;
@@ -844,19 +884,24 @@ void fc_plan_build_program(fc_plan* pl) {
     L.fused.N = fs.pass.N;
     L.fused.n_in = fs.pass.n_in;
     L.fused.n_out = bs.pass.n_out;
-    L.fused.nb = (P.batch >= 2 && fs.pass.N <= 512) ? 2 : 1;
-    L.fused.ci = 8;
+    L.fused.n_seg = seg_ax ? seg_ax->seg_n : 1;
+    L.fused.seg_V = seg_ax ? seg_ax->seg_V : fs.pass.N;
+    L.fused.seg_off = seg_ax ? seg_ax->seg_off : 0;
+    L.fused.ci = (Ig <= 8 && Og <= 8) ? 8 : 16;
+    const int64_t items = (int64_t)P.batch * L.fused.n_seg;  // (batch, segment) pairs per bin
+    L.fused.nb = (items >= 2 && fs.pass.N * L.fused.ci <= 4096) ? 2 : 1;
     L.fused.warps = 8;
-    L.fused.occ = fs.pass.N * L.fused.nb <= 1024 ? 2 : 1;
+    L.fused.occ = fs.pass.N * L.fused.nb * L.fused.ci <= 8192 ? 2 : 1;
     {
       const fc_imap& im = fs.pass.imap;
       const fc_omap& om = bs.pass.omap;
       L.fused.plain = im.mode == FC_PAD_CONSTANT && im.pad == 0 && im.up == 1 && im.sub == 1 && im.L >= fs.pass.N && im.ext >= fs.pass.N &&
-                      om.og == 1 && om.os == 1 && om.ob == 0 && om.Lout <= om.lim && Ig == 8 && Og == 8;
+                      om.og == 1 && om.os == 1 && om.ob == 0 && om.Lout <= om.lim && Ig == L.fused.ci && Og == L.fused.ci && L.fused.n_seg == 1;
     }
     if (const char* tune = std::getenv("FFTCONV_B200_TUNE")) {  // A/B timing knobs: "nb=1,warps=4"
       const char* q;
-      if ((q = std::strstr(tune, "nb="))) L.fused.nb = std::atoi(q + 3) >= 2 && fs.pass.N <= 512 && P.batch >= 2 ? 2 : 1;
+      if (L.fused.ci == 8) {
+      if ((q = std::strstr(tune, "nb="))) L.fused.nb = std::atoi(q + 3) >= 2 && fs.pass.N <= 512 && items >= 2 ? 2 : 1;
       if ((q = std::strstr(tune, "warps="))) L.fused.warps = (std::atoi(q + 6) == 4 && L.fused.plain && fs.pass.N <= 512) ? 4 : 8;
       if (L.fused.warps == 4 && fs.pass.N == 256 && L.fused.nb == 1) L.fused.warps = 8;
       L.fused.occ = fs.pass.N * L.fused.nb <= 1024 ? (L.fused.warps == 4 ? 3 : 2) : 1;
@@ -864,11 +909,12 @@ void fc_plan_build_program(fc_plan* pl) {
         const int o = std::atoi(q + 4);
         if (o == 3 || (o == 4 && L.fused.nb == 1)) L.fused.occ = o;
       }
+      }
     }
     L.fused.R = fs.pass.R;
     L.fused.imap = fs.pass.imap;
     L.fused.omap = bs.pass.omap;
-    L.name = "fused_axis_N" + std::to_string(fs.pass.N);
+    L.name = "fused_axis_N" + std::to_string(fs.pass.N) + (L.fused.n_seg > 1 ? "_seg" + std::to_string(L.fused.n_seg) : "");
     L.bytes = 8 * ((int64_t)P.batch * P.cin * fs.pass.R * fs.pass.n_in + (int64_t)P.cout * Ig * fs.pass.R * fs.pass.N +
                    (int64_t)P.batch * P.cout * bs.pass.R * bs.pass.n_out);
     pl->prog.push_back(L);
@@ -954,7 +1000,9 @@ std::string fc_plan_to_string(const fc_plan* pl) {
     os << "  axis" << i << ": L=" << a.L << " K=" << a.K << " s=" << a.stride << " p=" << a.pad << " d=" << a.dil
        << " op=" << a.opad << " g=" << a.g << " N=" << a.N << " Nk=" << a.Nk << " Lout=" << a.Lout << " imap(ext=" << a.imap_sig.ext
        << ",up=" << a.imap_sig.up << ",sub=" << a.imap_sig.sub << ",pad=" << a.imap_sig.pad << ") omap(os=" << a.omap.os
-       << ",ob=" << a.omap.ob << ",og=" << a.omap.og << ",lim=" << a.omap.lim << ")\n";
+       << ",ob=" << a.omap.ob << ",og=" << a.omap.og << ",lim=" << a.omap.lim << ")";
+    if (a.seg_n > 1) os << " segments(n=" << a.seg_n << ",V=" << a.seg_V << ",off=" << a.seg_off << ",N_full=" << a.N_full << ")";
+    os << "\n";
   }
   auto dump = [&](const char* name, const std::vector<fc_step>& v) {
     for (size_t i = 0; i < v.size(); ++i) {

@@ -37,6 +37,10 @@ struct fc_fused_desc {
   int32_t warps;  // warps per CTA
   int32_t occ;    // CTAs per SM the instantiation is compiled for (register cap)
   int32_t plain;  // identity gather map and plain crop: use the instantiation without the general map code
+  // overlap-save segments of the fused axis (n_seg == 1: none): segment s transforms the dense positions
+  // [s*seg_V - seg_off, s*seg_V - seg_off + N) and owns the dense outputs [s*seg_V, (s+1)*seg_V), which sit at local
+  // index seg_off .. seg_off + seg_V - 1 of its circular result
+  int32_t n_seg, seg_V, seg_off;
   int64_t R;      // lines (bins of the other axes) per (batch, channel)
   fc_imap imap;
   fc_omap omap;
@@ -69,6 +73,11 @@ struct fc_axis {
   int N;        // transform extent
   int Nk;       // stored bins on this axis
   int Lout;     // output extent
+  // overlap-save segmentation (first axis of a 2-d problem only; seg_n == 1: none). N is then the segment transform
+  // length, seg_V = N - (dense kernel extent - 1) the outputs a segment owns, seg_off the local index of the first one
+  // (0 for the correlation of fft_conv, dense kernel extent - 1 for the true convolution of fft_conv_transpose).
+  int seg_n, seg_V, seg_off;
+  int N_full;   // transform extent without segmentation
   fc_imap imap_sig, imap_ker;
   fc_omap omap;
 };

@@ -78,7 +78,8 @@ enum {
   FC_FLAG_NO_FAST_C2R = 8,
   FC_FLAG_NO_FUSED_MID = 16,
   FC_FLAG_NO_TC = 32,       /* keep the contraction on the SIMT kernel even when the tensor-core path qualifies */
-  FC_FLAG_NO_FAST_C2C = 64  /* keep contiguous complex axis passes on the generic block-level kernel */
+  FC_FLAG_NO_FAST_C2C = 64, /* keep contiguous complex axis passes on the generic block-level kernel */
+  FC_FLAG_NO_SEGMENT = 128  /* never split the first axis of a 2-d problem into overlap-save segments */
 };
 
 typedef struct fc_plan fc_plan; /* opaque */
@@ -91,7 +92,9 @@ typedef struct fc_plan_info {
   int32_t n_launches;            /* kernels queued by one fc_conv call */
   int32_t n_launches_kspec;      /* kernels queued by one fc_kernel_spectrum call */
   int32_t fused;                 /* 1 if fc_conv runs the fused axis+contract+axis kernel */
-  int32_t reserved;
+  int32_t segments;              /* overlap-save segments on the first axis of a 2-d problem (1 = unsegmented); fft_size[0]
+                                    is then the segment transform length. Segmented plans run through fc_conv /
+                                    fc_kernel_spectrum only: the stage calls return FC_EUNSUPPORTED */
   int64_t bins;                  /* half-spectrum bins per (batch, channel) */
   int64_t out_elems;             /* B*Cout*prod(out_size) */
   int64_t xspec_bytes;           /* signal spectrum buffer */

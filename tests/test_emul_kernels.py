@@ -312,3 +312,49 @@ def test_wide_channel_contraction_tiling(xs, ws, groups):
     ref = O.fft_conv(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), groups=groups)
     assert not np.isnan(y).any()
     assert rel_err(y, ref) < 1e-5
+
+
+_SEGMENT_SHAPES = [
+    # first axis long enough (and the kernel short enough) that the fused axis kernel runs overlap-save segments
+    ((2, 2, 530, 40), (3, 2, 9, 3), {}, False),
+    ((1, 12, 530, 36), (12, 12, 7, 3), {}, False),  # 9..16 channels per group: the one-bin-per-thread contraction
+    ((1, 32, 300, 36), (32, 16, 5, 3), dict(stride=(2, 2), dilation=(2, 2), groups=2), True),  # BASELINE c5 in small
+    ((2, 3, 700, 40), (3, 3, 5, 3), dict(padding=(2, 1), padding_mode="reflect"), False),  # general gather map
+    ((1, 2, 1200, 36), (2, 1, 4, 3), dict(groups=2, stride=(3, 1), padding=(5, 0)), False),  # strided scatter on store
+    ((1, 2, 330, 40), (2, 2, 3, 3), dict(stride=2, padding=1, output_padding=1), True),  # zero-stuffed signal
+    ((1, 2, 5000, 34), (2, 2, 31, 3), {}, False),  # longer than any single-line transform of this axis
+    ((3, 2, 600, 34), (2, 2, 17, 3), dict(padding=(40, 0)), True),  # crop larger than the segment overlap
+]
+
+
+@pytest.mark.parametrize("xs,ws,kw,tr", _SEGMENT_SHAPES)
+def test_overlap_save_segments_match_unsegmented_and_oracle(xs, ws, kw, tr):
+    from oracle import fftconv_oracle as O
+
+    rng = np.random.RandomState(61)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = rng.standard_normal(ws).astype(np.float32)
+    cout = ws[1] * kw.get("groups", 1) if tr else ws[0]
+    b = rng.standard_normal(cout).astype(np.float32)
+    ofn = O.fft_conv_transpose if tr else O.fft_conv
+    ref = ofn(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), **kw)
+    y, p = emul.conv(x, w, b, transposed=tr, threads=256, **kw)
+    assert p.info.segments > 1 and p.info.fused == 1 and "_seg" in p.describe(), p.describe()
+    assert p.fft_size[0] in (256, 512, 1024)
+    assert y.shape == ref.shape and not np.isnan(y).any()
+    assert rel_err(y, ref) < 1e-5
+    if xs[2] <= 4096:  # the unsegmented layout of the same call (one transform over the whole axis)
+        y2, p2 = emul.conv(x, w, b, transposed=tr, threads=256, flags=L.FC_FLAG_NO_SEGMENT, **kw)
+        assert p2.info.segments == 1 and "_seg" not in p2.describe()
+        assert rel_err(y2, ref) < 1e-5
+        assert rel_err(y, y2) < 5e-6
+
+
+def test_segmented_plans_refuse_the_stage_calls():
+    p = emul.plan_for((1, 2, 530, 40), (2, 2, 9, 3))
+    assert p.info.segments > 1
+    lb = emul.lib()
+    buf = np.zeros(16, np.float32)
+    rc = lb.fc_contract(p.handle, emul._ptr(buf), emul._ptr(buf), emul._ptr(buf), None)
+    assert rc == -2 and b"FC_FLAG_NO_SEGMENT" in lb.fc_last_error()
+    assert emul.plan_for((1, 2, 530, 40), (2, 2, 9, 3), flags=L.FC_FLAG_NO_SEGMENT).info.segments == 1

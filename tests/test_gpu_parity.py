@@ -293,6 +293,48 @@ def test_baseline_c5_shard_spot_checked():
     assert torch.equal(odd, bd.view(1, -1, 1, 1).expand_as(odd))
 
 
+_SEGMENT_CASES = [
+    # 2-d problems whose first axis runs as overlap-save segments inside the fused axis kernel
+    ((2, 8, 600, 300), (8, 8, 9, 7), {}, False),
+    ((2, 12, 530, 200), (12, 12, 7, 3), {}, False),
+    ((1, 32, 300, 260), (32, 16, 5, 3), dict(stride=(2, 2), dilation=(2, 2), groups=2), True),
+    ((2, 3, 700, 140), (3, 3, 5, 3), dict(padding=(2, 1), padding_mode="reflect"), False),
+    ((1, 2, 1200, 136), (2, 1, 4, 3), dict(groups=2, stride=(3, 1), padding=(5, 0)), False),
+    ((1, 2, 330, 140), (2, 2, 3, 3), dict(stride=2, padding=1, output_padding=1), True),
+    ((1, 4, 5000, 134), (4, 4, 31, 3), {}, False),
+    ((3, 2, 600, 134), (2, 2, 17, 3), dict(padding=(40, 0)), True),
+]
+
+
+@pytest.mark.parametrize("xs,ws,kw,tr", _SEGMENT_CASES)
+def test_overlap_save_segments(xs, ws, kw, tr):
+    x, w, b = _seeded(xs, ws, ws[1] * kw.get("groups", 1) if tr else ws[0], seed=3)
+    fn = fcp.fft_conv_transpose if tr else fcp.fft_conv
+    tfn = F.conv_transpose2d if tr else F.conv2d
+    tkw = dict(kw)
+    mode = tkw.pop("padding_mode", None)
+    xd = x.double()
+    if mode:
+        pd = tkw.pop("padding")
+        xd = F.pad(xd, (pd[1], pd[1], pd[0], pd[0]), mode=mode)
+    with torch.no_grad():
+        y = fn(x.cuda(), w.cuda(), b.cuda(), **kw)
+        ref = tfn(xd, w.double(), b.double(), **tkw)
+        y_one = Fn._run(tr, x.cuda(), w.cuda(), b.cuda(), kw.get("stride", 1), kw.get("padding", 0), kw.get("output_padding", 0),
+                        kw.get("dilation", 1), kw.get("groups", 1), kw.get("padding_mode", "constant"), flags=Fn.L.FC_FLAG_NO_SEGMENT) \
+            if xs[2] <= 4096 else None
+    nd = 2
+    tup = lambda v: tuple(v) if hasattr(v, "__iter__") else (v,) * nd
+    cout = ws[1] * kw.get("groups", 1) if tr else ws[0]
+    entry = Fn.get_plan(tr, xs[0], xs[1], cout, kw.get("groups", 1), tuple(xs[2:]), tuple(ws[2:]), tup(kw.get("stride", 1)),
+                        tup(kw.get("padding", 0)), tup(kw.get("dilation", 1)), tup(kw.get("output_padding", 0)), kw.get("padding_mode", "constant"))
+    assert entry.plan.info.segments > 1 and entry.plan.info.fused == 1
+    assert y.shape == ref.shape
+    assert rel_err(y.cpu().numpy(), ref.numpy()) < TOL
+    if y_one is not None:
+        assert rel_err(y.cpu().numpy(), y_one.cpu().numpy()) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------- backward
 @pytest.mark.parametrize("ndim", [1, 2, 3])
 def test_backward_matches_torch_forward_conv(ndim):
