@@ -452,6 +452,7 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
   a.n_items = P.batch * a.n_seg;
   a.nbs = (a.n_items + f.nb - 1) / f.nb;
   a.R = f.R;
+  a.Rk = f.Rk > 0 ? f.Rk : f.R;
   a.n_units = (int64_t)P.groups * f.R * a.nbs;
   a.imap = f.imap;
   a.omap = f.omap;

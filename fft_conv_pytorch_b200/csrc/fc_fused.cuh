@@ -277,25 +277,32 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
   // index math in 32 bits (host guarantees n_tiles < 2^31); this kernel only serves the signal tensor, whose outer
   // items are in_vol apart (o_c2 == o_q == 1)
   const int tpo = (int)p.tiles_per_outer, n_tiles = (int)p.n_tiles, R = (int)p.R;
+  // overlap-save segments (fc_pass::seg_*): the tiles of an outer item run segment-major, tps tiles per segment
+  const int tps = tpo / p.seg_n;
   auto load_rows = [&](int t, float2 (&v)[NL][E]) {
     const int o = t / tpo;
-    const int r0 = (t - o * tpo) * TR;
+    const int rem = t - o * tpo;
+    const int sg = p.seg_n > 1 ? rem / tps : 0;
+    const int r0 = (rem - sg * tps) * TR;
+    const int ub = sg * p.seg_V - p.seg_off;  // first dense position of this segment (even)
     const float* img = a.x + (int64_t)o * p.o_sA;
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       const int r = r0 + lrow + l;
       const bool valid = r < R;
-      const float2* row = reinterpret_cast<const float2*>(img + (int64_t)(valid ? r : 0) * p.in_rs) + gl;
+      const float2* row = reinterpret_cast<const float2*>(img + (int64_t)(valid ? r : 0) * p.in_rs + ub) + gl;
 #pragma unroll
-      for (int q = 0; q < E; ++q)  // L is even (host check), so the pair (2m, 2m + 1) is in or out together
-        v[l][q] = (valid && 2 * (gl + G * q) < L) ? __ldg(row + G * q) : make_float2(0.f, 0.f);
+      for (int q = 0; q < E; ++q)  // L and ub are even (host check), so the pair (2m, 2m + 1) is in or out together
+        v[l][q] = (valid && (unsigned)(ub + 2 * (gl + G * q)) < (unsigned)L) ? __ldg(row + G * q) : make_float2(0.f, 0.f);
     }
   };
   float2 v[NL][E];
   if ((int)blockIdx.x < n_tiles) load_rows(blockIdx.x, v);
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int o = t / tpo;
-    const int r0 = (t - o * tpo) * TR;
+    const int rem = t - o * tpo;
+    const int sg = p.seg_n > 1 ? rem / tps : 0;
+    const int r0 = (rem - sg * tps) * TR;
     const int tn = t + gridDim.x;
     if (a.dbg != 1) {
       if constexpr (G == 32)
@@ -337,7 +344,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
       load_rows(tn, v);  // in flight during the store below
       // and pull the tile after that one into L2: its TR rows are one contiguous run of TR*in_rs floats
       const int t2 = tn + gridDim.x;
-      if (t2 < n_tiles) {
+      if (t2 < n_tiles && p.seg_n == 1) {  // (the segments of a row re-read it from L2 anyway)
         const int on = t2 / tpo;
         const int rn = (t2 - on * tpo) * TR;
         const int rows = (R - rn < TR) ? R - rn : TR;
@@ -349,7 +356,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
     {  // transposed store: thread (l = tid % TR, k = tid / TR + KS j) writes TR consecutive rows of one bin (128 / 256 bytes)
       const int l = tid & (TR - 1);  // tile line l lives at smem + l*LP (see lrow)
       if (r0 + l < R && a.dbg != 2) {
-        float2* dst = a.out + (int64_t)o * p.out_os + r0 + l + (int64_t)(tid / TR) * p.out_es;
+        float2* dst = a.out + (int64_t)o * p.out_os + r0 + l + (int64_t)(tid / TR + sg * (M + 1)) * p.out_es;
         const float2* src = smem + l * LP;
         const int64_t dstep = KS * p.out_es;
         for (int k = tid / TR; k <= M; k += KS, dst += dstep) *dst = src[k < M ? fc_swz2(k) : M];
@@ -384,17 +391,21 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
   float2* line0 = smem + lrow * LP;
   const int tstep = p.tw_len / (2 * M);
   const fc_omap om = p.omap;
-  const bool plain_out = om.os == 1 && om.ob == 0 && om.og == 1 && !(om.Lout & 1) && !(p.out_rs & 1) && !(p.out_os & 1) && p.row_og == 1;
+  const bool plain_out = om.os == 1 && om.ob == 0 && om.og == 1 && !(om.Lout & 1) && !(p.out_rs & 1) && !(p.out_os & 1) && p.row_og == 1 &&
+                         p.seg_n == 1;
   fc_wofs ofs;
   if (G == 32) ofs.init(lane);
   const int tpo = (int)p.tiles_per_outer, n_tiles = (int)p.n_tiles, R = (int)p.R;  // 32-bit index math (host: n_tiles < 2^31)
+  const int tps = tpo / p.seg_n;  // overlap-save segments (fc_pass::seg_*): segment-major tiles, tps per segment
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int o = t / tpo;
-    const int r0 = (t - o * tpo) * TR;
+    const int rem = t - o * tpo;
+    const int sg = p.seg_n > 1 ? rem / tps : 0;
+    const int r0 = (rem - sg * tps) * TR;
     {  // transposed load: thread (l = tid % TR, k = tid / TR + KS j) reads TR consecutive rows of one bin (128 / 256 bytes)
       const int l = tid & (TR - 1);
       const bool ok = r0 + l < R;
-      const float2* src = a.in + (int64_t)o * p.in_os + r0 + (ok ? l : 0) + (int64_t)(tid / TR) * p.in_es;
+      const float2* src = a.in + (int64_t)o * p.in_os + r0 + (ok ? l : 0) + (int64_t)(tid / TR + sg * (M + 1)) * p.in_es;
       float2* dst = smem + l * LP + tid / TR;
       const int64_t sstep = KS * p.in_es;
       // all loads of a thread are issued before the first shared-memory store (NIT requests in flight per thread)
@@ -410,8 +421,10 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
       const int tn = t + gridDim.x;
       if (tn < n_tiles) {
         const int on = tn / tpo;
-        const int rn = (tn - on * tpo) * TR;
-        const float2* nxt = a.in + (int64_t)on * p.in_os + rn;
+        const int remn = tn - on * tpo;
+        const int sn = p.seg_n > 1 ? remn / tps : 0;
+        const int rn = (remn - sn * tps) * TR;
+        const float2* nxt = a.in + (int64_t)on * p.in_os + rn + (int64_t)sn * (M + 1) * p.in_es;
         for (int k = tid; k < (M + 1) * (TR / 16); k += NW * 32)
           fc_prefetch_l2(nxt + (int64_t)(k / (TR / 16)) * p.in_es + 16 * (k % (TR / 16)));
       }
@@ -458,10 +471,17 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
 #pragma unroll
         for (int q = 0; q < E; ++q) line0[l * LP + gl + G * q] = make_float2(v[l][q].x, -v[l][q].y);
       FC_SYNCWARP();
+      // this (row, segment) line owns the dense samples n in [n_lo, n_hi), i.e. the outputs j with
+      // n(j) = (j*os + ob) / og in that range: a contiguous run of j because n(j) is monotone
+      const int n_lo = sg * p.seg_V, n_hi = n_lo + p.seg_V;
+      const int c_lo = n_lo * om.og - om.ob, c_hi = n_hi * om.og - om.ob;
+      const int j_lo = c_lo > 0 ? (c_lo + om.os - 1) / om.os : 0;
+      int j_hi = c_hi > 0 ? (c_hi + om.os - 1) / om.os : 0;
+      if (j_hi > om.Lout) j_hi = om.Lout;
       for (int l = 0; l < NL; ++l) {
         const int64_t r = r0 + lrow + l;
         if (r >= p.R) continue;
-        const float* rl = reinterpret_cast<const float*>(line0 + l * LP);
+        const float* rl = reinterpret_cast<const float*>(line0 + l * LP) + (p.seg_off - n_lo);
         for (int er = 0; er < p.row_og; ++er) {  // output rows owned by this dense line (one unless row lattice)
           const int64_t jr = r * p.row_og + er - p.row_ob;
           if (jr < 0 || jr >= p.row_Lout) continue;
@@ -469,10 +489,9 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
           // output-driven (coalesced stores): output j takes dense sample n = (j*os + ob) / og when the remainder
           // is 0 and n < lim, else it is bias only
 #pragma unroll 8
-          for (int j = gl; j < om.Lout; j += G) {
+          for (int j = j_lo + gl; j < j_hi; j += G) {
             const int tt = j * om.os + om.ob;
             const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
-            if (n >= 2 * M) continue;
             const bool live = er == 0 && tt == n * om.og && n < om.lim;
             yrow[j] = (live ? rl[n] : 0.f) + b;
           }
@@ -626,6 +645,7 @@ struct fc_fused_args {
   int32_t n_seg, seg_V, seg_off;  // overlap-save segments of the fused axis (fc_fused_desc)
   int32_t prefetch_dist;  // units between a CTA and the one whose operands it pulls into L2 (0 = off)
   int64_t R;
+  int64_t Rk;  // kernel-spectrum lines per channel pair (line r uses kernel line r % Rk)
   int64_t n_units;
   fc_imap imap;
   fc_omap omap;
@@ -651,7 +671,7 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
   FC_DYN_SMEM(xy);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int Ig = a.Ig, Og = a.Og;
-  const int64_t kstride = a.R * N;  // kernel-spectrum stride between input channels
+  const int64_t kstride = a.Rk * N;  // kernel-spectrum stride between input channels
   fc_wofs ofs;
   ofs.init(lane);
   const fc_omap om = a.omap;
@@ -669,8 +689,19 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
   for (int64_t unit = blockIdx.x; unit < a.n_units; unit += gridDim.x) {
     const int bs = (int)(unit % a.nbs);
     const int64_t gr = unit / a.nbs;
-    const int64_t r = gr % a.R;
-    const int g = (int)(gr / a.R);
+    // lines of the other axis: when that axis is segmented (Rk < R) the segments sharing kernel line rk run back to
+    // back, so the kernel-spectrum slice of (g, rk) is read from HBM once and from L2 afterwards
+    int64_t r, rk;
+    int g;
+    if (a.Rk == a.R) {
+      r = rk = gr % a.R;
+      g = (int)(gr / a.R);
+    } else {
+      const int64_t nsx = a.R / a.Rk, t = gr / nsx;
+      rk = t % a.Rk;
+      g = (int)(t / a.Rk);
+      r = (gr - t * nsx) * a.Rk + rk;
+    }
     const int b0 = bs * NB;
     // ---- phase 1: forward transform of every (batch, input channel) line of this bin
     const int n_task1 = Ig * NBG;
@@ -722,8 +753,16 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
       if (un < a.n_units) {
         const int bsn = (int)(un % a.nbs);
         const int64_t grn = un / a.nbs;
-        const int64_t rn = grn % a.R;
-        const int gn = (int)(grn / a.R);
+        int64_t rn;
+        int gn;
+        if (a.Rk == a.R) {
+          rn = grn % a.R;
+          gn = (int)(grn / a.R);
+        } else {
+          const int64_t nsx = a.R / a.Rk, t = grn / nsx;
+          gn = (int)(t / a.Rk);
+          rn = (grn - t * nsx) * a.Rk + t % a.Rk;
+        }
         if (a.n_seg == 1) {  // (segments of one batch share their input line: nothing to pull ahead)
           const int per_line = (a.n_in * 8 + 127) / 128;  // 128-byte lines per input line
           for (int idx = tid; idx < NB * Ig * per_line; idx += W * 32) {
@@ -737,7 +776,7 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
           constexpr int kper = N * 8 / 128;
           for (int idx = tid; idx < Og * Ig * kper; idx += W * 32) {
             const int ln = idx / kper, seg = idx - ln * kper;
-            fc_prefetch_l2(a.kspec + ((int64_t)(gn * Og * Ig + ln) * a.R + rn) * N + seg * 16);
+            fc_prefetch_l2(a.kspec + ((int64_t)(gn * Og * Ig + ln) * a.Rk + rn % a.Rk) * N + seg * 16);
           }
         }
       }
@@ -755,7 +794,7 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
 #pragma unroll
         for (int i = 0; i < CI; ++i) xr[b][i] = *reinterpret_cast<const float4*>(xb + (size_t)(b * CI + i) * N);
       // one running pointer over the (o, i) lines of this bin: consecutive lines are kstride apart
-      const char* kp = reinterpret_cast<const char*>(a.kspec + (((int64_t)(g * Og) * Ig) * a.R + r) * N + 2 * u);
+      const char* kp = reinterpret_cast<const char*>(a.kspec + (((int64_t)(g * Og) * Ig) * a.Rk + rk) * N + 2 * u);
       const int64_t ksb = kstride * (int64_t)sizeof(float2);
       const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
       float4 ka[H], kb[H];
@@ -839,7 +878,7 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
       for (int b = 0; b < NL; ++b)
 #pragma unroll
         for (int i = 0; i < CI; ++i) xr[b][i] = xb[(size_t)(b * CI + i) * N];
-      const char* kp = reinterpret_cast<const char*>(a.kspec + (((int64_t)(g * Og) * Ig) * a.R + r) * N + u);
+      const char* kp = reinterpret_cast<const char*>(a.kspec + (((int64_t)(g * Og) * Ig) * a.Rk + rk) * N + u);
       const int64_t ksb = kstride * (int64_t)sizeof(float2);
       const float2 zero2 = make_float2(0.f, 0.f);
       float2 ka[H], kb[H];

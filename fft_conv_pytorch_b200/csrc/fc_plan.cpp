@@ -103,6 +103,8 @@ fc_pass blank_pass(int kind, int N, int tw_len) {
   p.o_q = 1;
   p.twN = 1;
   p.row_og = 1;
+  p.seg_n = 1;
+  p.seg_V = N;
   p.imap = identity_imap(N);
   p.omap = identity_omap(N);
   return p;
@@ -116,6 +118,7 @@ struct SrcDesc {
   int L[FC_MAX_ND];
   bool conj;
   float scale;
+  bool segmented_x;  // the signal of a plan with overlap-save segments on the last axis (the kernel has one segment)
 };
 
 void build_forward(const fc_plan& pl, const SrcDesc& s, std::vector<fc_step>& out) {
@@ -188,6 +191,7 @@ void build_forward(const fc_plan& pl, const SrcDesc& s, std::vector<fc_step>& ou
   } else if (pl.structure == FC_S_2D) {
     const fc_axis &ay = pl.ax[0], &ax = pl.ax[1];
     const int Ly = s.L[0], Lx = s.L[1];
+    const int64_t nkx = (int64_t)ax.Nk * (s.segmented_x ? ax.seg_n : 1);  // bins of all segments of a row
     fc_pass p = blank_pass(FC_R2C, ax.N, tw);
     p.n_outer = s.n_outer;
     p.R = Ly;
@@ -197,23 +201,28 @@ void build_forward(const fc_plan& pl, const SrcDesc& s, std::vector<fc_step>& ou
     p.imap = s.imap[1];
     p.n_in = Lx;
     p.n_out = ax.Nk;
-    p.out_os = (int64_t)ax.Nk * Ly;  // [o][kx][y]
+    p.out_os = nkx * Ly;  // [o][kx][y]
     p.out_es = Ly;
     p.out_rs = 1;
     p.out_rfast = 1;
+    if (s.segmented_x) {
+      p.seg_n = ax.seg_n;
+      p.seg_V = ax.seg_V;
+      p.seg_off = ax.seg_off;
+    }
     finish_pass(p);
     out.push_back({p, FC_BUF_USER_IN, FC_BUF_SA});
     fc_pass q = blank_pass(FC_C2C_FWD, ay.N, tw);
     q.n_outer = s.n_outer;
-    q.R = ax.Nk;
+    q.R = nkx;
     q.flat = 1;
-    q.in_os = (int64_t)ax.Nk * Ly;
+    q.in_os = nkx * Ly;
     q.in_rs = Ly;
     q.in_es = 1;
     q.imap = s.imap[0];
     q.n_in = Ly;
     q.n_out = ay.N;
-    q.out_os = (int64_t)ax.Nk * ay.N;  // [o][kx][ky]
+    q.out_os = nkx * ay.N;  // [o][kx][ky]
     q.out_rs = ay.N;
     q.out_es = 1;
     q.conj_out = s.conj;
@@ -345,16 +354,17 @@ void build_inverse(const fc_plan& pl, std::vector<fc_step>& out) {
     // fills the og-1 bias-only rows it owns.
     const bool row_lattice = ay.omap.og > 1;
     const int D0 = row_lattice ? (ay.Lout - 1 + ay.omap.ob) / ay.omap.og + 1 : ay.Lout;
+    const int64_t nkx = (int64_t)ax.Nk * ax.seg_n;  // bins of all segments of a row
     fc_pass q = blank_pass(FC_C2C_INV, ay.N, tw);
     q.n_outer = n_outer;
-    q.R = ax.Nk;
+    q.R = nkx;
     q.flat = 1;
-    q.in_os = (int64_t)ax.Nk * ay.N;
+    q.in_os = nkx * ay.N;
     q.in_rs = ay.N;
     q.in_es = 1;
     q.n_in = ay.N;
     q.n_out = D0;
-    q.out_os = (int64_t)ax.Nk * D0;  // [o][kx][jy]
+    q.out_os = nkx * D0;  // [o][kx][jy]
     q.out_rs = D0;
     q.out_es = 1;
     q.omap = ay.omap;
@@ -369,7 +379,10 @@ void build_inverse(const fc_plan& pl, std::vector<fc_step>& out) {
     fc_pass p = blank_pass(FC_C2R, ax.N, tw);
     p.n_outer = n_outer;
     p.R = D0;
-    p.in_os = (int64_t)ax.Nk * D0;
+    p.seg_n = ax.seg_n;
+    p.seg_V = ax.seg_n > 1 ? ax.seg_V : ax.N;
+    p.seg_off = ax.seg_off;
+    p.in_os = nkx * D0;
     p.in_es = D0;
     p.in_rs = 1;
     p.in_rfast = 1;
@@ -468,6 +481,9 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   if (pl->threads % 32 || pl->threads > 1024) return fail(FC_EINVAL, "threads must be a multiple of 32, <= 1024");
   const bool poly = !(P.flags & FC_FLAG_NO_POLYPHASE);
   const int Ig_ = P.cin / P.groups, Og_ = P.cout / P.groups;
+  static const char* env_seg = std::getenv("FFTCONV_B200_SEG");  // experiments: "Ny,Nx" forces the segment lengths (0 = automatic)
+  int force_seg[2] = {0, 0};
+  if (env_seg) std::sscanf(env_seg, "%d,%d", &force_seg[0], &force_seg[1]);
   // segments need the fused axis kernel (fc_plan_build_program: fuse_mid)
   const bool seg_ok = !(P.flags & (FC_FLAG_NO_SEGMENT | FC_FLAG_NO_FUSED | FC_FLAG_NO_FUSED_MID)) && Ig_ <= 16 && Og_ <= 16;
 
@@ -540,6 +556,36 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     a.seg_n = 1;
     a.seg_V = 0;
     a.seg_off = 0;
+    if (nd == 2 && i == 1 && seg_ok && (pl->ax[0].N == 256 || pl->ax[0].N == 512 || pl->ax[0].N == 1024) &&
+        !(P.flags & (FC_FLAG_NO_FAST_R2C | FC_FLAG_NO_FAST_C2R)) && !(a.L & 1) &&
+        (P.transposed ? s2 == 1 : (a.pad == 0 && a.g == 1 && P.padding_mode == FC_PAD_CONSTANT))) {
+      // Overlap-save along x as well: the transposing row kernels K1 / K4 (which must both apply, see
+      // fc_plan_build_program) treat a (row, segment) pair as a line. Segment extents are kept even so that the packed
+      // real transforms load and store aligned pairs.
+      const int64_t Kd2 = (int64_t)(a.K - 1) * d2 + 1;
+      const int64_t n_need = ((int64_t)(a.Lout - 1) * a.omap.os + a.omap.ob) / a.omap.og + 1;
+      const int64_t off = P.transposed ? ((Kd2 - 1 + 1) & ~int64_t(1)) : 0;
+      const double io = (double)P.batch * (P.cin + P.cout), kio = (double)P.cout * Ig_;
+      double best = N <= kMaxRealLine ? (double)(N / 2 + 1) * (io + kio) : 1e300;
+      int best_ns = 0;
+      for (int Ns = 256; Ns <= 2048 && Ns < N; Ns *= 2) {  // (128-point segments measured slower: the short-row kernels lose more than the bins save)
+        const int64_t V = P.transposed ? Ns - off : ((Ns - Kd2 + 1) & ~int64_t(1));
+        if (V < Ns / 2) continue;
+        const int64_t ns = (n_need + V - 1) / V;
+        const double c = (double)ns * (Ns / 2 + 1) * io + (double)(Ns / 2 + 1) * kio;
+        if (force_seg[1] ? Ns == force_seg[1] : c < best) {
+          best = c;
+          best_ns = Ns;
+        }
+      }
+      if (best_ns) {
+        a.seg_V = (int)(P.transposed ? best_ns - off : ((best_ns - Kd2 + 1) & ~int64_t(1)));
+        a.seg_n = (int)((n_need + a.seg_V - 1) / a.seg_V);
+        a.seg_off = (int)off;
+        a.omap.lim = P.transposed ? a.omap.lim : a.seg_n * a.seg_V;
+        N = best_ns;
+      }
+    }
     if (nd == 2 && i == 0 && seg_ok) {
       // Overlap-save along y: the fused axis kernel transforms segments of Ns points, of which
       // V = Ns - (Kd - 1) outputs are alias-free, so the kernel spectrum is Ns instead of N bins long on this axis
@@ -555,7 +601,7 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
         if (V < Ns / 2) continue;
         const int64_t ns = (n_need + V - 1) / V;
         const double c = (double)ns * Ns * io + (double)Ns * kio;
-        if (c < best) {
+        if (force_seg[0] ? Ns == force_seg[0] : c < best) {
           best = c;
           best_ns = Ns;
         }
@@ -621,6 +667,7 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   sig.o_sC = 0;
   sig.conj = false;
   sig.scale = 1.f;
+  sig.segmented_x = nd == 2 && pl->ax[1].seg_n > 1;
   SrcDesc ker;
   ker.n_outer = (int64_t)P.cout * Ig;
   ker.o_c2 = Ig;
@@ -635,6 +682,7 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     ker.o_sB = k_vol;
     ker.o_sC = (int64_t)Og * k_vol;
   }
+  ker.segmented_x = false;
   ker.conj = !P.transposed;
   ker.scale = (float)(1.0 / inv_scale);
   for (int i = 0; i < nd; ++i) {
@@ -668,7 +716,7 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   I.xspec_bytes = (int64_t)P.batch * P.cin * bins * 8;
   I.kspec_bytes = (int64_t)P.cout * Ig * bins * 8;
   I.yspec_bytes = (int64_t)P.batch * P.cout * bins * 8;
-  I.segments = (nd == 2) ? pl->ax[0].seg_n : 1;
+  I.segments = (nd == 2) ? pl->ax[0].seg_n * pl->ax[1].seg_n : 1;
   if (I.segments > 1)  // the fused kernel writes all dense rows of the first axis into the product-spectrum buffer
     I.yspec_bytes = std::max<int64_t>(I.yspec_bytes, (int64_t)P.batch * P.cout * pl->inv[0].pass.R * pl->inv[0].pass.n_out * 8);
   int64_t sA = 0, sB = 0;
@@ -719,6 +767,8 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   I.algo_bytes_s4 = I.yspec_bytes + 4 * I.out_elems + 4 * (int64_t)P.cout;
   fc_plan_build_program(pl);
   if (I.segments > 1 && !I.fused) return fail(FC_EUNSUPPORTED, "internal: segmented plan without the fused axis kernel");
+  if (nd == 2 && pl->ax[1].seg_n > 1 && (pl->prog.front().type != FC_L_FAST_R2C || pl->prog.back().type != FC_L_FAST_C2R))
+    return fail(FC_EUNSUPPORTED, "internal: segmented rows without the transposing row kernels");
   return FC_OK;
 }
 
@@ -808,7 +858,7 @@ void retile16(fc_pass& p) {
   p.T = T;
   p.log2T = ilog2(T);
   p.flat = 0;
-  p.tiles_per_outer = (p.R + T - 1) / T;
+  p.tiles_per_outer = (p.R + T - 1) / T * p.seg_n;  // tiles of one outer item: segment-major, then rows
   p.n_tiles = p.tiles_per_outer * p.n_outer;
 }
 
@@ -912,10 +962,11 @@ void fc_plan_build_program(fc_plan* pl) {
       }
     }
     L.fused.R = fs.pass.R;
+    L.fused.Rk = pl->structure == FC_S_2D ? pl->ax[1].Nk : fs.pass.R;
     L.fused.imap = fs.pass.imap;
     L.fused.omap = bs.pass.omap;
     L.name = "fused_axis_N" + std::to_string(fs.pass.N) + (L.fused.n_seg > 1 ? "_seg" + std::to_string(L.fused.n_seg) : "");
-    L.bytes = 8 * ((int64_t)P.batch * P.cin * fs.pass.R * fs.pass.n_in + (int64_t)P.cout * Ig * fs.pass.R * fs.pass.N +
+    L.bytes = 8 * ((int64_t)P.batch * P.cin * fs.pass.R * fs.pass.n_in + (int64_t)P.cout * Ig * L.fused.Rk * fs.pass.N +
                    (int64_t)P.batch * P.cout * bs.pass.R * bs.pass.n_out);
     pl->prog.push_back(L);
   } else if (pl->use_tc) {

@@ -42,6 +42,8 @@ struct fc_fused_desc {
   // index seg_off .. seg_off + seg_V - 1 of its circular result
   int32_t n_seg, seg_V, seg_off;
   int64_t R;      // lines (bins of the other axes) per (batch, channel)
+  int64_t Rk;     // ... per kernel-spectrum channel pair: line r multiplies kernel line r % Rk (Rk < R when the other
+                  // axis is segmented: all its segments share one kernel spectrum)
   fc_imap imap;
   fc_omap omap;
 };

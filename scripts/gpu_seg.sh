@@ -1,4 +1,4 @@
 # overlap-save segments: GPU parity + per-config timing
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q --timeout=600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-FFTCONV_SKIP_REF=1 timeout 900 python scripts/time_configs.py c2 c5_shard img256 c1 > gpurun_out/time_configs.log 2>&1
+FFTCONV_SKIP_REF=1 timeout 900 python scripts/time_configs.py > gpurun_out/time_configs.log 2>&1

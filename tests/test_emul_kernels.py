@@ -89,7 +89,10 @@ def test_plan_shapes_follow_reference_formulas():
     assert p.info.bins == 512 * 257
     p = emul.plan_for((4, 64, 1024, 1024), (64, 16, 31, 31), transposed=True, stride=2, dilation=2, groups=4)
     assert p.out_size == (2107, 2107)
-    assert p.fft_size == (2048, 2048)  # polyphase: dense 1024 (*) 31 -> 1054 per axis
+    # polyphase: dense 1024 (*) 31 -> 1054 per axis, run as 5 x 5 overlap-save segments of 256 (f3)
+    assert p.fft_size == (256, 256) and p.info.segments == 25
+    p = emul.plan_for((4, 64, 1024, 1024), (64, 16, 31, 31), transposed=True, stride=2, dilation=2, groups=4, flags=L.FC_FLAG_NO_SEGMENT)
+    assert p.fft_size == (2048, 2048) and p.info.segments == 1
     p = emul.plan_for((16, 256, 65536), (256, 256, 4097))
     assert p.out_size == (61440,) and p.fft_size == (65536,)
     p = emul.plan_for((1, 8, 32768), (8, 8, 1025))
@@ -324,6 +327,14 @@ _SEGMENT_SHAPES = [
     ((1, 2, 330, 40), (2, 2, 3, 3), dict(stride=2, padding=1, output_padding=1), True),  # zero-stuffed signal
     ((1, 2, 5000, 34), (2, 2, 31, 3), {}, False),  # longer than any single-line transform of this axis
     ((3, 2, 600, 34), (2, 2, 17, 3), dict(padding=(40, 0)), True),  # crop larger than the segment overlap
+    # ... and segments on the last axis as well: the row kernels K1 / K4 treat a (row, segment) pair as a line
+    ((2, 2, 300, 600), (3, 2, 9, 5), {}, False),
+    ((1, 32, 140, 600), (32, 16, 5, 7), dict(stride=(2, 2), dilation=(2, 2), groups=2), True),  # BASELINE c5 in small
+    ((1, 2, 130, 700), (2, 2, 3, 4), {}, False),  # even kernel extent: segment stride rounded down to even
+    ((1, 2, 270, 640), (2, 1, 4, 6), dict(groups=2, stride=(1, 3)), False),  # strided scatter across segments
+    ((1, 2, 280, 660), (2, 2, 3, 4), dict(padding=(1, 3), dilation=(1, 2), output_padding=(0, 1)), True),
+    ((1, 2, 260, 2500), (2, 2, 3, 33), {}, False),
+    ((1, 3, 200, 1100), (3, 3, 3, 10), dict(padding=(0, 20)), True),  # crop across a segment boundary
 ]
 
 
@@ -339,13 +350,15 @@ def test_overlap_save_segments_match_unsegmented_and_oracle(xs, ws, kw, tr):
     ofn = O.fft_conv_transpose if tr else O.fft_conv
     ref = ofn(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), **kw)
     y, p = emul.conv(x, w, b, transposed=tr, threads=256, **kw)
-    assert p.info.segments > 1 and p.info.fused == 1 and "_seg" in p.describe(), p.describe()
+    assert p.info.segments > 1 and p.info.fused == 1 and "segments(n=" in p.describe(), p.describe()
     assert p.fft_size[0] in (256, 512, 1024)
+    if xs[3] >= 600:
+        assert "axis1" in [ln.split(":")[0].strip() for ln in p.describe().splitlines() if "segments(n=" in ln]
     assert y.shape == ref.shape and not np.isnan(y).any()
     assert rel_err(y, ref) < 1e-5
-    if xs[2] <= 4096:  # the unsegmented layout of the same call (one transform over the whole axis)
+    if xs[2] <= 4096 and xs[3] <= 4096:  # the unsegmented layout of the same call (one transform over the whole axis)
         y2, p2 = emul.conv(x, w, b, transposed=tr, threads=256, flags=L.FC_FLAG_NO_SEGMENT, **kw)
-        assert p2.info.segments == 1 and "_seg" not in p2.describe()
+        assert p2.info.segments == 1 and "segments(n=" not in p2.describe()
         assert rel_err(y2, ref) < 1e-5
         assert rel_err(y, y2) < 5e-6
 

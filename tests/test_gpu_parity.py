@@ -303,6 +303,15 @@ _SEGMENT_CASES = [
     ((1, 2, 330, 140), (2, 2, 3, 3), dict(stride=2, padding=1, output_padding=1), True),
     ((1, 4, 5000, 134), (4, 4, 31, 3), {}, False),
     ((3, 2, 600, 134), (2, 2, 17, 3), dict(padding=(40, 0)), True),
+    # segments on both axes (row kernels with (row, segment) lines)
+    ((2, 8, 300, 600), (8, 8, 9, 5), {}, False),
+    ((1, 32, 300, 600), (32, 16, 5, 7), dict(stride=(2, 2), dilation=(2, 2), groups=2), True),
+    ((1, 2, 130, 700), (2, 2, 3, 4), {}, False),
+    ((1, 2, 270, 640), (2, 1, 4, 6), dict(groups=2, stride=(1, 3)), False),
+    ((1, 2, 280, 660), (2, 2, 3, 4), dict(padding=(1, 3), dilation=(1, 2), output_padding=(0, 1)), True),
+    ((2, 2, 260, 2500), (2, 2, 3, 33), {}, False),
+    ((1, 3, 200, 1100), (3, 3, 3, 10), dict(padding=(0, 20)), True),
+    ((2, 16, 1100, 1300), (16, 16, 15, 15), {}, False),
 ]
 
 
@@ -322,7 +331,7 @@ def test_overlap_save_segments(xs, ws, kw, tr):
         ref = tfn(xd, w.double(), b.double(), **tkw)
         y_one = Fn._run(tr, x.cuda(), w.cuda(), b.cuda(), kw.get("stride", 1), kw.get("padding", 0), kw.get("output_padding", 0),
                         kw.get("dilation", 1), kw.get("groups", 1), kw.get("padding_mode", "constant"), flags=Fn.L.FC_FLAG_NO_SEGMENT) \
-            if xs[2] <= 4096 else None
+            if xs[2] <= 4096 and xs[3] <= 4096 else None
     nd = 2
     tup = lambda v: tuple(v) if hasattr(v, "__iter__") else (v,) * nd
     cout = ws[1] * kw.get("groups", 1) if tr else ws[0]
