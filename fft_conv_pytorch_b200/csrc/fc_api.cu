@@ -650,6 +650,10 @@ int fc_kernel_spectrum(const fc_plan* plan, const void* d_const, const float* d_
 int fc_contract(const fc_plan* plan, const float* d_xspec, const float* d_kspec, float* d_yspec, void* stream) {
   if (!plan || !d_xspec || !d_kspec || !d_yspec) return set_err(FC_ENULL, "fc_contract: NULL argument");
   if (plan->info.segments > 1) return set_err(FC_EUNSUPPORTED, kSegMsg);
+  if (plan->info.fused)
+    return set_err(FC_EUNSUPPORTED,
+                   "fc_contract: this plan keeps the kernel spectrum in the bin-major layout of the fused axis kernel; create the plan with "
+                   "FC_FLAG_NO_FUSED_MID for the stage calls, or use fc_conv");
   init_once();
   if (plan->use_tc) return set_err(FC_EUNSUPPORTED, "fc_contract: this plan keeps the kernel spectrum in the tensor-core layout; use fc_conv");
   const fc_contract_desc& c = plan->contract;

@@ -651,6 +651,117 @@ struct fc_fused_args {
   fc_omap omap;
 };
 
+// Complex multiply-accumulate of one (float2) or two adjacent (float4) bins: acc += x * k.
+FC_DEV void fc_cmac(float2& acc, const float2& x, const float2& k) {
+  acc.x = fmaf(x.x, k.x, acc.x);
+  acc.y = fmaf(x.x, k.y, acc.y);
+  acc.x = fmaf(-x.y, k.y, acc.x);
+  acc.y = fmaf(x.y, k.x, acc.y);
+}
+FC_DEV void fc_cmac(float4& acc, const float4& x, const float4& k) {
+  acc.x = fmaf(x.x, k.x, acc.x);
+  acc.y = fmaf(x.x, k.y, acc.y);
+  acc.z = fmaf(x.z, k.z, acc.z);
+  acc.w = fmaf(x.z, k.w, acc.w);
+  acc.x = fmaf(-x.y, k.y, acc.x);
+  acc.y = fmaf(x.y, k.x, acc.y);
+  acc.z = fmaf(-x.w, k.w, acc.z);
+  acc.w = fmaf(x.w, k.z, acc.w);
+}
+FC_DEV void fc_vzero(float2& v) { v = make_float2(0.f, 0.f); }
+FC_DEV void fc_vzero(float4& v) { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+template <int CI>
+struct fc_cvec {
+  typedef float4 type;  // up to 8 channels per group: two adjacent bins per thread (16-byte accesses)
+};
+template <>
+struct fc_cvec<16> {
+  typedef float2 type;  // 9..16 channels: one bin per thread keeps the signal values of both items in registers
+};
+
+// Phase 2 of the fused axis kernel: per-bin contraction over the input channels of the group, in place (X -> Y) in
+// the CTA's lines (complex_matmul, reference functional.py:11-16). FULL: every group has CI input channels (no
+// per-load predicate, no zero-filled kernel values).
+// The kernel spectrum is stored bin-major for this kernel: the Og*Ig lines (o, i) of (group g, line rk) are adjacent,
+// N elements apart, so every load of a thread is its base pointer plus a compile-time offset. With full groups
+// (Ig == Og == CI) the loop over the output channels is unrolled completely: there are then no loop-carried register
+// buffers for ptxas to stage and copy (a rolled, double-buffered loop spent 20 % of this phase's issue slots on MOVs
+// and as many on 64-bit address arithmetic).
+template <int N, int CI, int NL, int NBG, int W, bool FULL>
+FC_DEV void fc_fused_contract(float2* xy, const fc_fused_args& a, int g, int rk, int tid) {
+  typedef typename fc_cvec<CI>::type V;
+  constexpr int BP = (int)(sizeof(V) / sizeof(float2));  // bins per thread
+  constexpr int LV = N / BP;                              // line pitch in V units
+  constexpr int H = CI / 2;
+  const int Ig = a.Ig, Og = a.Og;
+  for (int idx = tid; idx < LV * NBG; idx += W * 32) {
+    const int u = idx & (LV - 1), bg = idx / LV;
+    float2* xb = xy + (size_t)(bg * NL * CI) * N + BP * u;  // line (bl, c) of this item group at xb + (bl*CI + c)*N
+    V xr[NL][CI];
+#pragma unroll
+    for (int b = 0; b < NL; ++b)
+#pragma unroll
+      for (int i = 0; i < CI; ++i) xr[b][i] = *reinterpret_cast<const V*>(xb + (size_t)(b * CI + i) * N);
+    const V* kp = reinterpret_cast<const V*>(a.kspec + ((int64_t)g * a.Rk + rk) * ((int64_t)Og * Ig * N)) + u;
+    if (FULL && Og == CI) {
+#pragma unroll
+      for (int o = 0; o < CI; ++o) {
+        V acc[NL];
+#pragma unroll
+        for (int b = 0; b < NL; ++b) fc_vzero(acc[b]);
+#pragma unroll
+        for (int i = 0; i < CI; ++i) {
+          const V k = __ldg(kp + (o * CI + i) * LV);
+#pragma unroll
+          for (int b = 0; b < NL; ++b) fc_cmac(acc[b], xr[b][i], k);
+        }
+#pragma unroll
+        for (int b = 0; b < NL; ++b) *reinterpret_cast<V*>(xb + (size_t)(b * CI + o) * N) = acc[b];
+      }
+    } else {
+      // ragged groups: rolled loop, the kernel-spectrum loads run in two half-sets, one always in flight
+      const int ostep = Ig * LV;
+      V ka[H], kb[H];
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        if (FULL || i < Ig) ka[i] = __ldg(kp + i * LV); else fc_vzero(ka[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        if (FULL || i + H < Ig) kb[i] = __ldg(kp + (i + H) * LV); else fc_vzero(kb[i]);
+      }
+#pragma unroll 1
+      for (int o = 0; o < Og; ++o) {
+        const bool more = o + 1 < Og;
+        kp += ostep;
+        V acc[NL];
+#pragma unroll
+        for (int b = 0; b < NL; ++b) fc_vzero(acc[b]);
+#pragma unroll
+        for (int i = 0; i < H; ++i)
+#pragma unroll
+          for (int b = 0; b < NL; ++b) fc_cmac(acc[b], xr[b][i], ka[i]);
+        if (more) {
+#pragma unroll
+          for (int i = 0; i < H; ++i)
+            if (FULL || i < Ig) ka[i] = __ldg(kp + i * LV);
+        }
+#pragma unroll
+        for (int i = 0; i < H; ++i)
+#pragma unroll
+          for (int b = 0; b < NL; ++b) fc_cmac(acc[b], xr[b][i + H], kb[i]);
+        if (more) {
+#pragma unroll
+          for (int i = 0; i < H; ++i)
+            if (FULL || i + H < Ig) kb[i] = __ldg(kp + (i + H) * LV);
+        }
+#pragma unroll
+        for (int b = 0; b < NL; ++b) *reinterpret_cast<V*>(xb + (size_t)(b * CI + o) * N) = acc[b];
+      }
+    }
+  }
+}
+
 // N: transform length of the fused axis. CI: bound on channels per group (in and out; 8 or 16). NB: items per CTA, an
 // item being a (batch, overlap-save segment) pair; a warp transforms NL = min(NB, 2) lines (one channel, two items) at a
 // time. W: compute warps per CTA. PLAIN: the axis has an identity gather map with all N points stored, full channel
@@ -666,12 +777,10 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
   constexpr int E = N / 32, LS = CI * N;  // line (b, c) at xy + (b*CI + c)*N
   constexpr int NL = NB < 2 ? NB : 2;     // lines per warp = batches per contraction thread
   constexpr int NBG = NB / NL;            // batch groups of a CTA
-  constexpr int H = CI / 2;               // input channels per kernel-spectrum half-set
   static_assert(NB == NL * NBG, "NB is 1, 2 or a multiple of 2");
   FC_DYN_SMEM(xy);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int Ig = a.Ig, Og = a.Og;
-  const int64_t kstride = a.Rk * N;  // kernel-spectrum stride between input channels
   fc_wofs ofs;
   ofs.init(lane);
   const fc_omap om = a.omap;
@@ -686,21 +795,22 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
     for (int e = tid; e < NB * CI * N; e += W * 32) xy[e] = make_float2(0.f, 0.f);
     fc_named_bar_sync(1, W * 32);
   }
-  for (int64_t unit = blockIdx.x; unit < a.n_units; unit += gridDim.x) {
-    const int bs = (int)(unit % a.nbs);
-    const int64_t gr = unit / a.nbs;
+  // 32-bit index math: the host guarantees n_units < 2^31
+  const int n_units = (int)a.n_units, R = (int)a.R, Rk = (int)a.Rk, nsx = R / Rk;
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int bs = unit % a.nbs;
+    const int gr = unit / a.nbs;
     // lines of the other axis: when that axis is segmented (Rk < R) the segments sharing kernel line rk run back to
     // back, so the kernel-spectrum slice of (g, rk) is read from HBM once and from L2 afterwards
-    int64_t r, rk;
-    int g;
-    if (a.Rk == a.R) {
-      r = rk = gr % a.R;
-      g = (int)(gr / a.R);
+    int r, rk, g;
+    if (nsx == 1) {
+      g = gr / R;
+      r = rk = gr - g * R;
     } else {
-      const int64_t nsx = a.R / a.Rk, t = gr / nsx;
-      rk = t % a.Rk;
-      g = (int)(t / a.Rk);
-      r = (gr - t * nsx) * a.Rk + rk;
+      const int t = gr / nsx;
+      g = t / Rk;
+      rk = t - g * Rk;
+      r = (gr - t * nsx) * Rk + rk;
     }
     const int b0 = bs * NB;
     // ---- phase 1: forward transform of every (batch, input channel) line of this bin
@@ -716,7 +826,7 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
         const bool active = bb < a.n_items;
         const int it = active ? bb : b0;
         const int bt = PLAIN ? it : it / a.n_seg, sg = PLAIN ? 0 : it - bt * a.n_seg;
-        const float2* src = a.xin + (((int64_t)bt * a.Cin + g * Ig + i) * a.R + r) * a.n_in;
+        const float2* src = a.xin + (((int64_t)bt * a.Cin + g * Ig + i) * R + r) * a.n_in;
         if (plain_in) {
 #pragma unroll
           for (int q = 0; q < E; ++q) {
@@ -749,19 +859,19 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
     fc_named_bar_sync(1, W * 32);
     // ---- L2 prefetch for the unit that runs `prefetch_dist` units later (the next wave on this SM): its input lines
     if (a.prefetch_dist > 0) {
-      const int64_t un = unit + a.prefetch_dist;
-      if (un < a.n_units) {
-        const int bsn = (int)(un % a.nbs);
-        const int64_t grn = un / a.nbs;
-        int64_t rn;
-        int gn;
-        if (a.Rk == a.R) {
-          rn = grn % a.R;
-          gn = (int)(grn / a.R);
+      const int un = unit + a.prefetch_dist;
+      if (un < n_units) {
+        const int bsn = un % a.nbs;
+        const int grn = un / a.nbs;
+        int rn, rkn, gn;
+        if (nsx == 1) {
+          gn = grn / R;
+          rn = rkn = grn - gn * R;
         } else {
-          const int64_t nsx = a.R / a.Rk, t = grn / nsx;
-          gn = (int)(t / a.Rk);
-          rn = (grn - t * nsx) * a.Rk + t % a.Rk;
+          const int t = grn / nsx;
+          gn = t / Rk;
+          rkn = t - gn * Rk;
+          rn = (grn - t * nsx) * Rk + rkn;
         }
         if (a.n_seg == 1) {  // (segments of one batch share their input line: nothing to pull ahead)
           const int per_line = (a.n_in * 8 + 127) / 128;  // 128-byte lines per input line
@@ -772,179 +882,19 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
               fc_prefetch_l2(a.xin + (((int64_t)(bsn * NB + bl) * a.Cin + gn * Ig + i) * a.R + rn) * a.n_in + seg * 16);
           }
         }
-        if (bsn == 0) {  // and, once per bin, its slice of the kernel spectrum
-          constexpr int kper = N * 8 / 128;
-          for (int idx = tid; idx < Og * Ig * kper; idx += W * 32) {
-            const int ln = idx / kper, seg = idx - ln * kper;
-            fc_prefetch_l2(a.kspec + ((int64_t)(gn * Og * Ig + ln) * a.Rk + rn % a.Rk) * N + seg * 16);
-          }
+        if (bsn == 0) {  // and, once per bin, its slice of the kernel spectrum (one contiguous block)
+          const float2* ks = a.kspec + ((int64_t)gn * a.Rk + rkn) * ((int64_t)Og * Ig * N);
+          for (int idx = tid; idx < Og * Ig * (N / 16); idx += W * 32) fc_prefetch_l2(ks + idx * 16);
         }
       }
     }
     // ---- phase 2: per-bin contraction over the input channels of the group, in place (X -> Y); a thread takes two
     // adjacent bins (16-byte accesses) of one batch group. The kernel-spectrum loads run in two half-sets, one always
     // in flight.
-    if constexpr (CI <= 8) {
-    for (int idx = tid; idx < (N / 2) * NBG; idx += W * 32) {
-      const int u = idx & (N / 2 - 1), bg = idx / (N / 2);
-      float2* xb = xy + (size_t)(bg * NL * CI) * N + 2 * u;  // line (bl, c) of this batch group at xb + (bl*CI + c)*N
-      float4 xr[NL][CI];
-#pragma unroll
-      for (int b = 0; b < NL; ++b)
-#pragma unroll
-        for (int i = 0; i < CI; ++i) xr[b][i] = *reinterpret_cast<const float4*>(xb + (size_t)(b * CI + i) * N);
-      // one running pointer over the (o, i) lines of this bin: consecutive lines are kstride apart
-      const char* kp = reinterpret_cast<const char*>(a.kspec + (((int64_t)(g * Og) * Ig) * a.Rk + rk) * N + 2 * u);
-      const int64_t ksb = kstride * (int64_t)sizeof(float2);
-      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 ka[H], kb[H];
-#pragma unroll
-      for (int i = 0; i < H; ++i) {
-        const bool on = PLAIN || i < Ig;  // PLAIN implies Ig == CI
-        ka[i] = on ? __ldg(reinterpret_cast<const float4*>(kp)) : zero4;
-        if (on) kp += ksb;
-      }
-#pragma unroll
-      for (int i = 0; i < H; ++i) {
-        const bool on = PLAIN || i + H < Ig;
-        kb[i] = on ? __ldg(reinterpret_cast<const float4*>(kp)) : zero4;
-        if (on) kp += ksb;
-      }
-#pragma unroll 1
-      for (int o = 0; o < Og; ++o) {
-        const bool more = o + 1 < Og;
-        float4 acc[NL];
-#pragma unroll
-        for (int b = 0; b < NL; ++b) acc[b] = zero4;
-#pragma unroll
-        for (int i = 0; i < H; ++i) {
-#pragma unroll
-          for (int b = 0; b < NL; ++b) {
-            acc[b].x = fmaf(xr[b][i].x, ka[i].x, acc[b].x);
-            acc[b].y = fmaf(xr[b][i].x, ka[i].y, acc[b].y);
-            acc[b].z = fmaf(xr[b][i].z, ka[i].z, acc[b].z);
-            acc[b].w = fmaf(xr[b][i].z, ka[i].w, acc[b].w);
-            acc[b].x = fmaf(-xr[b][i].y, ka[i].y, acc[b].x);
-            acc[b].y = fmaf(xr[b][i].y, ka[i].x, acc[b].y);
-            acc[b].z = fmaf(-xr[b][i].w, ka[i].w, acc[b].z);
-            acc[b].w = fmaf(xr[b][i].w, ka[i].z, acc[b].w);
-          }
-        }
-        if (more) {
-#pragma unroll
-          for (int i = 0; i < H; ++i) {
-            const bool on = PLAIN || i < Ig;
-            if (on) {
-              ka[i] = __ldg(reinterpret_cast<const float4*>(kp));
-              kp += ksb;
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < H; ++i) {
-#pragma unroll
-          for (int b = 0; b < NL; ++b) {
-            acc[b].x = fmaf(xr[b][i + H].x, kb[i].x, acc[b].x);
-            acc[b].y = fmaf(xr[b][i + H].x, kb[i].y, acc[b].y);
-            acc[b].z = fmaf(xr[b][i + H].z, kb[i].z, acc[b].z);
-            acc[b].w = fmaf(xr[b][i + H].z, kb[i].w, acc[b].w);
-            acc[b].x = fmaf(-xr[b][i + H].y, kb[i].y, acc[b].x);
-            acc[b].y = fmaf(xr[b][i + H].y, kb[i].x, acc[b].y);
-            acc[b].z = fmaf(-xr[b][i + H].w, kb[i].w, acc[b].z);
-            acc[b].w = fmaf(xr[b][i + H].w, kb[i].z, acc[b].w);
-          }
-        }
-        if (more) {
-#pragma unroll
-          for (int i = 0; i < H; ++i) {
-            const bool on = PLAIN || i + H < Ig;
-            if (on) {
-              kb[i] = __ldg(reinterpret_cast<const float4*>(kp));
-              kp += ksb;
-            }
-          }
-        }
-#pragma unroll
-        for (int b = 0; b < NL; ++b) *reinterpret_cast<float4*>(xb + (size_t)(b * CI + o) * N) = acc[b];
-      }
-    }
-    } else {
-    // 9..16 channels per group: one bin per thread (8-byte accesses) keeps the signal values of both items in registers
-    for (int idx = tid; idx < N * NBG; idx += W * 32) {
-      const int u = idx & (N - 1), bg = idx / N;
-      float2* xb = xy + (size_t)(bg * NL * CI) * N + u;
-      float2 xr[NL][CI];
-#pragma unroll
-      for (int b = 0; b < NL; ++b)
-#pragma unroll
-        for (int i = 0; i < CI; ++i) xr[b][i] = xb[(size_t)(b * CI + i) * N];
-      const char* kp = reinterpret_cast<const char*>(a.kspec + (((int64_t)(g * Og) * Ig) * a.Rk + rk) * N + u);
-      const int64_t ksb = kstride * (int64_t)sizeof(float2);
-      const float2 zero2 = make_float2(0.f, 0.f);
-      float2 ka[H], kb[H];
-#pragma unroll
-      for (int i = 0; i < H; ++i) {
-        const bool on = PLAIN || i < Ig;
-        ka[i] = on ? __ldg(reinterpret_cast<const float2*>(kp)) : zero2;
-        if (on) kp += ksb;
-      }
-#pragma unroll
-      for (int i = 0; i < H; ++i) {
-        const bool on = PLAIN || i + H < Ig;
-        kb[i] = on ? __ldg(reinterpret_cast<const float2*>(kp)) : zero2;
-        if (on) kp += ksb;
-      }
-#pragma unroll 1
-      for (int o = 0; o < Og; ++o) {
-        const bool more = o + 1 < Og;
-        float2 acc[NL];
-#pragma unroll
-        for (int b = 0; b < NL; ++b) acc[b] = zero2;
-#pragma unroll
-        for (int i = 0; i < H; ++i) {
-#pragma unroll
-          for (int b = 0; b < NL; ++b) {
-            acc[b].x = fmaf(xr[b][i].x, ka[i].x, acc[b].x);
-            acc[b].y = fmaf(xr[b][i].x, ka[i].y, acc[b].y);
-            acc[b].x = fmaf(-xr[b][i].y, ka[i].y, acc[b].x);
-            acc[b].y = fmaf(xr[b][i].y, ka[i].x, acc[b].y);
-          }
-        }
-        if (more) {
-#pragma unroll
-          for (int i = 0; i < H; ++i) {
-            const bool on = PLAIN || i < Ig;
-            if (on) {
-              ka[i] = __ldg(reinterpret_cast<const float2*>(kp));
-              kp += ksb;
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < H; ++i) {
-#pragma unroll
-          for (int b = 0; b < NL; ++b) {
-            acc[b].x = fmaf(xr[b][i + H].x, kb[i].x, acc[b].x);
-            acc[b].y = fmaf(xr[b][i + H].x, kb[i].y, acc[b].y);
-            acc[b].x = fmaf(-xr[b][i + H].y, kb[i].y, acc[b].x);
-            acc[b].y = fmaf(xr[b][i + H].y, kb[i].x, acc[b].y);
-          }
-        }
-        if (more) {
-#pragma unroll
-          for (int i = 0; i < H; ++i) {
-            const bool on = PLAIN || i + H < Ig;
-            if (on) {
-              kb[i] = __ldg(reinterpret_cast<const float2*>(kp));
-              kp += ksb;
-            }
-          }
-        }
-#pragma unroll
-        for (int b = 0; b < NL; ++b) xb[(size_t)(b * CI + o) * N] = acc[b];
-      }
-    }
-    }
+    if (PLAIN || Ig == CI)
+      fc_fused_contract<N, CI, NL, NBG, W, true>(xy, a, g, rk, tid);
+    else
+      fc_fused_contract<N, CI, NL, NBG, W, false>(xy, a, g, rk, tid);
     fc_named_bar_sync(1, W * 32);
     // ---- phase 3: inverse transform of every (batch, output channel) line, crop / stride on store
     const int n_task3 = Og * NBG;

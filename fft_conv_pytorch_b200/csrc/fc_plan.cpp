@@ -766,6 +766,16 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   I.algo_bytes_s3 = I.xspec_bytes + I.kspec_bytes + I.yspec_bytes;
   I.algo_bytes_s4 = I.yspec_bytes + 4 * I.out_elems + 4 * (int64_t)P.cout;
   fc_plan_build_program(pl);
+  if (I.fused) {
+    // The fused axis kernel reads the kernel spectrum bin-major: [group][line r][o_local][i][n], i.e. the Og*Ig channel
+    // pairs of one (group, line) are adjacent lines (fc_fused_contract). The last pass of the kernel program writes it.
+    fc_pass& k = pl->ker_fwd.back().pass;
+    const int64_t OI = (int64_t)Og * Ig, Nl = k.n_out;
+    k.out_oq = OI;
+    k.out_osA = k.R * OI * Nl;
+    k.out_os = Nl;
+    k.out_rs = OI * Nl;
+  }
   if (I.segments > 1 && !I.fused) return fail(FC_EUNSUPPORTED, "internal: segmented plan without the fused axis kernel");
   if (nd == 2 && pl->ax[1].seg_n > 1 && (pl->prog.front().type != FC_L_FAST_R2C || pl->prog.back().type != FC_L_FAST_C2R))
     return fail(FC_EUNSUPPORTED, "internal: segmented rows without the transposing row kernels");

@@ -76,6 +76,9 @@ struct fc_pass {
   // element (outer o, line r, index n) lives at o*os + r*rs + n*es (complex elements, or floats on the real side)
   int64_t in_os, in_rs, in_es;
   int64_t out_os, out_rs, out_es;
+  // generic pass only: when out_oq > 0 the output base of outer item o is (o / out_oq)*out_osA + (o % out_oq)*out_os
+  // (the bin-major kernel spectrum of the fused plans: the out_oq = Og*Ig channel pairs of a group are adjacent lines)
+  int64_t out_oq, out_osA;
   // R2C input base: base(o) = ((o/o_c2)/o_q)*o_sA + ((o/o_c2)%o_q)*o_sB + (o%o_c2)*o_sC   (replaces in_os)
   int64_t o_c2, o_q, o_sA, o_sB, o_sC;
   fc_imap imap;

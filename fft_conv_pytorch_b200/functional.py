@@ -252,7 +252,8 @@ def _run(transposed: bool, signal: Tensor, kernel: Tensor, bias: Optional[Tensor
         s_in, s_out = _side_streams(dev)
         s_in.wait_stream(cur)
         s_out.wait_stream(cur)
-        bounds = [(B * c) // n_chunks for c in range(n_chunks + 1)]
+        bounds = _chunk_bounds(B, n_chunks)
+        n_chunks = len(bounds) - 1
         ev_in = []
         with torch.cuda.stream(s_in):
             for c in range(n_chunks):
@@ -283,7 +284,20 @@ def _run(transposed: bool, signal: Tensor, kernel: Tensor, bias: Optional[Tensor
         return y_host
 
 
-_HOST_PIPELINE_CHUNKS = int(os.environ.get("FFTCONV_B200_HOST_CHUNKS", "4"))
+_HOST_PIPELINE_CHUNKS = int(os.environ.get("FFTCONV_B200_HOST_CHUNKS", "5"))
+
+
+def _chunk_bounds(B: int, n_chunks: int):
+    """Batch ranges of the host pipeline: an even split into n_chunks - 1 parts whose last part is halved again, so
+    that the tail nothing can overlap with (kernels + download of the last chunk) is short. B = 8, 5 chunks: 2,2,2,1,1
+    (measured 1.81 ms against 1.87 ms for 2,2,2,2 at BASELINE c2)."""
+    if n_chunks < 3 or B < n_chunks:
+        n = min(B, n_chunks)
+        return [(B * c) // n for c in range(n + 1)]
+    n = n_chunks - 1
+    b = [(B * c) // n for c in range(n + 1)]
+    mid = (b[-2] + b[-1]) // 2
+    return b[:-1] + ([mid] if b[-2] < mid < b[-1] else []) + [b[-1]]
 _side = {}
 
 

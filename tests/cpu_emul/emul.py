@@ -50,8 +50,8 @@ def conv(x, w, b=None, transposed=False, staged=False, **kw):
     x = np.ascontiguousarray(x, np.float32)
     w = np.ascontiguousarray(w, np.float32)
     b = None if b is None else np.ascontiguousarray(b, np.float32)
-    if staged:  # the stage calls need the unsegmented layout
-        kw = dict(kw, flags=kw.get("flags", 0) | L.FC_FLAG_NO_SEGMENT)
+    if staged:  # the stage calls need the unsegmented layout and the channel-major kernel spectrum
+        kw = dict(kw, flags=kw.get("flags", 0) | L.FC_FLAG_NO_SEGMENT | L.FC_FLAG_NO_FUSED_MID)
     plan = plan_for(x.shape, w.shape, transposed, **kw)
     info = plan.info
     const = np.zeros(info.const_bytes, np.uint8)
