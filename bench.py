@@ -223,8 +223,9 @@ def bench_ours(args, cfg):
 
         # ---- end to end through the public API with host buffers (pinned): H2D + kernels + D2H every step
         xh = [torch.randn(*cfg["x"]).pin_memory() for _ in range(2)]
-        for i in range(2):
-            mod(xh[i % 2])
+        yh = None
+        for i in range(max(args.warmup, 3)):  # same call pattern as the timed loop (the previous result is still referenced while
+            yh = mod(xh[i % 2])               # the next one is allocated), so no first-use pinned allocation lands in the timed region
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):

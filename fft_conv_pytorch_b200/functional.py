@@ -284,13 +284,13 @@ def _run(transposed: bool, signal: Tensor, kernel: Tensor, bias: Optional[Tensor
         return y_host
 
 
-_HOST_PIPELINE_CHUNKS = int(os.environ.get("FFTCONV_B200_HOST_CHUNKS", "5"))
+_HOST_PIPELINE_CHUNKS = int(os.environ.get("FFTCONV_B200_HOST_CHUNKS", "6"))
 
 
 def _chunk_bounds(B: int, n_chunks: int):
     """Batch ranges of the host pipeline: an even split into n_chunks - 1 parts whose last part is halved again, so
-    that the tail nothing can overlap with (kernels + download of the last chunk) is short. B = 8, 5 chunks: 2,2,2,1,1
-    (measured 1.81 ms against 1.87 ms for 2,2,2,2 at BASELINE c2)."""
+    that the tail nothing can overlap with (kernels + download of the last chunk) is short. B = 8, 6 chunks: 1,2,1,2,1,1
+    (BASELINE c2 through bench.py: 1.72 ms per call; 1.75 with 5 chunks, 1.84 with 4, 1.87 with 8, 2.32 unchunked)."""
     if n_chunks < 3 or B < n_chunks:
         n = min(B, n_chunks)
         return [(B * c) // n for c in range(n + 1)]

@@ -120,7 +120,10 @@ int fc_plan_describe(const fc_plan* plan, char* buf, size_t buflen);
 /* One-time: fill the plan's constant table (twiddle factors) in caller-owned device memory of const_bytes. */
 int fc_plan_init_const(const fc_plan* plan, void* d_const, void* stream);
 
-/* Stage calls (unfused pipeline). d_ws: workspace_bytes scratch. */
+/* Stage calls (unfused pipeline). d_ws: workspace_bytes scratch. The kernel spectrum is a plan-specific object (layout
+ * chosen for the plan's contraction kernel): fc_contract takes the channel-major layout [o*Cin/g + i][bins] only and
+ * returns FC_EUNSUPPORTED for plans with info.fused / info.tensor_core set; all three stage calls return FC_EUNSUPPORTED
+ * for plans with info.segments > 1. Plans made with FC_FLAG_NO_FUSED_MID | FC_FLAG_NO_SEGMENT | FC_FLAG_NO_TC run them. */
 int fc_signal_spectrum(const fc_plan* plan, const void* d_const, const float* d_x, float* d_xspec, void* d_ws, void* stream);
 int fc_kernel_spectrum(const fc_plan* plan, const void* d_const, const float* d_w, float* d_kspec, void* d_ws, void* stream);
 int fc_contract(const fc_plan* plan, const float* d_xspec, const float* d_kspec, float* d_yspec, void* stream);

@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-timeout 300 python scripts/e2e_timeline.py > gpurun_out/e2e_timeline.log 2>&1
+for c in 1 4 5 6 8; do
+FFTCONV_B200_HOST_CHUNKS=$c timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/bench_short$c.log 2>&1
+done
