@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
     const int rem = t - o * tpo;
     const int sg = p.seg_n > 1 ? rem / tps : 0;
     const int r0 = (rem - sg * tps) * TR;
-    const int ub = sg * p.seg_V - p.seg_off;  // first dense position of this segment (even)
+    const int ub = sg * p.seg_V - p.seg_off - p.imap.pad;  // source index of the segment's first dense position (even)
     const float* img = a.x + (int64_t)o * p.o_sA;
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
       const bool valid = r < R;
       const float2* row = reinterpret_cast<const float2*>(img + (int64_t)(valid ? r : 0) * p.in_rs + ub) + gl;
 #pragma unroll
-      for (int q = 0; q < E; ++q)  // L and ub are even (host check), so the pair (2m, 2m + 1) is in or out together
+      for (int q = 0; q < E; ++q)  // L, the zero padding and ub are even (host check): the pair (2m, 2m + 1) is in or out together
         v[l][q] = (valid && (unsigned)(ub + 2 * (gl + G * q)) < (unsigned)L) ? __ldg(row + G * q) : make_float2(0.f, 0.f);
     }
   };
@@ -486,13 +486,18 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
           const int64_t jr = r * p.row_og + er - p.row_ob;
           if (jr < 0 || jr >= p.row_Lout) continue;
           float* yrow = a.out + o * p.out_os + jr * p.out_rs;
+          if (er != 0) {  // a row between the lattice rows: bias only
+#pragma unroll 8
+            for (int j = j_lo + gl; j < j_hi; j += G) yrow[j] = b;
+            continue;
+          }
           // output-driven (coalesced stores): output j takes dense sample n = (j*os + ob) / og when the remainder
           // is 0 and n < lim, else it is bias only
 #pragma unroll 8
           for (int j = j_lo + gl; j < j_hi; j += G) {
             const int tt = j * om.os + om.ob;
             const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
-            const bool live = er == 0 && tt == n * om.og && n < om.lim;
+            const bool live = tt == n * om.og && n < om.lim;
             yrow[j] = (live ? rl[n] : 0.f) + b;
           }
         }

@@ -558,7 +558,7 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     a.seg_off = 0;
     if (nd == 2 && i == 1 && seg_ok && (pl->ax[0].N == 256 || pl->ax[0].N == 512 || pl->ax[0].N == 1024) &&
         !(P.flags & (FC_FLAG_NO_FAST_R2C | FC_FLAG_NO_FAST_C2R)) && !(a.L & 1) &&
-        (P.transposed ? s2 == 1 : (a.pad == 0 && a.g == 1 && P.padding_mode == FC_PAD_CONSTANT))) {
+        (P.transposed ? s2 == 1 : (!(a.pad & 1) && a.g == 1 && P.padding_mode == FC_PAD_CONSTANT))) {
       // Overlap-save along x as well: the transposing row kernels K1 / K4 (which must both apply, see
       // fc_plan_build_program) treat a (row, segment) pair as a line. Segment extents are kept even so that the packed
       // real transforms load and store aligned pairs.
@@ -916,7 +916,8 @@ void fc_plan_build_program(fc_plan* pl) {
     std::memset(&L.fused, 0, sizeof(L.fused));
     const fc_pass& p = L.pass;
     if (i == 0 && allow && !(flags & FC_FLAG_NO_FAST_R2C) && p.kind == FC_R2C && !p.in_rfast && p.out_rfast && !p.twiddle && fast_line_len(p.M) &&
-        p.imap.mode == FC_PAD_CONSTANT && p.imap.pad == 0 && p.imap.up == 1 && p.imap.sub == 1 && p.imap.ext == p.imap.L && !(p.imap.L & 1) && !(p.in_rs & 1) &&
+        p.imap.mode == FC_PAD_CONSTANT && !(p.imap.pad & 1) && p.imap.up == 1 && p.imap.sub == 1 && p.imap.ext == p.imap.L + 2 * p.imap.pad &&
+        !(p.imap.L & 1) && !(p.in_rs & 1) &&
         !(p.o_sA & 1) && !(p.o_sB & 1) && !(p.o_sC & 1) && p.scale == 1.f && !p.conj_out && p.pos_n == 1 && p.pos_r == 0) {
       L.type = FC_L_FAST_R2C;
       retile16(L.pass);

@@ -112,7 +112,15 @@ _FAST_SHAPES = [
     ((1, 2, 260, 600), (2, 2, 3, 3), dict(padding=(1, 1), padding_mode="reflect")),
     ((1, 2, 20, 1100), (2, 2, 3, 5), {}),  # last axis 2048: the one-line-per-warp, 16-warp variant
     ((1, 2, 18, 1030), (2, 1, 3, 4), dict(groups=2, stride=(1, 3))),  # ... with a strided scatter on store
+    ((2, 2, 150, 300), (3, 2, 7, 9), dict(padding=(3, 4))),  # "same" convolution: even zero padding stays on the row kernel K1
 ]
+
+
+def test_row_kernel_takes_even_zero_padding():
+    p = emul.plan_for((2, 2, 150, 300), (3, 2, 7, 9), padding=(3, 4), threads=256)
+    assert "fast_r2c" in p.describe()
+    p = emul.plan_for((2, 2, 150, 300), (3, 2, 7, 9), padding=(3, 3), threads=256)  # odd: pairs would straddle the edge
+    assert "fast_r2c" not in p.describe()
 
 
 @pytest.mark.parametrize("xs,ws,kw", _FAST_SHAPES)
@@ -335,6 +343,8 @@ _SEGMENT_SHAPES = [
     ((1, 2, 280, 660), (2, 2, 3, 4), dict(padding=(1, 3), dilation=(1, 2), output_padding=(0, 1)), True),
     ((1, 2, 140, 2500), (2, 2, 3, 33), {}, False),
     ((1, 3, 200, 1100), (3, 3, 3, 10), dict(padding=(0, 20)), True),  # crop across a segment boundary
+    ((1, 2, 130, 700), (2, 2, 3, 5), dict(padding=(1, 2)), False),  # zero padding inside the first / last row segment
+    ((1, 2, 280, 600), (2, 2, 3, 3), dict(dilation=(3, 2)), False),  # dilated kernel: longer segment overlap
 ]
 
 

@@ -312,6 +312,9 @@ _SEGMENT_CASES = [
     ((2, 2, 260, 2500), (2, 2, 3, 33), {}, False),
     ((1, 3, 200, 1100), (3, 3, 3, 10), dict(padding=(0, 20)), True),
     ((2, 16, 1100, 1300), (16, 16, 15, 15), {}, False),
+    ((2, 8, 640, 720), (8, 8, 9, 9), dict(padding=(4, 4)), False),  # "same" convolution
+    ((1, 2, 600, 700), (2, 2, 5, 5), dict(dilation=(3, 2)), False),  # dilated kernel: longer segment overlap
+    ((1, 2, 300, 4200), (2, 2, 1, 1), {}, False),  # 1 x 1 kernel: segments without overlap
 ]
 
 
