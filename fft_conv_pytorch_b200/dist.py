@@ -30,6 +30,25 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
         p.data.add_(0)
 
 
+def broadcast_kernel_spectrum(entry, kernel: torch.Tensor, device: torch.device, src: int = 0) -> torch.Tensor:
+    """Build the cached kernel spectrum of `kernel` for plan entry `entry` (``functional.get_plan``) on rank `src` only and
+    ship it to the other ranks (NCCL broadcast over NVLink), which install it in their caches. Worth it when the spectrum
+    is small: with overlap-save segments BASELINE c5's is 258 MB and the broadcast takes 0.45 ms on B200 NVLink against
+    3.2 ms for rebuilding it on every rank; an unsegmented multi-GB spectrum is cheaper to rebuild (K << N)."""
+    from . import functional as Fn
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return Fn.kernel_spectrum(entry, kernel, device)
+    if dist.get_rank() == src:
+        kspec = Fn.kernel_spectrum(entry, kernel, device)
+    else:
+        kspec = torch.empty(int(entry.plan.info.kspec_bytes) // 4, dtype=torch.float32, device=device)
+    dist.broadcast(kspec, src=src)
+    if dist.get_rank() != src:
+        Fn.install_kernel_spectrum(entry, kernel, device, kspec)
+    return kspec
+
+
 def shard_batch(x: torch.Tensor, rank: int = None, world: int = None) -> torch.Tensor:
     """This rank's slice of a replicated batch."""
     rank = dist.get_rank() if rank is None else rank

@@ -130,7 +130,7 @@ def kernel_spectrum(entry: _PlanEntry, kernel: Tensor, device: torch.device, use
     It is a derived, non-persistent object: never part of a ``state_dict``."""
     global _kspec_cache_bytes, _launch_counter
     plan = entry.plan
-    dev_idx = device.index if device.index is not None else torch.cuda.current_device()
+    dev_idx = device.index if device.index is not None else (torch.cuda.current_device() if device.type == "cuda" else -1)
     key = (id(plan), id(kernel), dev_idx)
     if use_cache:
         with _lock:
@@ -160,6 +160,22 @@ def kernel_spectrum(entry: _PlanEntry, kernel: Tensor, device: torch.device, use
             while _kspec_cache_bytes > _KSPEC_CACHE_MAX_BYTES and len(_kspec_cache) > 1:
                 _drop_kspec(next(iter(_kspec_cache)))
     return kspec
+
+
+def install_kernel_spectrum(entry: _PlanEntry, kernel: Tensor, device: torch.device, kspec: Tensor) -> None:
+    """Put an externally produced spectrum of `kernel` (same plan layout, e.g. received from another rank:
+    ``dist.broadcast_kernel_spectrum``) into the cache; it is served until the weight changes, like a local one."""
+    global _kspec_cache_bytes
+    plan = entry.plan
+    if kspec.numel() * kspec.element_size() != int(plan.info.kspec_bytes):
+        raise ValueError(f"kernel spectrum has {kspec.numel() * kspec.element_size()} bytes, the plan expects {int(plan.info.kspec_bytes)}")
+    dev_idx = device.index if device.index is not None else (torch.cuda.current_device() if device.type == "cuda" else -1)
+    key = (id(plan), id(kernel), dev_idx)
+    with _lock:
+        _drop_kspec(key)
+        ref = weakref.ref(kernel, lambda _r, k=key: _drop_kspec(k))
+        _kspec_cache[key] = (ref, kernel._version, kernel.data_ptr(), kspec)
+        _kspec_cache_bytes += kspec.numel() * 4
 
 
 def _drop_kspec(key) -> None:

@@ -71,6 +71,46 @@ def test_batch_and_channel_partition_world2():
         assert r[2].shape == ref.shape and np.abs(r[2] - ref).max() < 1e-4  # channel-sharded, gathered
 
 
+def _kspec_worker(rank, world, port, q):
+    from fft_conv_pytorch_b200 import functional as Fn
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # host plan only (no GPU here): rank 0 "owns" a spectrum, the others receive and cache it
+        entry = Fn.get_plan(True, 2, 8, 8, 2, (300, 300), (5, 5), (2, 2), (0, 0), (2, 2), (0, 0), "constant")
+        w = torch.randn(8, 4, 5, 5)
+        cpu = torch.device("cpu")
+        n = int(entry.plan.info.kspec_bytes) // 4
+        if rank == 0:
+            Fn.install_kernel_spectrum(entry, w, cpu, torch.arange(n, dtype=torch.float32))
+        k = fdist.broadcast_kernel_spectrum(entry, w, cpu, src=0)
+        hit = Fn.kernel_spectrum(entry, w, cpu)  # served from the cache: no device work
+        ok = hit.data_ptr() == k.data_ptr() and bool((k == torch.arange(n, dtype=torch.float32)).all())
+        w.add_(1.0)  # a weight update invalidates the received spectrum like a local one
+        stale = Fn._kspec_cache.get((id(entry.plan), id(w), -1))
+        q.put((rank, ok, stale is not None and stale[1] != w._version, int(entry.plan.info.segments)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_kernel_spectrum_broadcast_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_kspec_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, version_moved, segments in res:
+        assert ok and version_moved and segments > 1
+
+
 @pytest.mark.parametrize("total,world", [(8, 2), (5, 2), (32, 8), (3, 4), (1, 8)])
 def test_shard_range_covers_everything(total, world):
     spans = [fdist.shard_range(total, r, world) for r in range(world)]
