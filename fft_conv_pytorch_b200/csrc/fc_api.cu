@@ -793,7 +793,7 @@ int fc_tc_supported(int64_t batch, int64_t cin, int64_t cout, int64_t groups) {
 
 int64_t fc_tc_scratch_bytes(int64_t batch, int64_t cin, int64_t cout, int64_t groups, int64_t bins) {
   const int64_t bp = tc_padded_batch((int)batch), I = cin / groups;
-  return (bins * groups * 2 * bp * 2 * I * 4 * 2 + 255) / 256 * 256 + bins * cout * 2 * bp * 4 + 512;
+  return (bins * groups * 2 * bp * 2 * I * 4 + 255) / 256 * 256 + bins * cout * 2 * bp * 4 + 512;
 }
 
 int fc_tc_prepare_kernel(const float* d_kspec, float* d_kspec_tc, int64_t cin, int64_t cout, int64_t groups, int64_t bins, void* stream) {
@@ -810,10 +810,10 @@ int fc_tc_complex_matmul(const float* d_a, const float* d_b_tc, float* d_y, void
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t bp = tc_padded_batch((int)batch), I = cin / groups;
   float* xtc = (float*)d_scratch;
-  const int64_t xtc_bytes = (bins * groups * 2 * bp * 2 * I * 4 * 2 + 255) / 256 * 256;
+  const int64_t xtc_bytes = (bins * groups * 2 * bp * 2 * I * 4 + 255) / 256 * 256;
   float* ytc = (float*)((char*)d_scratch + xtc_bytes);
   if (bp != batch) {
-    cudaError_t e = cudaMemsetAsync(xtc, 0, (size_t)(bins * groups * 2 * bp * 2 * I * 4 * 2), st);
+    cudaError_t e = cudaMemsetAsync(xtc, 0, (size_t)(bins * groups * 2 * bp * 2 * I * 4), st);
     if (e != cudaSuccess) return set_err((int)e, "fc_tc_complex_matmul: memset failed");
   }
   int rc = launch_tc_relayout(1, d_a, xtc, bins, (int)batch, (int)cin, (int)cout, (int)groups, st);

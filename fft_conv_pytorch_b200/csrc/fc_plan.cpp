@@ -747,7 +747,7 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     I.kspec_workspace_bytes = I.workspace_bytes;
     if (pl->use_tc) {
       pl->off_xtc = align_up(I.workspace_bytes, 256);
-      const int64_t xtc = bins * P.groups * 2 * bp * 2 * Ig * 4 * 2;  // hi and lo copies
+      const int64_t xtc = bins * P.groups * 2 * bp * 2 * Ig * 4;
       pl->off_ytc = align_up(pl->off_xtc + xtc, 256);
       const int64_t ytc = bins * P.cout * 2 * bp * 4;
       I.workspace_bytes = align_up(pl->off_ytc + ytc, 256) + 256;
@@ -982,7 +982,7 @@ void fc_plan_build_program(fc_plan* pl) {
     pl->prog.push_back(L);
   } else if (pl->use_tc) {
     const int bp = P.batch <= 8 ? 8 : (P.batch + 7) / 8 * 8;
-    const int64_t xtc = pl->info.bins * P.groups * 2 * bp * 2 * Ig * 4 * 2, ytc = pl->info.bins * P.cout * 2 * bp * 4;
+    const int64_t xtc = pl->info.bins * P.groups * 2 * bp * 2 * Ig * 4, ytc = pl->info.bins * P.cout * 2 * bp * 4;
     const char* names[3] = {"tc_relayout_x", "tc_gemm_3xtf32", "tc_relayout_y"};
     const int64_t bytes[3] = {pl->info.xspec_bytes + xtc, pl->info.kspec_bytes + xtc + ytc, ytc + pl->info.yspec_bytes};
     for (int j = 0; j < 3; ++j) {

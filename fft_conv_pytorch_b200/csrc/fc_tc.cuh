@@ -23,8 +23,9 @@
 // (1024 bytes), the eight 16-byte pieces of a row XOR-swizzled with the row index (UMMA SWIZZLE_128B, K-major). A
 // blob is contiguous, so one bulk async copy (cp.async.bulk) moves it into its pipeline stage at full DRAM efficiency.
 //   A blobs : [bin][group][pass][chunk] x (MT*128 rows x 32 fp32)          kernel spectrum, rows = output channels
-//   Bt blobs: [bin][group][chunk] x {hi, lo} x (N rows x 32 fp32)          signal spectrum, rows = (batch, re/im);
-//             hi = the raw value (the tensor core ignores the low 13 mantissa bits), lo = value - truncated value
+//   Bt blobs: [bin][group][chunk] x (N rows x 32 fp32)                     signal spectrum, rows = (batch, re/im); the
+//             raw values (the tensor core ignores the low 13 mantissa bits = the "hi" operand); like A's, the "lo" operand
+//             (value - truncated value) is derived in shared memory by the GEMM kernel, so it never crosses HBM
 // One CTA of the relayout kernels moves a 32 x 32 (rows x bins) tile through shared memory so that the bin-innermost
 // side is coalesced; mode 2 brings the product D[bin][o][2*Bp] back to the pass-order layout [(b*Cout + o)][bin].
 FC_DEV int64_t fc_tc_swz_off(int r, int j) {  // float offset of (row r, fp32 column j < 32) inside a blob
@@ -84,11 +85,7 @@ __global__ void fc_tc_relayout_kernel(fc_tc_relayout_args a) {
         const int rows[4] = {2 * b, 2 * b, 2 * b + 1, 2 * b + 1};
         const int cols[4] = {i, a.I + i, i, a.I + i};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float* dst = a.out + (blob + (cols[e] >> 5)) * (2 * N * 32) + fc_tc_swz_off(rows[e], cols[e] & 31);
-          dst[0] = vals[e];
-          dst[N * 32] = fc_tc_lo(vals[e]);
-        }
+        for (int e = 0; e < 4; ++e) a.out[(blob + (cols[e] >> 5)) * (N * 32) + fc_tc_swz_off(rows[e], cols[e] & 31)] = vals[e];
       }
     }
   } else {
@@ -215,7 +212,7 @@ FC_DEV void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // ------------------------------------------------------------------------------------------------ the GEMM kernel
 struct fc_tc_args {
   const float* A;   // A blobs  [item][pass][chunk][MT*128 x 32]
-  const float* Bt;  // Bt blobs [item][chunk][2][N x 32]
+  const float* Bt;  // Bt blobs [item][chunk][N x 32]
   float* D;         // [item][O][N]   product (complex Y[f][g][o][b])
   int64_t n_items;  // bins * G
   int32_t O, I, B;  // per group; O % 128 == 0, (2I) % 32 == 0, B = padded batch: N = 2B in {16, 32, 48, 64}
@@ -223,8 +220,8 @@ struct fc_tc_args {
 
 // One CTA per SM, persistent over (bin, group) items; warp-specialised:
 //   producer (warp 8, one lane): for every chunk, waits until the stage is free and issues two bulk async copies
-//     (A blob, Bt hi+lo blob) that complete on the stage's "full" mbarrier;
-//   splitters (warps 0-7): wait "full", derive the low part of A in shared memory, fence to the async proxy and
+//     (A blob, Bt blob) that complete on the stage's "full" mbarrier;
+//   splitters (warps 0-7): wait "full", derive the low parts of A and Bt in shared memory, fence to the async proxy and
 //     arrive on the stage's "ready" mbarrier; after the last chunk of an item they drain the accumulator
 //     (warps 0-3 / 4-7: the two 128-row tiles) from TMEM straight to global memory and release it ("acc_free");
 //   MMA issuer (warp 9, one lane): waits "ready", issues the 3 x 4 x MT tcgen05.mma of the chunk into one of two
@@ -285,9 +282,9 @@ __global__ void __launch_bounds__(FC_TC_THREADS, 1) fc_tc_gemm_kernel(fc_tc_args
         const int pass = (int)(ip % passes);
         const int64_t item = blockIdx.x + (ip / passes) * gridDim.x;
         unsigned char* st = sbase + (size_t)s * stage_bytes;
-        mbar_expect_tx(&bar_full[s], (uint32_t)(A_BYTES + 2 * B_BYTES));
+        mbar_expect_tx(&bar_full[s], (uint32_t)(A_BYTES + B_BYTES));
         bulk_g2s(st, a.A + (((item * passes + pass) * n_chunks + c) * (int64_t)(A_BYTES / 4)), A_BYTES, &bar_full[s]);
-        bulk_g2s(st + 2 * A_BYTES, a.Bt + ((item * n_chunks + c) * (int64_t)(2 * B_BYTES / 4)), 2 * B_BYTES, &bar_full[s]);
+        bulk_g2s(st + 2 * A_BYTES, a.Bt + ((item * n_chunks + c) * (int64_t)(B_BYTES / 4)), B_BYTES, &bar_full[s]);
       }
     }
   } else if (warp == 9) {
@@ -338,7 +335,15 @@ __global__ void __launch_bounds__(FC_TC_THREADS, 1) fc_tc_gemm_kernel(fc_tc_args
         const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
         *reinterpret_cast<float4*>(a_lo + off) = make_float4(fc_tc_lo(v.x), fc_tc_lo(v.y), fc_tc_lo(v.z), fc_tc_lo(v.w));
       }
-      fence_proxy_async();  // generic-proxy writes of a_lo -> visible to the tensor core (async proxy)
+      {  // low part of Bt: N rows x eight 16-byte pieces, same positions
+        unsigned char* b_hi = st + 2 * A_BYTES;
+        unsigned char* b_lo = b_hi + B_BYTES;
+        for (int pc = tid; pc < N * 8; pc += 256) {
+          const float4 v = *reinterpret_cast<const float4*>(b_hi + (pc << 4));
+          *reinterpret_cast<float4*>(b_lo + (pc << 4)) = make_float4(fc_tc_lo(v.x), fc_tc_lo(v.y), fc_tc_lo(v.z), fc_tc_lo(v.w));
+        }
+      }
+      fence_proxy_async();  // generic-proxy writes of a_lo / b_lo -> visible to the tensor core (async proxy)
       mbar_arrive(&bar_ready[s]);
       if (c == n_chunks - 1) {
         // ---- epilogue of this (item, pass): TMEM -> registers -> global
