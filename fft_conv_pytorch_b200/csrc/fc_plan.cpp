@@ -565,14 +565,16 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
       const int64_t Kd2 = (int64_t)(a.K - 1) * d2 + 1;
       const int64_t n_need = ((int64_t)(a.Lout - 1) * a.omap.os + a.omap.ob) / a.omap.og + 1;
       const int64_t off = P.transposed ? ((Kd2 - 1 + 1) & ~int64_t(1)) : 0;
-      const double io = (double)P.batch * (P.cin + P.cout), kio = (double)P.cout * Ig_;
-      double best = N <= kMaxRealLine ? (double)(N / 2 + 1) * (io + kio) : 1e300;
+      // cost = bins per row (the work of every later kernel is proportional to it); it depends on the geometry only, never
+      // on the batch, so the plans of the batch chunks of the host pipeline agree with the full-batch plan they share
+      // the kernel spectrum with
+      double best = N <= kMaxRealLine ? (double)(N / 2 + 1) : 1e300;
       int best_ns = 0;
       for (int Ns = 256; Ns <= 2048 && Ns < N; Ns *= 2) {  // (128-point segments measured slower: the short-row kernels lose more than the bins save)
         const int64_t V = P.transposed ? Ns - off : ((Ns - Kd2 + 1) & ~int64_t(1));
         if (V < Ns / 2) continue;
         const int64_t ns = (n_need + V - 1) / V;
-        const double c = (double)ns * (Ns / 2 + 1) * io + (double)(Ns / 2 + 1) * kio;
+        const double c = (double)ns * (Ns / 2 + 1);
         if (force_seg[1] ? Ns == force_seg[1] : c < best) {
           best = c;
           best_ns = Ns;
@@ -590,17 +592,17 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
       // Overlap-save along y: the fused axis kernel transforms segments of Ns points, of which
       // V = Ns - (Kd - 1) outputs are alias-free, so the kernel spectrum is Ns instead of N bins long on this axis
       // (BASELINE c5: 2048 -> 256, 17.2 GB -> 2.1 GB) and a long axis stays inside the fused kernel's line lengths.
-      // Cost model: elements moved through the fused kernel, signal + product lines plus the kernel spectrum.
+      // Cost: points transformed per line (segments * Ns against the unsegmented N, when that is fusable at all); geometry
+      // only, see the last axis below.
       const int64_t Kd2 = (int64_t)(a.K - 1) * d2 + 1;
       const int64_t n_need = ((int64_t)(a.Lout - 1) * a.omap.os + a.omap.ob) / a.omap.og + 1;  // dense outputs to produce
-      const double io = (double)P.batch * (P.cin + P.cout), kio = (double)P.cout * Ig_;
-      double best = (N >= 256 && N <= 1024) ? (double)N * io + (double)N * kio : 1e300;  // unsegmented and fusable
+      double best = (N >= 256 && N <= 1024) ? (double)N : 1e300;  // unsegmented and fusable
       int best_ns = 0;
       for (int Ns = 256; Ns <= 1024 && Ns < N; Ns *= 2) {
         const int64_t V = Ns - Kd2 + 1;
         if (V < Ns / 2) continue;
         const int64_t ns = (n_need + V - 1) / V;
-        const double c = (double)ns * Ns * io + (double)Ns * kio;
+        const double c = (double)ns * Ns;
         if (force_seg[0] ? Ns == force_seg[0] : c < best) {
           best = c;
           best_ns = Ns;

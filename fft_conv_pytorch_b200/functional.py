@@ -283,6 +283,8 @@ def _run(transposed: bool, signal: Tensor, kernel: Tensor, bias: Optional[Tensor
             sub = entry if a1 - a0 == B else get_plan(transposed, a1 - a0, cin, cout, groups, tuple(int(v) for v in signal.shape[2:]),
                                                       tuple(int(v) for v in kernel.shape[2:]), stride_, padding_, dilation_, opad_, padding_mode, flags)
             sp = sub.plan
+            if (sp.fft_size, int(sp.info.segments), int(sp.info.kspec_bytes)) != (plan.fft_size, int(plan.info.segments), int(plan.info.kspec_bytes)):
+                raise RuntimeError("internal: the plan of a batch chunk does not share the kernel-spectrum layout of the full-batch plan")
             cur.wait_event(ev_in[c])
             L.check(lib, lib.fc_conv(sp.handle, _ptr(sub.const_for(dev)), ctypes.c_void_p(x_stage[a0:a1].data_ptr()), _ptr(kspec), _ptr(b_dev),
                                      ctypes.c_void_p(y_stage[a0:a1].data_ptr()), _ptr(ws), stream), "fc_conv")

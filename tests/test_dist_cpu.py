@@ -79,7 +79,7 @@ def _kspec_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         # host plan only (no GPU here): rank 0 "owns" a spectrum, the others receive and cache it
-        entry = Fn.get_plan(True, 2, 8, 8, 2, (300, 300), (5, 5), (2, 2), (0, 0), (2, 2), (0, 0), "constant")
+        entry = Fn.get_plan(True, 2, 8, 8, 2, (520, 300), (5, 5), (2, 2), (0, 0), (2, 2), (0, 0), "constant")
         w = torch.randn(8, 4, 5, 5)
         cpu = torch.device("cpu")
         n = int(entry.plan.info.kspec_bytes) // 4

@@ -329,7 +329,7 @@ _SEGMENT_SHAPES = [
     # first axis long enough (and the kernel short enough) that the fused axis kernel runs overlap-save segments
     ((2, 2, 530, 40), (3, 2, 9, 3), {}, False),
     ((1, 12, 530, 36), (12, 12, 7, 3), {}, False),  # 9..16 channels per group: the one-bin-per-thread contraction
-    ((1, 18, 300, 36), (18, 9, 5, 3), dict(stride=(2, 2), dilation=(2, 2), groups=2), True),  # BASELINE c5 in small
+    ((1, 18, 520, 36), (18, 9, 5, 3), dict(stride=(2, 2), dilation=(2, 2), groups=2), True),  # BASELINE c5 in small
     ((2, 3, 700, 40), (3, 3, 5, 3), dict(padding=(2, 1), padding_mode="reflect"), False),  # general gather map
     ((1, 2, 1200, 36), (2, 1, 4, 3), dict(groups=2, stride=(3, 1), padding=(5, 0)), False),  # strided scatter on store
     ((1, 2, 330, 40), (2, 2, 3, 3), dict(stride=2, padding=1, output_padding=1), True),  # zero-stuffed signal
