@@ -675,13 +675,13 @@ FC_DEV void fc_cmac(float4& acc, const float4& x, const float4& k) {
 }
 FC_DEV void fc_vzero(float2& v) { v = make_float2(0.f, 0.f); }
 FC_DEV void fc_vzero(float4& v) { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+// One bin per thread (8-byte accesses): the signal values of both items of a thread take 4*CI registers, which leaves
+// room for 3-4 output channels' worth of kernel-spectrum loads in flight under the 128-register cap. Two adjacent bins
+// per thread (16-byte accesses, 8*CI registers of signal values) measured 9 % slower at BASELINE c2 and 12 % at 256 x 256:
+// this phase waits on its loads (profiles/r1s3_kb_phase_ablation.txt), so prefetch depth beats wider accesses.
 template <int CI>
 struct fc_cvec {
-  typedef float4 type;  // up to 8 channels per group: two adjacent bins per thread (16-byte accesses)
-};
-template <>
-struct fc_cvec<16> {
-  typedef float2 type;  // 9..16 channels: one bin per thread keeps the signal values of both items in registers
+  typedef float2 type;
 };
 
 // Phase 2 of the fused axis kernel: per-bin contraction over the input channels of the group, in place (X -> Y) in
