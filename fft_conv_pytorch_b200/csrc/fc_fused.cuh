@@ -27,6 +27,18 @@ FC_DEV void fc_prefetch_l2(const void*) {}
 FC_DEV void fc_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
 
+// fc_swz2(k0 + KS*it) for k0 < KS with `it` a compile-time constant of an unrolled loop: for KS <= 16 the XOR mask only
+// depends on it.
+template <int KS>
+FC_DEV int fc_swz2_step(int k0, int it) {
+  if constexpr (KS <= 16) {
+    const int h = (KS * it) >> 4;
+    return (k0 + KS * it) ^ ((h & 7) | (((h >> 2) & 1) << 3));
+  } else {
+    return fc_swz2(k0 + KS * it);
+  }
+}
+
 // Powers w[1..R-1] of a twiddle factor with a shallow dependency tree.
 template <int R>
 FC_DEV void fc_twiddle_powers(float2 w1, float2 (&w)[R]) {
@@ -356,10 +368,14 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
     {  // transposed store: thread (l = tid % TR, k = tid / TR + KS j) writes TR consecutive rows of one bin (128 / 256 bytes)
       const int l = tid & (TR - 1);  // tile line l lives at smem + l*LP (see lrow)
       if (r0 + l < R && a.dbg != 2) {
-        float2* dst = a.out + (int64_t)o * p.out_os + r0 + l + (int64_t)(tid / TR + sg * (M + 1)) * p.out_es;
+        const int k0 = (tid / TR) & (KS - 1);
+        float2* dst = a.out + (int64_t)o * p.out_os + r0 + l + (int64_t)(k0 + sg * (M + 1)) * p.out_es;
         const float2* src = smem + l * LP;
         const int64_t dstep = KS * p.out_es;
-        for (int k = tid / TR; k <= M; k += KS, dst += dstep) *dst = src[k < M ? fc_swz2(k) : M];
+        // bin k = k0 + KS*it: unrolled, so the XOR mask of the swizzle (a function of k >> 4) is a constant per step
+#pragma unroll
+        for (int it = 0; it < M / KS; ++it) dst[it * dstep] = src[fc_swz2_step<KS>(k0, it)];
+        if (k0 == 0) dst[(M / KS) * dstep] = src[M];  // the Nyquist bin
       }
     }
     __syncthreads();
