@@ -351,6 +351,94 @@ def test_overlap_save_segments(xs, ws, kw, tr):
         assert rel_err(y.cpu().numpy(), y_one.cpu().numpy()) < 1e-5
 
 
+def _random_2d_case(rng):
+    """A random 2-d problem in the size range where the plan chooses between segmented and unsegmented layouts, fast and
+    generic kernels (odd / even extents and paddings, lattices, groups, channel bounds 8 / 16 / generic)."""
+    tr = bool(rng.randint(2))
+    groups = int(rng.choice([1, 1, 2, 4]))
+    ig, og = int(rng.choice([1, 2, 3, 8, 12, 16, 20])), int(rng.choice([1, 2, 5, 8, 16]))
+    cin, cout = ig * groups, og * groups
+    k = (int(rng.randint(1, 34)), int(rng.randint(1, 34)))
+    dil = (int(rng.choice([1, 1, 1, 2, 3])), int(rng.choice([1, 1, 1, 2, 3])))
+    stride = (int(rng.choice([1, 1, 2, 3])), int(rng.choice([1, 1, 2, 3])))
+    size = (int(rng.randint(120, 1500)), int(rng.randint(120, 1500)))
+    size = tuple(max(s, (kk - 1) * d + 1) for s, kk, d in zip(size, k, dil))
+    kw = dict(stride=stride, dilation=dil, groups=groups)
+    if tr:
+        kw["padding"] = tuple(int(rng.randint(0, min(6, (kk - 1) * d + 1))) for kk, d in zip(k, dil))
+        kw["output_padding"] = tuple(int(rng.randint(0, max(s, d))) for s, d in zip(stride, dil))
+        w_shape = (cin, og) + k
+    else:
+        kw["padding"] = (int(rng.randint(0, 9)), int(rng.randint(0, 9)))
+        w_shape = (cout, ig) + k
+    B = 1 if cin * cout * size[0] * size[1] > 6e7 else int(rng.randint(1, 4))
+    return tr, (B, cin) + size, w_shape, cout, kw
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_2d_problems_match_torch(seed):
+    rng = np.random.RandomState(1000 + seed)
+    tr, xs, ws, cout, kw = _random_2d_case(rng)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(*xs, device="cuda", generator=g)
+    w = torch.randn(*ws, device="cuda", generator=g)
+    b = torch.randn(cout, device="cuda", generator=g)
+    with torch.no_grad():
+        if tr:
+            y = fcp.fft_conv_transpose(x, w, b, **kw)
+            ref = F.conv_transpose2d(x.double(), w.double(), b.double(), **kw)
+        else:
+            y = fcp.fft_conv(x, w, b, **kw)
+            ref = F.conv2d(x.double(), w.double(), b.double(), **kw)
+    assert y.shape == ref.shape, (xs, ws, kw)
+    err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < TOL, (err, tr, xs, ws, kw)
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_random_1d_and_3d_problems_match_torch(seed):
+    """1-d lines up to the four-step layouts (64 x N2 column kernels, fused axis inside the split) and 3-d volumes (row
+    kernels with lane groups, plane kernels), random arguments."""
+    rng = np.random.RandomState(2000 + seed)
+    nd = 1 if seed % 2 == 0 else 3
+    tr = bool(rng.randint(2))
+    groups = int(rng.choice([1, 1, 2, 4]))
+    ig, og = int(rng.choice([1, 2, 3, 8])), int(rng.choice([1, 2, 5, 8]))
+    cin, cout = ig * groups, og * groups
+    if nd == 1:
+        k = (int(rng.choice([1, 3, 17, 64, 129, 1025])),)
+        size = (int(rng.choice([900, 5000, 9000, 20000, 40000, 70000, 150000])) + int(rng.randint(0, 50)),)
+    else:
+        k = tuple(int(rng.randint(1, 8)) for _ in range(3))
+        size = tuple(int(rng.randint(12, 90)) for _ in range(3))
+    dil = tuple(int(rng.choice([1, 1, 2, 3])) for _ in range(nd))
+    stride = tuple(int(rng.choice([1, 1, 2, 3])) for _ in range(nd))
+    size = tuple(max(s, (kk - 1) * d + 1) for s, kk, d in zip(size, k, dil))
+    kw = dict(stride=stride, dilation=dil, groups=groups)
+    if tr:
+        kw["padding"] = tuple(int(rng.randint(0, min(4, (kk - 1) * d + 1))) for kk, d in zip(k, dil))
+        kw["output_padding"] = tuple(int(rng.randint(0, max(s_, d))) for s_, d in zip(stride, dil))
+        ws = (cin, og) + k
+    else:
+        kw["padding"] = tuple(int(rng.randint(0, 5)) for _ in range(nd))
+        ws = (cout, ig) + k
+    B = int(rng.randint(1, 4))
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(B, cin, *size, device="cuda", generator=g)
+    w = torch.randn(*ws, device="cuda", generator=g)
+    b = torch.randn(cout, device="cuda", generator=g)
+    with torch.no_grad():
+        if tr:
+            y = fcp.fft_conv_transpose(x, w, b, **kw)
+            ref = getattr(F, f"conv_transpose{nd}d")(x.double(), w.double(), b.double(), **kw)
+        else:
+            y = fcp.fft_conv(x, w, b, **kw)
+            ref = getattr(F, f"conv{nd}d")(x.double(), w.double(), b.double(), **kw)
+    assert y.shape == ref.shape, (size, ws, kw)
+    err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < TOL, (err, tr, size, ws, kw)
+
+
 # ------------------------------------------------------------------------------------------- backward (SURVEY §8 f1)
 @pytest.mark.parametrize("ndim", [1, 2, 3])
 def test_backward_matches_torch_forward_conv(ndim):
