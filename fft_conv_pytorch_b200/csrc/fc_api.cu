@@ -18,7 +18,32 @@
 #ifdef FC_CPU_EMUL
 #define FC_LAUNCH(kfn, grid, block, smem, stream, arg) fc_emul_launch(grid, block, smem, [=]() { kfn(arg); })
 #else
-#define FC_LAUNCH(kfn, grid, block, smem, stream, arg) kfn<<<grid, block, smem, stream>>>(arg)
+// Every kernel launched here starts with fc_grid_dep_sync() (fc_kernels.cuh), so it may be launched as a programmatic
+// dependent of the kernel before it in the stream: its CTAs become resident while that kernel drains, and the launch
+// latency, CTA start-up and (inside a captured graph) the kernel-boundary drain overlap with the predecessor's tail.
+// FFTCONV_B200_PDL=0 restores plain stream-ordered launches (A/B timing).
+inline bool fc_pdl_enabled() {
+  static const bool on = []() {
+    const char* e = std::getenv("FFTCONV_B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+template <typename K, typename A>
+inline void fc_launch_pdl(K kfn, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const A& arg) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = fc_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kfn, arg);
+}
+#define FC_LAUNCH(kfn, grid, block, smem, stream, arg) fc_launch_pdl(kfn, grid, block, smem, stream, arg)
 #endif
 
 namespace {

@@ -91,6 +91,7 @@ struct fc_col_args {
 // PLAIN: constant padding mode without zero-stuffing / subsampling (the gather is a shift by the padding).
 template <bool PLAIN>
 __global__ void __launch_bounds__(128, 4) fc_col_r2c_kernel(fc_col_args a) {
+  fc_grid_dep_sync();
   constexpr int M = FC_COL_N / 2;
   const fc_pass& p = a.p;
   const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(128, 4) fc_col_r2c_kernel(fc_col_args a) {
 }
 
 __global__ void __launch_bounds__(128) fc_col_c2r_kernel(fc_col_args a) {
+  fc_grid_dep_sync();
   constexpr int M = FC_COL_N / 2;
   const fc_pass& p = a.p;
   const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

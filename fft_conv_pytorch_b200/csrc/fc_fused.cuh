@@ -270,6 +270,7 @@ struct fc_fast_r2c_args {
 // separate transposition tile is needed and M = 512 leaves room for several CTAs per SM.
 template <int M, int NL, int NW, int OCC>
 __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_args a) {
+  fc_grid_dep_sync();
   constexpr int G = M >= 256 ? 32 : M / 8;  // lanes per line (short lines: a group of M/8 lanes, 32/G lines per warp pass)
   constexpr int E = M / G, GPW = 32 / G;
   constexpr int TR = NL * NW * GPW, LP = M + 1, KS = NW * 32 / TR;  // TR lines per tile; KS bins per store sweep
@@ -395,6 +396,7 @@ struct fc_fast_c2r_args {
 // its bins and their Hermitian partners, and the lines then serve as the exchange buffers of the transform.
 template <int M, int NL, int NW, int OCC>
 __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_args a) {
+  fc_grid_dep_sync();
   constexpr int G = M >= 256 ? 32 : M / 8;  // lanes per line (short lines: a group of M/8 lanes, 32/G lines per warp pass)
   constexpr int E = M / G, GPW = 32 / G;
   constexpr int TR = NL * NW * GPW, LP = M + 1, KS = NW * 32 / TR;  // TR lines per tile; KS bins per load sweep
@@ -537,6 +539,7 @@ struct fc_fast_c2c_args {
 // and scale / conjugation on store; inverse passes the crop / stride / lattice map on store.
 template <int N, int NL, int NW, int OCC>
 __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2c_kernel(fc_fast_c2c_args a) {
+  fc_grid_dep_sync();
   constexpr int G = N >= 256 ? 32 : N / 8;  // lanes per line: the whole warp, or a group of N/8 lanes for short lines
   constexpr int E = N / G, GPW = 32 / G;    // points per lane; line groups per warp
   constexpr int LP = G == 32 ? N : N + 2;   // line pitch (short lines: the groups of a warp start on different banks)
@@ -795,6 +798,7 @@ FC_DEV void fc_fused_contract(float2* xy, const fc_fused_args& a, int g, int rk,
 // of bulk-copy stages (84 us), and 16-warp CTAs with NB = 4 whose batch pairs share kernel-spectrum reads (87 us).
 template <int N, int CI, int NB, int W, bool PLAIN, int OCC>
 __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_args a) {
+  fc_grid_dep_sync();
   constexpr int E = N / 32, LS = CI * N;  // line (b, c) at xy + (b*CI + c)*N
   constexpr int NL = NB < 2 ? NB : 2;     // lines per warp = batches per contraction thread
   constexpr int NBG = NB / NL;            // batch groups of a CTA

@@ -18,6 +18,16 @@
 
 #define FC_DEV __device__ __forceinline__
 
+// Programmatic dependent launch: every kernel of the library is launched with the programmatic-stream-serialization
+// attribute (fc_api.cu: FC_LAUNCH), so its CTAs may become resident while the previous kernel of the stream is still
+// draining. The first statement of every kernel lets its own successor do the same and then waits until the
+// predecessor grids have completed and their writes are visible; nothing before it may touch global memory.
+#ifdef FC_CPU_EMUL
+FC_DEV void fc_grid_dep_sync() {}
+#else
+FC_DEV void fc_grid_dep_sync() { asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // ------------------------------------------------------------------------------------------------ complex helpers
 FC_DEV float2 fc_c(float x, float y) { return make_float2(x, y); }
 #if defined(FC_CPU_EMUL) || !defined(FC_PACKED_F32X2)
@@ -221,6 +231,7 @@ struct fc_line_info {
 
 template <int KIND>
 __global__ void fc_pass_kernel(fc_pass_args a) {
+  fc_grid_dep_sync();
   const fc_pass& p = a.p;
   FC_DYN_SMEM(smem);
   float2* bufA = smem;
@@ -539,6 +550,7 @@ struct fc_contract_args {
 
 template <int TB, int TO>
 __global__ void fc_contract_kernel(fc_contract_args a) {
+  fc_grid_dep_sync();
   // blockDim = (bins, output-channel tiles): the tiles of one CTA read the same signal spectrum, which then comes
   // from L1 for all but the first of them
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -597,6 +609,7 @@ __global__ void fc_contract_kernel(fc_contract_args a) {
 // Twiddle tables, evaluated in double precision: tw[j] = exp(-2*pi*i*j/len) for j < len, then (four-step plans)
 // tw[len + b] = exp(-2*pi*i*b/big) for b < len2.
 __global__ void fc_twiddle_kernel(float2* tw, int len, int len2, double big) {
+  fc_grid_dep_sync();
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len + len2; j += gridDim.x * blockDim.x) {
     double s, c;
     if (j < len)

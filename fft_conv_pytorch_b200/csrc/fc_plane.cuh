@@ -31,6 +31,7 @@ struct fc_plane_args {
 // one exchange line of pitch NZ + 2 per line of the column pass.
 template <int NY, int NZ>
 __global__ void __launch_bounds__(FC_PLANE_WARPS * 32, 3) fc_plane_fwd_kernel(fc_plane_args a) {
+  fc_grid_dep_sync();
   constexpr int GY = NY / 8, GZ = NZ / 8, NL = 2, NW = FC_PLANE_WARPS;
   constexpr int GPWY = 32 / GY, GPWZ = 32 / GZ;
   constexpr int PY = NY + 1, PZ = NZ + 2;
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(FC_PLANE_WARPS * 32, 3) fc_plane_fwd_kernel(fc
 // Shared memory: the plane, NY rows (ky) of pitch NZ + 1, then one exchange line of pitch NY + 2 per column-pass line.
 template <int NY, int NZ>
 __global__ void __launch_bounds__(FC_PLANE_WARPS * 32, 3) fc_plane_inv_kernel(fc_plane_args a) {
+  fc_grid_dep_sync();
   constexpr int GY = NY / 8, GZ = NZ / 8, NL = 2, NW = FC_PLANE_WARPS;
   constexpr int GPWY = 32 / GY, GPWZ = 32 / GZ;
   constexpr int PZ = NZ + 1, PY = NY + 2;

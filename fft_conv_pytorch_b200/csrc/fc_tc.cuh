@@ -49,6 +49,7 @@ struct fc_tc_relayout_args {
 };
 
 __global__ void fc_tc_relayout_kernel(fc_tc_relayout_args a) {
+  fc_grid_dep_sync();
   __shared__ float2 tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
   const int64_t f0 = (int64_t)blockIdx.x * 32;
