@@ -384,6 +384,21 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
 }
 
 // ------------------------------------------------------------------------------------------------ K4
+// y[j] = b for j in [j_lo, j_hi), by the G lanes of a group (lane gl): 16-byte stores between an unaligned head and tail.
+template <int G>
+FC_DEV void fc_fill_run(float* y, int j_lo, int j_hi, float b, int gl) {
+  if (j_lo >= j_hi) return;
+  int head = (int)((4 - ((reinterpret_cast<uintptr_t>(y + j_lo) >> 2) & 3)) & 3);
+  if (head > j_hi - j_lo) head = j_hi - j_lo;
+  const int ja = j_lo + head, nq = (j_hi - ja) >> 2, jt = ja + 4 * nq;
+  float4* y4 = reinterpret_cast<float4*>(y + ja);
+  const float4 b4 = make_float4(b, b, b, b);
+#pragma unroll 4
+  for (int m = gl; m < nq; m += G) y4[m] = b4;
+  if (gl < head) y[j_lo + gl] = b;
+  if (gl < j_hi - jt) y[jt + gl] = b;  // G >= 4 lanes
+}
+
 struct fc_fast_c2r_args {
   fc_pass p;
   const float2* in;
@@ -505,8 +520,31 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
           if (jr < 0 || jr >= p.row_Lout) continue;
           float* yrow = a.out + o * p.out_os + jr * p.out_rs;
           if (er != 0) {  // a row between the lattice rows: bias only
-#pragma unroll 8
-            for (int j = j_lo + gl; j < j_hi; j += G) yrow[j] = b;
+            fc_fill_run<G>(yrow, j_lo, j_hi, b, gl);
+            continue;
+          }
+          if (om.og == 2 && om.os == 1 && om.ob >= 0) {
+            // lattice of 2 (BASELINE c5: stride 2, dilation 2): of every aligned output pair exactly one is a dense
+            // sample, the other is bias only -> one shared-memory read and one 8-byte store per two outputs
+            const int mis = (int)((reinterpret_cast<uintptr_t>(yrow + j_lo) >> 2) & 1);
+            const int ja = j_lo + mis < j_hi ? j_lo + mis : j_hi;
+            const int npairs = (j_hi - ja) >> 1;
+            const int par = (ja + om.ob) & 1;          // 0: the first output of a pair is the dense sample, 1: the second
+            const int nb = (ja + om.ob + par) >> 1;    // dense index of the sample of pair 0
+            float2* y2 = reinterpret_cast<float2*>(yrow + ja);
+#pragma unroll 4
+            for (int m = gl; m < npairs; m += G) {
+              const int n = nb + m;
+              const float v = (n < om.lim ? rl[n] : 0.f) + b;
+              y2[m] = par ? make_float2(b, v) : make_float2(v, b);
+            }
+            if (gl < 2) {  // the unaligned first and the odd last output of the run
+              const int j = gl == 0 ? j_lo : ja + 2 * npairs;
+              if (gl == 0 ? (mis && j_lo < j_hi) : j < j_hi) {
+                const int tt = j + om.ob, n = tt >> 1;
+                yrow[j] = ((tt & 1) == 0 && n < om.lim ? rl[n] : 0.f) + b;
+              }
+            }
             continue;
           }
           // output-driven (coalesced stores): output j takes dense sample n = (j*os + ob) / og when the remainder
