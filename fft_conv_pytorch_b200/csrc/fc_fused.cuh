@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
 #pragma unroll
           for (int q = 0; q < E; ++q) {
             const int n0 = 2 * (gl + G * q);
-            if (n0 < om.Lout) *reinterpret_cast<float2*>(yrow + n0) = make_float2(v[l][q].x + b, -v[l][q].y + b);
+            if (n0 < om.Lout) fc_st_stream(reinterpret_cast<float2*>(yrow + n0), make_float2(v[l][q].x + b, -v[l][q].y + b));
           }
         }
       }
@@ -894,7 +894,7 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
 #pragma unroll
           for (int q = 0; q < E; ++q) {
             const int n = lane + 32 * q;
-            v[bl][q] = active ? __ldg(src + n) : make_float2(0.f, 0.f);
+            v[bl][q] = active ? fc_ld_stream(src + n) : make_float2(0.f, 0.f);
           }
         } else if (simple_in) {
           const int ub = sg * a.seg_V - a.seg_off + lane;

@@ -28,6 +28,21 @@ FC_DEV void fc_grid_dep_sync() {}
 FC_DEV void fc_grid_dep_sync() { asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory"); }
 #endif
 
+// Streaming accesses: data that is read or written exactly once by the pipeline (the real input, a spectrum on its way
+// out of L2, the final output) is moved with the evict-first policy so that it does not push the spectra the next kernel
+// is about to read out of the 126 MB L2.
+#if defined(FC_CPU_EMUL) || defined(FC_NO_STREAM_HINTS)
+template <typename T>
+FC_DEV T fc_ld_stream(const T* p) { return __ldg(p); }
+template <typename T>
+FC_DEV void fc_st_stream(T* p, T v) { *p = v; }
+#else
+template <typename T>
+FC_DEV T fc_ld_stream(const T* p) { return __ldcs(p); }
+template <typename T>
+FC_DEV void fc_st_stream(T* p, T v) { __stcs(p, v); }
+#endif
+
 // ------------------------------------------------------------------------------------------------ complex helpers
 FC_DEV float2 fc_c(float x, float y) { return make_float2(x, y); }
 #if defined(FC_CPU_EMUL) || !defined(FC_PACKED_F32X2)
