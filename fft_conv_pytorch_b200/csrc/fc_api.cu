@@ -490,7 +490,15 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
     a.prefetch_dist = (int)(g_num_sms * per_sm);
   }
   int64_t grid = a.n_units;
-  const int64_t cap = (int64_t)g_num_sms * 16;
+  int64_t cap = (int64_t)g_num_sms * 16;
+  {  // A/B timing knob: "pgrid=K" in FFTCONV_B200_TUNE caps the grid at K CTAs per SM (persistent CTAs looping over units)
+    static const int pgrid = []() {
+      const char* t = std::getenv("FFTCONV_B200_TUNE");
+      const char* q = t ? std::strstr(t, "pgrid=") : nullptr;
+      return q ? std::atoi(q + 6) : 0;
+    }();
+    if (pgrid > 0) cap = (int64_t)g_num_sms * pgrid;
+  }
   if (grid > cap) grid = cap;
   dim3 g((unsigned)grid), b((unsigned)f.warps * 32);
   bool ok = false;

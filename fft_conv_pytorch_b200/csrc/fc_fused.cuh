@@ -268,6 +268,22 @@ struct fc_fast_r2c_args {
 // holds the untangled half spectrum (bin k at the swizzled slot of k, the Nyquist bin in the extra slot M); the odd
 // pitch makes the transposed read of the store phase (16 rows of one bin per half warp) bank-conflict free, so no
 // separate transposition tile is needed and M = 512 leaves room for several CTAs per SM.
+// First tile line of the NL lines owned by group gid (G lanes) of warp w in K1 / K4. Tile lines are M + 1 float2 apart
+// (odd pitch: the transposed sweeps are conflict-free), so consecutive lines start 2 banks apart. The 16/G groups of a
+// half warp share a shared-memory wavefront and each touches a window of G float2 (2G banks) of its line: giving them
+// lines G apart puts the windows on disjoint banks (adjacent line pairs, the plain assignment, overlap them 2- to
+// 4-way: ncu counted 2-3 wavefronts per ideal one in the M = 32 engine of BASELINE c3).
+template <int G, int NL>
+FC_DEV int fc_group_row(int w, int gid) {
+  if constexpr (G >= 16 || NL != 2) {
+    return (w * (32 / G) + gid) * NL;
+  } else {
+    constexpr int Q = 16 / G;  // groups per half warp
+    const int j = gid % Q, h = gid / Q, rho = (2 * w + h) * NL;
+    return 16 * (rho / G) + j * G + rho % G;
+  }
+}
+
 template <int M, int NL, int NW, int OCC>
 __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_args a) {
   fc_grid_dep_sync();
@@ -279,7 +295,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
   FC_DYN_SMEM(smem);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int gl = lane % G, gid = lane / G;
-  const int lrow = (w * GPW + gid) * NL;  // first tile line of this lane's group
+  const int lrow = fc_group_row<G, NL>(w, gid);  // first tile line of this lane's group
   float2* line0 = smem + lrow * LP;
   const int L = p.imap.L;
   const int tstep = p.tw_len / (2 * M);
@@ -420,7 +436,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
   FC_DYN_SMEM(smem);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int gl = lane % G, gid = lane / G;
-  const int lrow = (w * GPW + gid) * NL;  // first tile line of this lane's group
+  const int lrow = fc_group_row<G, NL>(w, gid);  // first tile line of this lane's group
   float2* line0 = smem + lrow * LP;
   const int tstep = p.tw_len / (2 * M);
   const fc_omap om = p.omap;
