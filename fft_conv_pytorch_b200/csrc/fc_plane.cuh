@@ -27,6 +27,22 @@ struct fc_plane_args {
 
 #define FC_PLANE_WARPS 8
 
+// Exchange line (pitch N + 2 float2 = 4 banks per line) of group gid inside its warp's block of 32/G * NL lines: the
+// two groups of a half warp (G = 8) get lines 4 apart, i.e. 16 banks, so that their 8-element windows are disjoint
+// (adjacent line pairs, 8 banks apart, overlap). G = 4 and G = 16 are conflict-free with adjacent pairs.
+template <int G, int NL>
+FC_DEV int fc_plane_scratch_line(int gid) {
+  if constexpr (G == 8 && NL == 2) return (gid & 1) * 4 + (gid >> 1) * 2;
+  else return gid * NL;
+}
+// Plane line (pitch N + 1) of group gid of warp w in a pass whose NW * 32/G * NL lines are exactly the plane's: the
+// bank-disjoint assignment of K1 / K4 (fc_group_row); otherwise the plain one (z0 = first line of this warp pass).
+template <int G, int NL, int LINES>
+FC_DEV int fc_plane_line(int w, int gid, int z0) {
+  if constexpr (LINES == FC_PLANE_WARPS * (32 / G) * NL) return fc_group_row<G, NL>(w, gid);
+  else return z0 + gid * NL;
+}
+
 // Shared memory: the plane, NZ rows of pitch NY + 1 (the rows double as the exchange buffers of the row pass), then
 // one exchange line of pitch NZ + 2 per line of the column pass.
 template <int NY, int NZ>
@@ -49,7 +65,7 @@ __global__ void __launch_bounds__(FC_PLANE_WARPS * 32, 3) fc_plane_fwd_kernel(fc
     const float2* src = a.in + o * a.in_os + (int64_t)kx * Lz * Ly;
     // ---- rows: transform along y (warp-uniform loop; NZ is a multiple of the rows a warp takes)
     for (int z0 = w * GPWY * NL; z0 < NZ; z0 += NW * GPWY * NL) {
-      const int zr0 = z0 + gidy * NL;
+      const int zr0 = fc_plane_line<GY, NL, NZ>(w, gidy, z0);
       float2 v[NL][8];
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
@@ -72,13 +88,13 @@ __global__ void __launch_bounds__(FC_PLANE_WARPS * 32, 3) fc_plane_fwd_kernel(fc
     __syncthreads();
     // ---- columns: transform along z, store [ky][kx][kz]
     for (int c0 = w * GPWZ * NL; c0 < NY; c0 += NW * GPWZ * NL) {
-      const int ky0 = c0 + gidz * NL;
+      const int ky0 = fc_plane_line<GZ, NL, NY>(w, gidz, c0);
       float2 v[NL][8];
 #pragma unroll
       for (int l = 0; l < NL; ++l)
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[l][q] = plane[(glz + GZ * q) * PY + ky0 + l];
-      float2* line0 = scratch + (size_t)((w * GPWZ + gidz) * NL) * PZ;
+      float2* line0 = scratch + (size_t)(w * GPWZ * NL + fc_plane_scratch_line<GZ, NL>(gidz)) * PZ;
       fc_gfft<NZ, GZ, NL, PZ>(v, line0, a.tw, a.tw_len, glz);
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
@@ -116,7 +132,7 @@ __global__ void __launch_bounds__(FC_PLANE_WARPS * 32, 3) fc_plane_inv_kernel(fc
     const float2* src = a.in + o * a.in_os + (int64_t)kx * NZ;
     // ---- rows (one per ky, kz contiguous): inverse transform along z (forward engine on conjugated data)
     for (int r0 = w * GPWZ * NL; r0 < NY; r0 += NW * GPWZ * NL) {
-      const int ky0 = r0 + gidz * NL;
+      const int ky0 = fc_plane_line<GZ, NL, NY>(w, gidz, r0);
       float2 v[NL][8];
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
@@ -134,8 +150,9 @@ __global__ void __launch_bounds__(FC_PLANE_WARPS * 32, 3) fc_plane_inv_kernel(fc
     __syncthreads();
     // ---- columns (one per kept z): inverse transform along y, crop, store [kx][jz][jy]
     float2* dst0 = a.out + o * a.out_os + (int64_t)kx * Oz * Oy;
-    for (int c0 = w * GPWY * NL; c0 < Oz; c0 += NW * GPWY * NL) {  // warp-uniform; columns past Oz idle along
-      const int jz0 = c0 + gidy * NL;
+    for (int c0 = w * GPWY * NL; c0 < NZ; c0 += NW * GPWY * NL) {  // warp-uniform; columns past Oz idle along
+      if (fc_plane_line<GY, NL, NZ>(w, 0, c0) >= Oz) break;  // (group 0 owns the warp's first column)
+      const int jz0 = fc_plane_line<GY, NL, NZ>(w, gidy, c0);
       float2 v[NL][8];
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
@@ -144,7 +161,7 @@ __global__ void __launch_bounds__(FC_PLANE_WARPS * 32, 3) fc_plane_inv_kernel(fc
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[l][q] = ok ? plane[(gly + GY * q) * PZ + n] : make_float2(0.f, 0.f);
       }
-      float2* line0 = scratch + (size_t)((w * GPWY + gidy) * NL) * PY;
+      float2* line0 = scratch + (size_t)(w * GPWY * NL + fc_plane_scratch_line<GY, NL>(gidy)) * PY;
       fc_gfft<NY, GY, NL, PY>(v, line0, a.tw, a.tw_len, gly);  // conj(conj(.)) = the inverse along both axes
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
