@@ -240,14 +240,22 @@ int launch_contract(const float2* X, const float2* K, float2* Y, int64_t bins, i
     // tile reads it once per thread and two output tiles per CTA share the signal spectrum through L1
     a.btiles = 1;
     a.otiles = (Og + 7) / 8;
-    const int oy = a.otiles >= 2 ? 2 : 1, bx = oy == 2 ? 32 : 128;
+    const int oy = a.otiles >= 2 ? 2 : 1, bx = oy == 2 ? 32 : 64;  // (64-thread CTAs: c3 35.5 -> 34.8 us against 128)
     dim3 b(bx, oy), g((unsigned)((bins + bx - 1) / bx), (unsigned)((a.otiles + oy - 1) / oy), (unsigned)groups);
     auto k = fc_contract_kernel<4, 8>;
     FC_LAUNCH(k, g, b, 0, st, a);
   } else {
     const int threads = 128;
     const unsigned gx = (unsigned)((bins + threads - 1) / threads);
-    if (batch >= 5 && Og >= 5) {
+    if (batch >= 5 && batch <= 64 && Og >= 5) {
+      // medium batch: 4 x 8 tiles (half the accumulators of 8 x 8, twice the resident warps; the kernel spectrum is
+      // re-read per batch tile from L1 / L2): (32,8,128,128) k15 18.5 -> 16.4 us
+      a.btiles = (batch + 3) / 4;
+      a.otiles = (Og + 7) / 8;
+      dim3 g((unsigned)((bins + 63) / 64), (unsigned)(a.btiles * a.otiles), (unsigned)groups), b(64);
+      auto k = fc_contract_kernel<4, 8>;
+      FC_LAUNCH(k, g, b, 0, st, a);
+    } else if (batch >= 5 && Og >= 5) {
       a.btiles = (batch + 7) / 8;
       a.otiles = (Og + 7) / 8;
       dim3 g(gx, (unsigned)(a.btiles * a.otiles), (unsigned)groups), b(threads);

@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-for t in "8,8,128,1" "8,8,32,4" "8,8,32,8" "16,4,32,4" "16,2,32,8" "16,2,64,4" "4,4,32,8"; do
-  FFTCONV_B200_CTILE="$t" timeout 300 python scripts/time_configs.py c4 2>&1 | grep -o '"kernel": "contract", "ms": [0-9.]*' | sed "s/^/$t  /" >> gpurun_out/ctile.log
+for t in "" "4,4,128,1" "4,4,64,2" "4,8,64,1" "4,8,32,1" "4,8,256,1" "4,4,32,2" "8,8,128,1" "8,8,64,1" "16,4,128,1" "16,2,128,1" "16,4,64,1"; do
+  if [ -n "$t" ]; then export FFTCONV_B200_CTILE="$t"; else unset FFTCONV_B200_CTILE; fi
+  echo "VARIANT [$t]" >> gpurun_out/ctile.log
+  timeout 300 python scripts/time_configs.py c3 img128 >> gpurun_out/ctile.log 2>&1
 done
