@@ -19,6 +19,7 @@ FC_FLAG_NO_FUSED_MID = 16
 FC_FLAG_NO_TC = 32
 FC_FLAG_NO_FAST_C2C = 64
 FC_FLAG_NO_SEGMENT = 128
+FC_FLAG_NO_PAIR = 256
 
 _I3 = ctypes.c_int32 * FC_MAX_ND
 

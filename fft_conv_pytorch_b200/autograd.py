@@ -75,6 +75,7 @@ class _FFTConvFn(torch.autograd.Function):
         return _raw_conv(transposed, x, w, b, stride, padding, opad, dilation, groups)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable  # the adjoints run on the opaque kernels: no double backward
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         transposed, stride, padding, opad, dilation, groups, has_bias = ctx.cfg

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfftconv_b200.so")
 SOURCES = ["fc_api.cu", "fc_plan.cpp"]
-DEPS = ["fc_api.cu", "fc_plan.cpp", "fc_plan.h", "fc_types.h", "fc_kernels.cuh", "fc_fused.cuh", "fc_column.cuh", "fc_plane.cuh", "fc_async.cuh", "fc_tc.cuh", os.path.join("..", "..", "include", "fftconv_b200.h")]
+DEPS = ["fc_api.cu", "fc_plan.cpp", "fc_plan.h", "fc_types.h", "fc_kernels.cuh", "fc_fused.cuh", "fc_pair.cuh", "fc_column.cuh", "fc_plane.cuh", "fc_tune.h", "fc_tc.cuh", os.path.join("..", "..", "include", "fftconv_b200.h")]
 
 
 def _nvcc() -> str:
@@ -46,6 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd += ["-ccbin", "/usr/bin/g++"]
     if os.environ.get("FFTCONV_B200_PACKED", "1") != "0":
         cmd += ["-DFC_PACKED_F32X2"]  # FADD2 for complex add/sub (sm_100a packed fp32)
+    if os.environ.get("FFTCONV_B200_TUNING", "0") == "1":
+        cmd += ["-DFC_TUNING"]  # development build: timing-experiment knobs read from the environment (csrc/fc_tune.h)
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]

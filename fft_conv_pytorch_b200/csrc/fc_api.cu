@@ -10,10 +10,12 @@
 
 #include "fc_kernels.cuh"
 #include "fc_fused.cuh"
+#include "fc_pair.cuh"
 #include "fc_column.cuh"
 #include "fc_plane.cuh"
 #include "fc_tc.cuh"
 #include "fc_plan.h"
+#include "fc_tune.h"
 
 #ifdef FC_CPU_EMUL
 #define FC_LAUNCH(kfn, grid, block, smem, stream, arg) fc_emul_launch(grid, block, smem, [=]() { kfn(arg); })
@@ -21,12 +23,9 @@
 // Every kernel launched here starts with fc_grid_dep_sync() (fc_kernels.cuh), so it may be launched as a programmatic
 // dependent of the kernel before it in the stream: its CTAs become resident while that kernel drains, and the launch
 // latency, CTA start-up and (inside a captured graph) the kernel-boundary drain overlap with the predecessor's tail.
-// FFTCONV_B200_PDL=0 restores plain stream-ordered launches (A/B timing).
+// (Tuning builds: PDL=0 restores plain stream-ordered launches for A/B timing.)
 inline bool fc_pdl_enabled() {
-  static const bool on = []() {
-    const char* e = std::getenv("FFTCONV_B200_PDL");
-    return !(e && e[0] == '0');
-  }();
+  static const bool on = fc_tune_int("PDL", 1) != 0;
   return on;
 }
 template <typename K, typename A>
@@ -83,7 +82,7 @@ const int kMaxSmem = 200 * 1024;
 const char* const kSegMsg =
     "this plan splits the first axis into overlap-save segments and runs through fc_conv only; create the plan with FC_FLAG_NO_SEGMENT "
     "for the stage calls";
-int g_num_sms = 148;
+thread_local int g_num_sms = 148;  // SM count of the calling thread's current device (set by init_once)
 
 // every instantiation of the fused kernel: (N, CI, NB, warps, plain, CTAs per SM)
 #define FC_FUSED_ALL(X) \
@@ -106,6 +105,14 @@ int g_num_sms = 148;
 // ... and of the two-axis plane kernels: X(NY, NZ).
 #define FC_PLANE_ALL(X) X(32, 32) X(32, 64) X(64, 32) X(64, 64)
 
+// ... of the pair pipeline (fc_pair.cuh). K1p / K4p: X(M, pair lines per warp group, warps, CTAs per SM);
+// KBp: X(N, channels per group, pair items per CTA, warps, plain, CTAs per SM).
+#define FC_PAIR_ROW_ALL(X) X(128, 1, 8, 4) X(128, 2, 8, 2) X(256, 1, 8, 4) X(256, 2, 8, 2) X(512, 1, 8, 2) X(1024, 1, 8, 1)
+#define FC_PAIR_FUSED_ALL(X) \
+  X(256, 8, 2, 8, true, 2) X(256, 8, 2, 8, false, 2) X(256, 8, 1, 8, true, 2) X(256, 8, 1, 8, false, 2) \
+  X(512, 8, 1, 8, true, 2) X(512, 8, 1, 8, false, 2) X(1024, 8, 1, 8, true, 1) X(1024, 8, 1, 8, false, 1) \
+  X(256, 16, 1, 8, true, 2) X(256, 16, 1, 8, false, 2) X(512, 16, 1, 8, true, 1) X(512, 16, 1, 8, false, 1)
+
 void fused_set_attr() {
 #ifndef FC_CPU_EMUL
 #define FC_FUSED_ATTR(NN, CC, NBB, WW, PL, OC) \
@@ -115,37 +122,58 @@ void fused_set_attr() {
 #endif
 }
 
+// Per-device one-time setup: the opt-in to > 48 KB of dynamic shared memory is a property of the function *in the
+// current device's context*, and the SM count differs between devices; a process that drives several GPUs runs this
+// once per device.
 void init_once() {
-  static std::once_flag flag;
-  std::call_once(flag, []() {
-#ifndef FC_CPU_EMUL
-    cudaFuncSetAttribute(fc_pass_kernel<FC_R2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(fc_pass_kernel<FC_C2C_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(fc_pass_kernel<FC_C2C_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(fc_pass_kernel<FC_C2R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-      g_num_sms = sms;
+#ifdef FC_CPU_EMUL
+  return;
+#else
+  static std::mutex m;
+  static int sms_of[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  std::lock_guard<std::mutex> lock(m);
+  if (sms_of[dev] > 0) {
+    g_num_sms = sms_of[dev];
+    return;
+  }
+  cudaFuncSetAttribute(fc_pass_kernel<FC_R2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  cudaFuncSetAttribute(fc_pass_kernel<FC_C2C_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  cudaFuncSetAttribute(fc_pass_kernel<FC_C2C_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  cudaFuncSetAttribute(fc_pass_kernel<FC_C2R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
 #define FC_FAST_ATTR(MM, NLL, NWW, OC)                                                                                   \
   cudaFuncSetAttribute(fc_fast_r2c_kernel<MM, NLL, NWW, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); \
   cudaFuncSetAttribute(fc_fast_c2r_kernel<MM, NLL, NWW, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    FC_FAST_ALL(FC_FAST_ATTR)
+  FC_FAST_ALL(FC_FAST_ATTR)
 #undef FC_FAST_ATTR
 #define FC_FAST_C2C_ATTR(NN, NLL, NWW, OC) \
   cudaFuncSetAttribute(fc_fast_c2c_kernel<NN, NLL, NWW, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    FC_FAST_C2C_ALL(FC_FAST_C2C_ATTR)
+  FC_FAST_C2C_ALL(FC_FAST_C2C_ATTR)
 #undef FC_FAST_C2C_ATTR
 #define FC_PLANE_ATTR(NY, NZ)                                                                                  \
   cudaFuncSetAttribute(fc_plane_fwd_kernel<NY, NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); \
   cudaFuncSetAttribute(fc_plane_inv_kernel<NY, NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    FC_PLANE_ALL(FC_PLANE_ATTR)
+  FC_PLANE_ALL(FC_PLANE_ATTR)
 #undef FC_PLANE_ATTR
-    fused_set_attr();
-    cudaFuncSetAttribute(fc_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    cudaFuncSetAttribute(fc_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    cudaGetLastError();
+#define FC_PAIR_ROW_ATTR(MM, NLL, NWW, OC)                                                                               \
+  cudaFuncSetAttribute(fc_pair_r2c_kernel<MM, NLL, NWW, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); \
+  cudaFuncSetAttribute(fc_pair_c2r_kernel<MM, NLL, NWW, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  FC_PAIR_ROW_ALL(FC_PAIR_ROW_ATTR)
+#undef FC_PAIR_ROW_ATTR
+#define FC_PAIR_FUSED_ATTR(NN, CC, NPP, WW, PL, OC) \
+  cudaFuncSetAttribute(fc_pair_fused_kernel<NN, CC, NPP, WW, PL, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  FC_PAIR_FUSED_ALL(FC_PAIR_FUSED_ATTR)
+#undef FC_PAIR_FUSED_ATTR
+  fused_set_attr();
+  cudaFuncSetAttribute(fc_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+  cudaFuncSetAttribute(fc_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+  cudaGetLastError();
+  sms_of[dev] = sms;
+  g_num_sms = sms;
 #endif
-  });
 }
 
 int launch_pass(const fc_plan* pl, const fc_pass& p, const void* in, void* out, const float2* tw, const float* bias, cudaStream_t st) {
@@ -204,7 +232,7 @@ int launch_contract(const float2* X, const float2* K, float2* Y, int64_t bins, i
   a.cout = cout;
   a.groups = groups;
   const int Og = cout / groups;
-  static const char* ctile = std::getenv("FFTCONV_B200_CTILE");  // timing experiments: "tb,to,bx,by"
+  static const char* ctile = fc_tune_str("CTILE");  // timing experiments: "tb,to,bx,by"
   if (ctile) {
     int tb = 8, to = 8, bx = 128, by = 1;
     std::sscanf(ctile, "%d,%d,%d,%d", &tb, &to, &bx, &by);
@@ -286,7 +314,7 @@ struct fast_cfg {
 };
 fast_cfg fast_config(int M) {
   fast_cfg c = M <= 256 ? fast_cfg{2, 8, 4} : M == 512 ? fast_cfg{2, 8, 2} : fast_cfg{1, 16, 1};
-  static const char* env = std::getenv("FFTCONV_B200_FAST");
+  static const char* env = fc_tune_str("FAST");
   if (env) {
     fast_cfg e = c;
     std::sscanf(env, "%d,%d,%d", &e.nl, &e.nw, &e.occ);
@@ -313,10 +341,6 @@ int launch_fast_r2c(const fc_pass& p, const void* in, void* out, const float2* t
   a.x = (const float*)in;
   a.out = (float2*)out;
   a.tw = tw;
-  {
-    static const int dbg = std::getenv("FFTCONV_B200_DBG") ? std::atoi(std::getenv("FFTCONV_B200_DBG")) : 0;
-    a.dbg = dbg;
-  }
   const fast_cfg c = fast_config(p.M);
   const size_t smem = (size_t)p.T * (p.M + 1) * sizeof(float2);
   const int64_t grid = fast_grid(p, c, smem);
@@ -501,7 +525,7 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
   int64_t cap = (int64_t)g_num_sms * 16;
   {  // A/B timing knob: "pgrid=K" in FFTCONV_B200_TUNE caps the grid at K CTAs per SM (persistent CTAs looping over units)
     static const int pgrid = []() {
-      const char* t = std::getenv("FFTCONV_B200_TUNE");
+      const char* t = fc_tune_str("TUNE");
       const char* q = t ? std::strstr(t, "pgrid=") : nullptr;
       return q ? std::atoi(q + 6) : 0;
     }();
@@ -521,6 +545,149 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
   if (!ok) return set_err(FC_EUNSUPPORTED, "no fused kernel instantiation for this shape");
   rec_mark();
   return check_cuda("fused axis launch");
+}
+
+// ---- pair pipeline (fc_pair.cuh)
+// Variant of K1p / K4p for a line length: (pair lines per warp group, CTAs per SM); 8 warps per CTA. The plan's tiling
+// (fc_pair_tile_lines) is recomputed here for the variant actually launched.
+struct pair_row_cfg {
+  int nlp, occ;
+};
+pair_row_cfg pair_row_config(int M) {
+  pair_row_cfg c = M <= 256 ? pair_row_cfg{1, 4} : M == 512 ? pair_row_cfg{1, 2} : pair_row_cfg{1, 1};
+  static const char* env = fc_tune_str("PAIRROW");  // tuning builds: "nlp,occ"
+  if (env) {
+    pair_row_cfg e = c;
+    std::sscanf(env, "%d,%d", &e.nlp, &e.occ);
+    bool known = false;
+#define FC_PAIR_KNOWN(MM, NLL, NWW, OC) known = known || (M == MM && e.nlp == NLL && e.occ == OC);
+    FC_PAIR_ROW_ALL(FC_PAIR_KNOWN)
+#undef FC_PAIR_KNOWN
+    if (known) c = e;
+  }
+  return c;
+}
+void pair_retile(fc_pass& p, int nlp) {
+  const int T = nlp * 8 * (p.M >= 256 ? 1 : 256 / p.M);
+  p.T = T;
+  p.tiles_per_outer = (p.R + T - 1) / T * p.seg_n;
+  p.n_tiles = p.tiles_per_outer * p.n_outer;
+}
+
+int launch_pair_r2c(const fc_plan* pl, const fc_pass& p, const void* in, void* out, const float2* tw, cudaStream_t st) {
+  fc_pair_r2c_args a;
+  a.p = p;
+  a.x = (const float*)in;
+  a.out = (fc_c2*)out;
+  a.tw = tw;
+  a.B = pl->prob.batch;
+  a.C = pl->prob.cin;
+  const pair_row_cfg c = pair_row_config(p.M);
+  pair_retile(a.p, c.nlp);
+  if (a.p.n_tiles < 1) return FC_OK;
+  const size_t smem = (size_t)a.p.T * (p.M + 1) * sizeof(fc_c2);
+  bool done = false;
+#define FC_PAIR_LAUNCH(MM, NLL, NWW, OC)                                         \
+  if (!done && p.M == MM && c.nlp == NLL && c.occ == OC) {                       \
+    int64_t per_sm = (int64_t)(224 * 1024) / (int64_t)(smem + 1024);            \
+    if (per_sm > OC) per_sm = OC;                                                \
+    if (per_sm < 1) per_sm = 1;                                                  \
+    int64_t grid = (int64_t)g_num_sms * per_sm;                                  \
+    if (grid > a.p.n_tiles) grid = a.p.n_tiles;                                  \
+    dim3 g((unsigned)grid), b(NWW * 32);                                         \
+    auto k = fc_pair_r2c_kernel<MM, NLL, NWW, OC>;                               \
+    FC_LAUNCH(k, g, b, smem, st, a);                                             \
+    done = true;                                                                 \
+  }
+  FC_PAIR_ROW_ALL(FC_PAIR_LAUNCH)
+#undef FC_PAIR_LAUNCH
+  if (!done) return set_err(FC_EUNSUPPORTED, "no pair R2C kernel for this line length");
+  rec_mark();
+  return check_cuda("pair r2c launch");
+}
+
+int launch_pair_c2r(const fc_plan* pl, const fc_pass& p, const void* in, void* out, const float2* tw, const float* bias, cudaStream_t st) {
+  fc_pair_c2r_args a;
+  a.p = p;
+  a.p.has_bias = bias ? 1 : 0;
+  a.in = (const fc_c2*)in;
+  a.out = (float*)out;
+  a.tw = tw;
+  a.bias = bias;
+  a.B = pl->prob.batch;
+  a.C = pl->prob.cout;
+  const pair_row_cfg c = pair_row_config(p.M);
+  pair_retile(a.p, c.nlp);
+  if (a.p.n_tiles < 1) return FC_OK;
+  const size_t smem = (size_t)a.p.T * (p.M + 1) * sizeof(fc_c2);
+  bool done = false;
+#define FC_PAIR_LAUNCH(MM, NLL, NWW, OC)                                         \
+  if (!done && p.M == MM && c.nlp == NLL && c.occ == OC) {                       \
+    int64_t per_sm = (int64_t)(224 * 1024) / (int64_t)(smem + 1024);            \
+    if (per_sm > OC) per_sm = OC;                                                \
+    if (per_sm < 1) per_sm = 1;                                                  \
+    int64_t grid = (int64_t)g_num_sms * per_sm;                                  \
+    if (grid > a.p.n_tiles) grid = a.p.n_tiles;                                  \
+    dim3 g((unsigned)grid), b(NWW * 32);                                         \
+    auto k = fc_pair_c2r_kernel<MM, NLL, NWW, OC>;                               \
+    FC_LAUNCH(k, g, b, smem, st, a);                                             \
+    done = true;                                                                 \
+  }
+  FC_PAIR_ROW_ALL(FC_PAIR_LAUNCH)
+#undef FC_PAIR_LAUNCH
+  if (!done) return set_err(FC_EUNSUPPORTED, "no pair C2R kernel for this line length");
+  rec_mark();
+  return check_cuda("pair c2r launch");
+}
+
+int launch_pair_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, const float2* kspec, void* out, const float2* tw, cudaStream_t st) {
+  const fc_problem& P = pl->prob;
+  fc_pair_fused_args a;
+  a.xin = (const fc_c2*)in;
+  a.kspec = kspec;
+  a.yout = (fc_c2*)out;
+  a.tw = tw;
+  a.tw_len = pl->tw_len;
+  a.BP = (P.batch + 1) / 2;
+  a.Cin = P.cin;
+  a.Cout = P.cout;
+  a.G = P.groups;
+  a.n_in = f.n_in;
+  a.n_out = f.n_out;
+  a.n_seg = f.n_seg > 1 ? f.n_seg : 1;
+  a.seg_V = f.n_seg > 1 ? f.seg_V : f.N;
+  a.seg_off = f.n_seg > 1 ? f.seg_off : 0;
+  a.n_items = a.BP * a.n_seg;
+  a.nbs = (a.n_items + f.nb - 1) / f.nb;
+  a.R = f.R;
+  a.Rk = f.Rk > 0 ? f.Rk : f.R;
+  a.n_units = (int64_t)P.groups * f.R * a.nbs;
+  a.imap = f.imap;
+  a.omap = f.omap;
+  const size_t smem = (size_t)f.nb * f.ci * f.N * sizeof(fc_c2);
+  {  // distance (in units) to the CTA of the next wave on the same SM: what this CTA prefetches into L2
+    int64_t per_sm = (int64_t)(228 * 1024) / (int64_t)(smem + 1024 + 256);
+    if (per_sm > f.occ) per_sm = f.occ;
+    if (per_sm < 1) per_sm = 1;
+    a.prefetch_dist = (int)(g_num_sms * per_sm);
+  }
+  int64_t grid = a.n_units;
+  const int64_t cap = (int64_t)g_num_sms * 16;
+  if (grid > cap) grid = cap;
+  if (grid < 1) return FC_OK;
+  dim3 g((unsigned)grid), b((unsigned)f.warps * 32);
+  bool ok = false;
+#define FC_PAIR_FUSED_CASE(NN, CC, NPP, WW, PL, OC)                                                                      \
+  if (!ok && f.N == NN && f.ci == CC && f.nb == NPP && f.warps == WW && (f.plain != 0) == PL && f.occ == OC) { \
+    auto k = fc_pair_fused_kernel<NN, CC, NPP, WW, PL, OC>;                                                              \
+    FC_LAUNCH(k, g, b, smem, st, a);                                                                                      \
+    ok = true;                                                                                                            \
+  }
+  FC_PAIR_FUSED_ALL(FC_PAIR_FUSED_CASE)
+#undef FC_PAIR_FUSED_CASE
+  if (!ok) return set_err(FC_EUNSUPPORTED, "no pair fused kernel instantiation for this shape");
+  rec_mark();
+  return check_cuda("pair fused launch");
 }
 
 // ---- tensor-core contraction (fc_tc.cuh)
@@ -734,6 +901,15 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
         break;
       case FC_L_FAST_C2C:
         rc = launch_fast_c2c(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, st);
+        break;
+      case FC_L_PAIR_R2C:
+        rc = launch_pair_r2c(plan, L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, st);
+        break;
+      case FC_L_PAIR_C2R:
+        rc = launch_pair_c2r(plan, L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, d_bias, st);
+        break;
+      case FC_L_PAIR_FUSED:
+        rc = launch_pair_fused(plan, L.fused, buf_ptr(b, L.src), (const float2*)d_kspec, buf_ptr(b, L.dst), tw, st);
         break;
       case FC_L_PLANE_FWD:
       case FC_L_PLANE_INV:

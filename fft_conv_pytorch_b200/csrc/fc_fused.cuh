@@ -15,7 +15,6 @@
 //                        for every output channel, without the two spectrum round trips through HBM
 //   fc_fast_c2r_kernel   K4: transposed load -> C2R -> crop / stride + bias -> coalesced real rows
 #pragma once
-#include "fc_async.cuh"
 #include "fc_kernels.cuh"
 
 #define FC_SYNCWARP() __syncwarp()
@@ -261,7 +260,6 @@ struct fc_fast_r2c_args {
   const float* x;
   float2* out;
   const float2* tw;
-  int32_t dbg;  // timing experiments only (FFTCONV_B200_DBG): 1 = skip the transform, 2 = skip the global stores
 };
 
 // Shared memory: TR lines of pitch M + 1 float2. A line is its warp's exchange buffer during the transform, then
@@ -333,12 +331,10 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
     const int sg = p.seg_n > 1 ? rem / tps : 0;
     const int r0 = (rem - sg * tps) * TR;
     const int tn = t + gridDim.x;
-    if (a.dbg != 1) {
-      if constexpr (G == 32)
-        fc_wfft<M, NL, LP>(v, line0, ofs, a.tw, p.tw_len, lane);
-      else
-        fc_gfft<M, G, NL, LP>(v, line0, a.tw, p.tw_len, gl);
-    }
+    if constexpr (G == 32)
+      fc_wfft<M, NL, LP>(v, line0, ofs, a.tw, p.tw_len, lane);
+    else
+      fc_gfft<M, G, NL, LP>(v, line0, a.tw, p.tw_len, gl);
     fc_lwrite<M, G, NL, LP>(v, line0, ofs, gl);
     FC_SYNCWARP();
     // untangle the packed real transforms (same algebra as the generic R2C pass) into the registers
@@ -384,7 +380,7 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_r2c_kernel(fc_fast_r2c_a
     }
     {  // transposed store: thread (l = tid % TR, k = tid / TR + KS j) writes TR consecutive rows of one bin (128 / 256 bytes)
       const int l = tid & (TR - 1);  // tile line l lives at smem + l*LP (see lrow)
-      if (r0 + l < R && a.dbg != 2) {
+      if (r0 + l < R) {
         const int k0 = (tid / TR) & (KS - 1);
         float2* dst = a.out + (int64_t)o * p.out_os + r0 + l + (int64_t)(k0 + sg * (M + 1)) * p.out_es;
         const float2* src = smem + l * LP;

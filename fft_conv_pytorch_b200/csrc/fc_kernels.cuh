@@ -28,6 +28,15 @@ FC_DEV void fc_grid_dep_sync() {}
 FC_DEV void fc_grid_dep_sync() { asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory"); }
 #endif
 
+// Named barrier over a subset of a CTA's threads (the compute warps of the fused kernels); tests/cpu_emul supplies a
+// host stand-in with the same semantics.
+#ifdef FC_CPU_EMUL
+void fc_emul_named_barrier(int id, int count);  // tests/cpu_emul/cuda_shim.cpp
+FC_DEV void fc_named_bar_sync(int id, int threads) { fc_emul_named_barrier(id, threads); }
+#else
+FC_DEV void fc_named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+#endif
+
 // Streaming accesses: data that is read or written exactly once by the pipeline (the real input, a spectrum on its way
 // out of L2, the final output) is moved with the evict-first policy so that it does not push the spectra the next kernel
 // is about to read out of the 126 MB L2.

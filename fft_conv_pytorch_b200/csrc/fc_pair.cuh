@@ -1,0 +1,789 @@
+// fc_pair.cuh — the "pair" pipeline of the fused 2-d program: K1p -> KBp -> K4p on packed fp32 pairs.
+//
+// Blackwell issues two fp32 operations per lane with one FADD2 / FMUL2 / FFMA2 (PTX add/mul/fma.rn.f32x2) when both
+// operands sit in aligned 64-bit register pairs, and FFMA2 / FMUL2 take a *scalar* second operand that is broadcast
+// to both halves. The kernels here are laid out around that: the two batch items 2p and 2p + 1 of one channel form a
+// "pair line", every complex value is held as (re of item 0, re of item 1), (im of item 0, im of item 1), and
+// everything the two items share — twiddle factors, the kernel spectrum — enters as the broadcast scalar operand.
+// A radix-8 butterfly of two lines is then 52 packed instructions instead of 2 x 32, a twiddle multiply 4 instead of
+// 2 x 4, and the per-bin channel contraction 2 FFMA2 per complex multiply-accumulate instead of 4 FFMA, with no
+// register shuffling anywhere: spectra live in HBM and in shared memory as 16-byte slots {re0, re1, im0, im1}, moved
+// with 128-bit loads and stores.
+//
+//   fc_pair_r2c_kernel   K1p: rows of the two images of a pair -> packed half spectra, stored transposed
+//                        ([pair image][bin][row] slots) so that the next axis is contiguous
+//   fc_pair_fused_kernel KBp: per bin of the other axis: forward transform of every input-channel pair line,
+//                        per-bin grouped contraction with the cached kernel spectrum (complex_matmul, reference
+//                        functional.py:11-16), inverse transform of every output-channel pair line
+//   fc_pair_c2r_kernel   K4p: transposed load -> C2R -> crop / stride / lattice + bias -> rows of the two images
+//
+// Replaces (reference functional.py) :60-62 / :126-139 (padding, zero-stuffing: gather maps), :70 / :157 rfftn of the
+// signal, :73 / :160 complex_matmul, :75 / :162 irfftn, :76-87 / :163-174 crop, stride, bias.
+#pragma once
+#include "fc_fused.cuh"
+
+// ------------------------------------------------------------------------------------------------ packed pairs
+#ifdef FC_CPU_EMUL
+struct fc_p2 {
+  float x, y;
+};
+FC_DEV fc_p2 p2_make(float lo, float hi) { return fc_p2{lo, hi}; }
+FC_DEV float p2_lo(fc_p2 a) { return a.x; }
+FC_DEV float p2_hi(fc_p2 a) { return a.y; }
+FC_DEV fc_p2 p2_add(fc_p2 a, fc_p2 b) { return fc_p2{a.x + b.x, a.y + b.y}; }
+FC_DEV fc_p2 p2_sub(fc_p2 a, fc_p2 b) { return fc_p2{a.x - b.x, a.y - b.y}; }
+FC_DEV fc_p2 p2_mul(fc_p2 a, fc_p2 b) { return fc_p2{a.x * b.x, a.y * b.y}; }
+FC_DEV fc_p2 p2_fma(fc_p2 a, fc_p2 b, fc_p2 c) { return fc_p2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+#else
+typedef unsigned long long fc_p2;
+FC_DEV fc_p2 p2_make(float lo, float hi) {
+  fc_p2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+FC_DEV float p2_lo(fc_p2 a) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+  return lo;
+}
+FC_DEV float p2_hi(fc_p2 a) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+  return hi;
+}
+FC_DEV fc_p2 p2_add(fc_p2 a, fc_p2 b) {
+  fc_p2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+FC_DEV fc_p2 p2_sub(fc_p2 a, fc_p2 b) {
+  fc_p2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+FC_DEV fc_p2 p2_mul(fc_p2 a, fc_p2 b) {
+  fc_p2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+FC_DEV fc_p2 p2_fma(fc_p2 a, fc_p2 b, fc_p2 c) {
+  fc_p2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+#endif
+// Scalar operand shared by both halves: ptxas folds the duplicate into the broadcast (".F32") operand form of
+// FMUL2 / FFMA2, negation included, so neither costs an instruction.
+FC_DEV fc_p2 p2_dup(float s) { return p2_make(s, s); }
+FC_DEV fc_p2 p2_muls(fc_p2 a, float s) { return p2_mul(a, p2_dup(s)); }
+FC_DEV fc_p2 p2_fmas(fc_p2 a, float s, fc_p2 c) { return p2_fma(a, p2_dup(s), c); }
+
+// Two complex numbers (one per item of the pair): a 16-byte slot {re0, re1, im0, im1}.
+struct alignas(16) fc_c2 {
+  fc_p2 re, im;
+};
+FC_DEV fc_c2 c2_make(fc_p2 re, fc_p2 im) {
+  fc_c2 r;
+  r.re = re;
+  r.im = im;
+  return r;
+}
+FC_DEV fc_c2 c2_zero() { return c2_make(p2_make(0.f, 0.f), p2_make(0.f, 0.f)); }
+FC_DEV fc_c2 c2_add(fc_c2 a, fc_c2 b) { return c2_make(p2_add(a.re, b.re), p2_add(a.im, b.im)); }
+FC_DEV fc_c2 c2_sub(fc_c2 a, fc_c2 b) { return c2_make(p2_sub(a.re, b.re), p2_sub(a.im, b.im)); }
+// Swapping the parts turns the forward transform into the (unnormalised) inverse: ifft(z) = swap(fft(swap(z))). With
+// separate registers for the parts it is a renaming, not an instruction.
+FC_DEV fc_c2 c2_swap(fc_c2 a) { return c2_make(a.im, a.re); }
+// a + b*(-i), a - b*(-i)
+FC_DEV fc_c2 c2_add_mi(fc_c2 a, fc_c2 b) { return c2_make(p2_add(a.re, b.im), p2_sub(a.im, b.re)); }
+FC_DEV fc_c2 c2_sub_mi(fc_c2 a, fc_c2 b) { return c2_make(p2_sub(a.re, b.im), p2_add(a.im, b.re)); }
+// a * w, w shared by the two items
+FC_DEV fc_c2 c2_muls(fc_c2 a, float2 w) {
+  return c2_make(p2_fmas(a.re, w.x, p2_muls(a.im, -w.y)), p2_fmas(a.re, w.y, p2_muls(a.im, w.x)));
+}
+
+#ifdef FC_CPU_EMUL
+FC_DEV fc_c2 c2_ldg(const fc_c2* p) { return *p; }
+FC_DEV fc_c2 c2_ld_stream(const fc_c2* p) { return *p; }
+FC_DEV void c2_st_stream(fc_c2* p, fc_c2 v) { *p = v; }
+#else
+FC_DEV fc_c2 c2_ldg(const fc_c2* p) {
+  const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2*>(p));
+  return c2_make(t.x, t.y);
+}
+FC_DEV fc_c2 c2_ld_stream(const fc_c2* p) {
+  const ulonglong2 t = __ldcs(reinterpret_cast<const ulonglong2*>(p));
+  return c2_make(t.x, t.y);
+}
+FC_DEV void c2_st_stream(fc_c2* p, fc_c2 v) { __stcs(reinterpret_cast<ulonglong2*>(p), make_ulonglong2(v.re, v.im)); }
+#endif
+
+// XOR swizzle of the slot index inside a pair line. 16-byte accesses are served a quarter warp at a time, so an access
+// is conflict-free when its 8 lanes touch 8 different slots mod 8. That holds for every pattern of the Stockham
+// stages below: 8 consecutive slots (the lane + G*q reads, the writes of the stages with Ns >= 8) and the stride-8
+// writes of the first stage (8j + r -> 8j + (r ^ (j & 7))).
+FC_DEV int fc_swz16(int p) { return p ^ ((p >> 3) & 7); }
+
+// ------------------------------------------------------------------------------------------------ butterflies
+template <int R>
+FC_DEV void fc_pbutterfly(fc_c2* v);
+
+template <>
+FC_DEV void fc_pbutterfly<2>(fc_c2* v) {
+  const fc_c2 a = v[0], b = v[1];
+  v[0] = c2_add(a, b);
+  v[1] = c2_sub(a, b);
+}
+
+template <>
+FC_DEV void fc_pbutterfly<4>(fc_c2* v) {
+  const fc_c2 b0 = c2_add(v[0], v[2]), b2 = c2_sub(v[0], v[2]);
+  const fc_c2 b1 = c2_add(v[1], v[3]), d = c2_sub(v[1], v[3]);
+  v[0] = c2_add(b0, b1);
+  v[2] = c2_sub(b0, b1);
+  v[1] = c2_add_mi(b2, d);
+  v[3] = c2_sub_mi(b2, d);
+}
+
+// Radix 8 (forward, sign -1). The two 45-degree rotations are left unscaled and their factor 1/sqrt2 is applied by the
+// FFMA2 of the last level: 52 packed instructions for two lines.
+template <>
+FC_DEV void fc_pbutterfly<8>(fc_c2* v) {
+  const float h = 0.70710678118654752440f;
+  const fc_c2 a0 = c2_add(v[0], v[4]), a4 = c2_sub(v[0], v[4]);
+  const fc_c2 a1 = c2_add(v[1], v[5]), a5 = c2_sub(v[1], v[5]);
+  const fc_c2 a2 = c2_add(v[2], v[6]), a6 = c2_sub(v[2], v[6]);
+  const fc_c2 a3 = c2_add(v[3], v[7]), a7 = c2_sub(v[3], v[7]);
+  const fc_c2 a5u = c2_make(p2_add(a5.re, a5.im), p2_sub(a5.im, a5.re));  // a5 * (1 - i)    [= sqrt2 * a5 * W8]
+  const fc_c2 a7n = c2_make(p2_sub(a7.re, a7.im), p2_add(a7.re, a7.im));  // a7 * (1 + i)    [= -sqrt2 * a7 * W8^3]
+  const fc_c2 b0 = c2_add(a0, a2), b2 = c2_sub(a0, a2);
+  const fc_c2 b1 = c2_add(a1, a3), d13 = c2_sub(a1, a3);
+  const fc_c2 b4 = c2_add_mi(a4, a6), b6 = c2_sub_mi(a4, a6);
+  const fc_c2 b5u = c2_sub(a5u, a7n);  // sqrt2 * (a5 W8 + a7 W8^3)
+  const fc_c2 s = c2_add(a5u, a7n);    // sqrt2 * (a5 W8 - a7 W8^3); b7 = s * (-i) / sqrt2
+  v[0] = c2_add(b0, b1);
+  v[4] = c2_sub(b0, b1);
+  v[2] = c2_add_mi(b2, d13);
+  v[6] = c2_sub_mi(b2, d13);
+  v[1] = c2_make(p2_fmas(b5u.re, h, b4.re), p2_fmas(b5u.im, h, b4.im));
+  v[5] = c2_make(p2_fmas(b5u.re, -h, b4.re), p2_fmas(b5u.im, -h, b4.im));
+  v[3] = c2_make(p2_fmas(s.im, h, b6.re), p2_fmas(s.re, -h, b6.im));
+  v[7] = c2_make(p2_fmas(s.im, -h, b6.re), p2_fmas(s.re, h, b6.im));
+}
+
+// ------------------------------------------------------------------------------------------------ the pair engine
+// A group of G lanes (G = 32 for M >= 256, else M/8) owns NLP pair lines of M points; lane gl of the group holds the
+// points gl + G*q, q < E = M/G, of each. v[l][t + NBF*r] = input r of butterfly t of pair line l.
+template <int M, int G, int NLP, int R, int Ns>
+FC_DEV void fc_pstage(fc_c2 (&v)[NLP][M / G], const float2* tw, int tw_len, int gl) {
+  constexpr int E = M / G, NBF = E / R;
+  float2 w[R];
+  if (Ns > 1 && Ns <= G) fc_twiddle_powers<R>(__ldg(tw + (gl & (Ns - 1)) * (tw_len / (Ns * R))), w);  // same for every t
+#pragma unroll
+  for (int t = 0; t < NBF; ++t) {
+    if (Ns > G) fc_twiddle_powers<R>(__ldg(tw + ((gl + G * t) & (Ns - 1)) * (tw_len / (Ns * R))), w);
+#pragma unroll
+    for (int l = 0; l < NLP; ++l) {
+      fc_c2 a[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r] = v[l][t + NBF * r];
+      if (Ns > 1) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) a[r] = c2_muls(a[r], w[r]);
+      }
+      fc_pbutterfly<R>(a);
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[l][t + NBF * r] = a[r];
+    }
+  }
+}
+
+// Exchange after a stage: outputs go to their Stockham positions in the group's lines (swizzled slots), then every
+// lane reads the gl + G*q layout back. Pair line l of the group lives at line0 + l*LS.
+template <int M, int G, int NLP, int LS, int R, int Ns>
+FC_DEV void fc_pxchg(fc_c2 (&v)[NLP][M / G], fc_c2* line0, int gl) {
+  constexpr int E = M / G, NBF = E / R;
+#pragma unroll
+  for (int t = 0; t < NBF; ++t) {
+    const int j = gl + G * t;
+    const int k = j & (Ns - 1);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int s = fc_swz16(j0 + r * Ns);
+#pragma unroll
+      for (int l = 0; l < NLP; ++l) line0[l * LS + s] = v[l][t + NBF * r];
+    }
+  }
+  FC_SYNCWARP();
+#pragma unroll
+  for (int q = 0; q < E; ++q) {
+    const int s = fc_swz16(gl + G * q);
+#pragma unroll
+    for (int l = 0; l < NLP; ++l) v[l][q] = line0[l * LS + s];
+  }
+  FC_SYNCWARP();
+}
+
+// Forward, unnormalised FFT of NLP pair lines of M points; on return v[l][q] is bin gl + G*q. Every lane of the warp
+// must call it (warp-wide __syncwarp); the lines are clobbered.
+template <int M, int G, int NLP, int LS>
+FC_DEV void fc_pfft(fc_c2 (&v)[NLP][M / G], fc_c2* line0, const float2* tw, int tw_len, int gl) {
+  static_assert(M == 128 || M == 256 || M == 512 || M == 1024 || M == 2048, "unsupported pair FFT length");
+  static_assert(G == (M >= 256 ? 32 : M / 8), "lanes per pair line");
+  fc_pstage<M, G, NLP, 8, 1>(v, tw, tw_len, gl);
+  fc_pxchg<M, G, NLP, LS, 8, 1>(v, line0, gl);
+  fc_pstage<M, G, NLP, 8, 8>(v, tw, tw_len, gl);
+  fc_pxchg<M, G, NLP, LS, 8, 8>(v, line0, gl);
+  if constexpr (M == 128) {
+    fc_pstage<M, G, NLP, 2, 64>(v, tw, tw_len, gl);
+  } else if constexpr (M == 256) {
+    fc_pstage<M, G, NLP, 4, 64>(v, tw, tw_len, gl);
+  } else if constexpr (M == 512) {
+    fc_pstage<M, G, NLP, 8, 64>(v, tw, tw_len, gl);
+  } else {
+    fc_pstage<M, G, NLP, 8, 64>(v, tw, tw_len, gl);
+    fc_pxchg<M, G, NLP, LS, 8, 64>(v, line0, gl);
+    fc_pstage<M, G, NLP, (M == 2048 ? 4 : 2), 512>(v, tw, tw_len, gl);
+  }
+}
+
+// Pair image o = p*C + c of a (B, C, ...) tensor: the images (2p, c) and (2p + 1, c); the second one is missing for
+// the last pair of an odd batch.
+struct fc_pair_img {
+  int64_t i0;  // image index of item 0: (2p)*C + c; item 1 is C images further
+  bool has1;
+};
+FC_DEV fc_pair_img fc_pair_image(int o, int B, int C) {
+  const int p = o / C, c = o - p * C;
+  fc_pair_img r;
+  r.i0 = (int64_t)(2 * p) * C + c;
+  r.has1 = 2 * p + 1 < B;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------ K1p
+struct fc_pair_r2c_args {
+  fc_pass p;  // the pass of the fast R2C kernel, retiled over pair images: n_outer = ceil(B/2)*C, T pair lines per tile
+  const float* x;
+  fc_c2* out;  // [pair image][bin (+ segment*(M+1))][row] slots
+  const float2* tw;
+  int32_t B, C;
+};
+
+// Shared memory: TR pair lines of pitch M + 1 slots (odd: the transposed sweep of the store phase is conflict-free).
+// A line is its group's exchange buffer during the transform, then holds the untangled half spectrum (bin k at the
+// swizzled slot of k, the Nyquist bin in the extra slot M).
+template <int M, int NLP, int NW, int OCC>
+__global__ void __launch_bounds__(NW * 32, OCC) fc_pair_r2c_kernel(fc_pair_r2c_args a) {
+  fc_grid_dep_sync();
+  constexpr int G = M >= 256 ? 32 : M / 8;
+  constexpr int E = M / G, GPW = 32 / G;
+  constexpr int TR = NLP * NW * GPW, LP = M + 1, KS = NW * 32 / TR;  // TR pair lines per tile; KS bins per store sweep
+  static_assert(TR >= 8 && (TR & (TR - 1)) == 0 && TR <= NW * 32, "a tile is a power-of-two number of pair lines");
+  const fc_pass& p = a.p;
+  FC_DYN_SMEM(smem_raw);
+  fc_c2* smem = reinterpret_cast<fc_c2*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int gl = lane % G, gid = lane / G;
+  const int lrow = (w * GPW + gid) * NLP;  // first tile line of this lane's group
+  fc_c2* line0 = smem + lrow * LP;
+  const int L = p.imap.L;
+  const int tstep = p.tw_len / (2 * M);
+  const int tpo = (int)p.tiles_per_outer, n_tiles = (int)p.n_tiles, R = (int)p.R;
+  const int tps = tpo / p.seg_n;  // overlap-save segments: the tiles of an outer item run segment-major
+  auto load_rows = [&](int t, fc_c2 (&v)[NLP][E]) {
+    const int o = t / tpo;
+    const int rem = t - o * tpo;
+    const int sg = p.seg_n > 1 ? rem / tps : 0;
+    const int r0 = (rem - sg * tps) * TR;
+    const int ub = sg * p.seg_V - p.seg_off - p.imap.pad;  // source index of the segment's first dense position (even)
+    const fc_pair_img pi = fc_pair_image(o, a.B, a.C);
+    const float* img0 = a.x + pi.i0 * p.o_sA;
+    const float* img1 = img0 + (int64_t)a.C * p.o_sA;
+#pragma unroll
+    for (int l = 0; l < NLP; ++l) {
+      const int r = r0 + lrow + l;
+      const bool valid = r < R;
+      const int64_t roff = (int64_t)(valid ? r : 0) * p.in_rs + ub;
+      const float2* row0 = reinterpret_cast<const float2*>(img0 + roff) + gl;
+      const float2* row1 = reinterpret_cast<const float2*>(img1 + roff) + gl;
+#pragma unroll
+      for (int q = 0; q < E; ++q) {  // L, the zero padding and ub are even (host check): the pair (2m, 2m + 1) is in or out together
+        const bool in = valid && (unsigned)(ub + 2 * (gl + G * q)) < (unsigned)L;
+        const float2 x0 = in ? __ldg(row0 + G * q) : make_float2(0.f, 0.f);
+        const float2 x1 = (in && pi.has1) ? __ldg(row1 + G * q) : make_float2(0.f, 0.f);
+        v[l][q] = c2_make(p2_make(x0.x, x1.x), p2_make(x0.y, x1.y));
+      }
+    }
+  };
+  fc_c2 v[NLP][E];
+  if ((int)blockIdx.x < n_tiles) load_rows(blockIdx.x, v);
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int o = t / tpo;
+    const int rem = t - o * tpo;
+    const int sg = p.seg_n > 1 ? rem / tps : 0;
+    const int r0 = (rem - sg * tps) * TR;
+    const int tn = t + gridDim.x;
+    fc_pfft<M, G, NLP, LP>(v, line0, a.tw, p.tw_len, gl);
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const int s = fc_swz16(gl + G * q);
+#pragma unroll
+      for (int l = 0; l < NLP; ++l) line0[l * LP + s] = v[l][q];
+    }
+    FC_SYNCWARP();
+    // untangle the packed real transforms: X[k] = (z[k] + conj z[M-k])/2 + w_k * (-i)(z[k] - conj z[M-k])/2
+    fc_p2 nyq[NLP];
+#pragma unroll
+    for (int l = 0; l < NLP; ++l) {
+      const fc_c2 z0 = line0[l * LP];  // fc_swz16(0) == 0
+      nyq[l] = p2_sub(z0.re, z0.im);   // bin k = M: E[0] - O[0]
+    }
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const int k = gl + G * q;
+      const float2 wk = __ldg(a.tw + k * tstep);
+      const float hx = 0.5f * wk.x, hy = 0.5f * wk.y;
+      const int km = fc_swz16((M - k) & (M - 1));
+#pragma unroll
+      for (int l = 0; l < NLP; ++l) {
+        const fc_c2 zk = v[l][q];
+        const fc_c2 zm = line0[l * LP + km];
+        const fc_p2 s_re = p2_add(zk.re, zm.re), s_im = p2_sub(zk.im, zm.im);
+        const fc_p2 d_re = p2_sub(zk.re, zm.re), d_im = p2_add(zk.im, zm.im);
+        v[l][q] = c2_make(p2_fmas(s_re, 0.5f, p2_fmas(d_im, hx, p2_muls(d_re, hy))),
+                          p2_fmas(s_im, 0.5f, p2_fmas(d_re, -hx, p2_muls(d_im, hy))));
+      }
+    }
+    FC_SYNCWARP();  // every partner has been read: the lines can take the spectrum
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const int s = fc_swz16(gl + G * q);
+#pragma unroll
+      for (int l = 0; l < NLP; ++l) line0[l * LP + s] = v[l][q];
+    }
+    if (gl == 0) {
+#pragma unroll
+      for (int l = 0; l < NLP; ++l) line0[l * LP + M] = c2_make(nyq[l], p2_make(0.f, 0.f));
+    }
+    __syncthreads();
+    if (tn < n_tiles) {
+      load_rows(tn, v);  // in flight during the store below
+      const int t2 = tn + gridDim.x;  // and pull the tile after that one into L2 (the segments of a row re-read it anyway)
+      if (t2 < n_tiles && p.seg_n == 1) {
+        const int on = t2 / tpo;
+        const int rn = (t2 - on * tpo) * TR;
+        const int rows = (R - rn < TR) ? R - rn : TR;
+        const fc_pair_img pn = fc_pair_image(on, a.B, a.C);
+        const int span = rows * (int)p.in_rs;  // floats: the TR rows of an image are one contiguous run
+        const float* nxt = a.x + pn.i0 * p.o_sA + (int64_t)rn * p.in_rs;
+        for (int e = tid * 32; e < span; e += NW * 32 * 32) {
+          fc_prefetch_l2(nxt + e);
+          if (pn.has1) fc_prefetch_l2(nxt + (int64_t)a.C * p.o_sA + e);
+        }
+      }
+    }
+    {  // transposed store: thread (l = tid % TR, k = tid / TR + KS*it) writes TR consecutive rows of one bin (TR*16 bytes)
+      const int l = tid & (TR - 1);
+      if (r0 + l < R) {
+        const int k0 = tid / TR;
+        fc_c2* dst = a.out + (int64_t)o * p.out_os + r0 + l + (int64_t)(k0 + sg * (M + 1)) * p.out_es;
+        const fc_c2* src = smem + l * LP;
+        const int64_t dstep = KS * p.out_es;
+#pragma unroll 8
+        for (int it = 0; it < M / KS; ++it) dst[it * dstep] = src[fc_swz16(k0 + KS * it)];
+        if (k0 == 0) dst[(M / KS) * dstep] = src[M];  // the Nyquist bin
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K4p
+struct fc_pair_c2r_args {
+  fc_pass p;  // the pass of the fast C2R kernel, retiled over pair images: n_outer = ceil(B/2)*Cout
+  const fc_c2* in;  // [pair image][bin (+ segment*(M+1))][row] slots
+  float* out;
+  const float2* tw;
+  const float* bias;
+  int32_t B, C;  // batch, output channels
+};
+
+template <int M, int NLP, int NW, int OCC>
+__global__ void __launch_bounds__(NW * 32, OCC) fc_pair_c2r_kernel(fc_pair_c2r_args a) {
+  fc_grid_dep_sync();
+  constexpr int G = M >= 256 ? 32 : M / 8;
+  constexpr int E = M / G, GPW = 32 / G;
+  constexpr int TR = NLP * NW * GPW, LP = M + 1, KS = NW * 32 / TR;
+  static_assert(TR >= 8 && (TR & (TR - 1)) == 0 && TR <= NW * 32, "a tile is a power-of-two number of pair lines");
+  const fc_pass& p = a.p;
+  FC_DYN_SMEM(smem_raw);
+  fc_c2* smem = reinterpret_cast<fc_c2*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int gl = lane % G, gid = lane / G;
+  const int lrow = (w * GPW + gid) * NLP;
+  fc_c2* line0 = smem + lrow * LP;
+  const int tstep = p.tw_len / (2 * M);
+  const fc_omap om = p.omap;
+  const bool plain_out = om.os == 1 && om.ob == 0 && om.og == 1 && !(om.Lout & 1) && !(p.out_rs & 1) && !(p.out_os & 1) && p.row_og == 1 &&
+                         p.seg_n == 1;
+  const int tpo = (int)p.tiles_per_outer, n_tiles = (int)p.n_tiles, R = (int)p.R;
+  const int tps = tpo / p.seg_n;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int o = t / tpo;
+    const int rem = t - o * tpo;
+    const int sg = p.seg_n > 1 ? rem / tps : 0;
+    const int r0 = (rem - sg * tps) * TR;
+    {  // transposed load: thread (l = tid % TR, k = tid / TR + KS*it) reads TR consecutive rows of one bin
+      const int l = tid & (TR - 1);
+      const bool ok = r0 + l < R;
+      const int k0 = tid / TR;
+      const fc_c2* src = a.in + (int64_t)o * p.in_os + r0 + (ok ? l : 0) + (int64_t)(k0 + sg * (M + 1)) * p.in_es;
+      fc_c2* dst = smem + l * LP + k0;
+      const int64_t sstep = KS * p.in_es;
+      constexpr int NIT = (M + KS) / KS;  // ceil((M + 1) / KS)
+      constexpr int CH = NIT < 8 ? NIT : 8;  // loads of a thread in flight before the first shared-memory store
+#pragma unroll 1
+      for (int i0 = 0; i0 < NIT; i0 += CH) {
+        fc_c2 tbuf[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int it = i0 + i;
+          tbuf[i] = (ok && it < NIT && k0 + it * KS <= M) ? c2_ldg(src + it * sstep) : c2_zero();
+        }
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int it = i0 + i;
+          if (it < NIT && k0 + it * KS <= M) dst[it * KS] = tbuf[i];
+        }
+      }
+    }
+    {  // L2 prefetch of the next tile of this CTA: (M+1) segments of TR slots
+      const int tn = t + gridDim.x;
+      if (tn < n_tiles) {
+        const int on = tn / tpo;
+        const int remn = tn - on * tpo;
+        const int sn = p.seg_n > 1 ? remn / tps : 0;
+        const int rn = (remn - sn * tps) * TR;
+        const fc_c2* nxt = a.in + (int64_t)on * p.in_os + rn + (int64_t)sn * (M + 1) * p.in_es;
+        constexpr int PL = TR / 8;  // 128-byte lines per segment
+        for (int k = tid; k < (M + 1) * PL; k += NW * 32) fc_prefetch_l2(nxt + (int64_t)(k / PL) * p.in_es + 8 * (k % PL));
+      }
+    }
+    __syncthreads();
+    const fc_pair_img pi = fc_pair_image(o, a.B, a.C);
+    const float b = p.has_bias ? __ldg(a.bias + (o % a.C)) : 0.f;
+    // Hermitian pre-twist: Z[k] = (Y[k] + conj Y[M-k]) + i * conj(w_k) * (Y[k] - conj Y[M-k]); the transform runs on
+    // swap(Z) and the real samples come out as x[2m] = im, x[2m+1] = re of the result
+    fc_c2 v[NLP][E];
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const int k = gl + G * q;
+      const float2 wk = __ldg(a.tw + k * tstep);
+#pragma unroll
+      for (int l = 0; l < NLP; ++l) {
+        const fc_c2 yk = line0[l * LP + k];
+        const fc_c2 ym = line0[l * LP + M - k];
+        const fc_p2 s_re = p2_add(yk.re, ym.re), s_im = p2_sub(yk.im, ym.im);
+        const fc_p2 t_re = p2_sub(yk.re, ym.re), t_im = p2_add(yk.im, ym.im);
+        // d = t * conj(w_k): d.re = t.re*wx + t.im*wy, d.im = t.im*wx - t.re*wy;  Z = (s.re - d.im, s.im + d.re)
+        const fc_p2 z_re = p2_fmas(t_re, wk.y, p2_fmas(t_im, -wk.x, s_re));
+        const fc_p2 z_im = p2_fmas(t_im, wk.y, p2_fmas(t_re, wk.x, s_im));
+        v[l][q] = c2_make(z_im, z_re);
+      }
+    }
+    FC_SYNCWARP();  // the lines are exchange buffers from here on
+    fc_pfft<M, G, NLP, LP>(v, line0, a.tw, p.tw_len, gl);
+    if (plain_out) {
+#pragma unroll
+      for (int l = 0; l < NLP; ++l) {
+        const int64_t r = r0 + lrow + l;
+        if (r < p.R) {
+          float* y0 = a.out + pi.i0 * p.out_os + r * p.out_rs;
+          float* y1 = y0 + (int64_t)a.C * p.out_os;
+#pragma unroll
+          for (int q = 0; q < E; ++q) {
+            const int n0 = 2 * (gl + G * q);
+            if (n0 < om.Lout) {
+              const fc_c2 f = v[l][q];
+              fc_st_stream(reinterpret_cast<float2*>(y0 + n0), make_float2(p2_lo(f.im) + b, p2_lo(f.re) + b));
+              if (pi.has1) fc_st_stream(reinterpret_cast<float2*>(y1 + n0), make_float2(p2_hi(f.im) + b, p2_hi(f.re) + b));
+            }
+          }
+        }
+      }
+    } else {
+      // general crop / stride / lattice map: stage the real rows of the two items in the group's lines (item h at floats
+      // [2M*h, 2M*h + 2M) of the pair line) and scatter from there
+      FC_SYNCWARP();
+#pragma unroll
+      for (int l = 0; l < NLP; ++l) {
+        float2* f2 = reinterpret_cast<float2*>(line0 + l * LP);
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const fc_c2 f = v[l][q];
+          f2[gl + G * q] = make_float2(p2_lo(f.im), p2_lo(f.re));
+          f2[M + gl + G * q] = make_float2(p2_hi(f.im), p2_hi(f.re));
+        }
+      }
+      FC_SYNCWARP();
+      // this (row, segment) line owns the dense samples n in [n_lo, n_hi), i.e. the outputs j with
+      // n(j) = (j*os + ob) / og in that range: a contiguous run of j because n(j) is monotone
+      const int n_lo = sg * p.seg_V, n_hi = n_lo + p.seg_V;
+      const int c_lo = n_lo * om.og - om.ob, c_hi = n_hi * om.og - om.ob;
+      const int j_lo = c_lo > 0 ? (c_lo + om.os - 1) / om.os : 0;
+      int j_hi = c_hi > 0 ? (c_hi + om.os - 1) / om.os : 0;
+      if (j_hi > om.Lout) j_hi = om.Lout;
+      for (int lh = 0; lh < 2 * NLP; ++lh) {
+        const int l = lh >> 1, h = lh & 1;
+        const int64_t r = r0 + lrow + l;
+        if (r >= p.R || (h && !pi.has1)) continue;
+        const float* rl = reinterpret_cast<const float*>(line0 + l * LP) + 2 * M * h + (p.seg_off - n_lo);
+        float* img = a.out + (pi.i0 + (int64_t)h * a.C) * p.out_os;
+        for (int er = 0; er < p.row_og; ++er) {  // output rows owned by this dense line (one unless row lattice)
+          const int64_t jr = r * p.row_og + er - p.row_ob;
+          if (jr < 0 || jr >= p.row_Lout) continue;
+          float* yrow = img + jr * p.out_rs;
+          if (er != 0) {  // a row between the lattice rows: bias only
+            fc_fill_run<G>(yrow, j_lo, j_hi, b, gl);
+            continue;
+          }
+          if (om.og == 2 && om.os == 1 && om.ob >= 0) {
+            // lattice of 2 (BASELINE c5: stride 2, dilation 2): of every aligned output pair exactly one is a dense
+            // sample, the other is bias only -> one shared-memory read and one 8-byte store per two outputs
+            const int mis = (int)((reinterpret_cast<uintptr_t>(yrow + j_lo) >> 2) & 1);
+            const int ja = j_lo + mis < j_hi ? j_lo + mis : j_hi;
+            const int npairs = (j_hi - ja) >> 1;
+            const int par = (ja + om.ob) & 1;        // 0: the first output of a pair is the dense sample, 1: the second
+            const int nb = (ja + om.ob + par) >> 1;  // dense index of the sample of pair 0
+            float2* y2 = reinterpret_cast<float2*>(yrow + ja);
+#pragma unroll 4
+            for (int m = gl; m < npairs; m += G) {
+              const int n = nb + m;
+              const float val = (n < om.lim ? rl[n] : 0.f) + b;
+              y2[m] = par ? make_float2(b, val) : make_float2(val, b);
+            }
+            if (gl < 2) {  // the unaligned first and the odd last output of the run
+              const int j = gl == 0 ? j_lo : ja + 2 * npairs;
+              if (gl == 0 ? (mis && j_lo < j_hi) : j < j_hi) {
+                const int tt = j + om.ob, n = tt >> 1;
+                yrow[j] = ((tt & 1) == 0 && n < om.lim ? rl[n] : 0.f) + b;
+              }
+            }
+            continue;
+          }
+          // output-driven (coalesced stores): output j takes dense sample n = (j*os + ob) / og when the remainder
+          // is 0 and n < lim, else it is bias only
+#pragma unroll 8
+          for (int j = j_lo + gl; j < j_hi; j += G) {
+            const int tt = j * om.os + om.ob;
+            const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
+            const bool live = tt == n * om.og && n < om.lim;
+            yrow[j] = (live ? rl[n] : 0.f) + b;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ KBp
+struct fc_pair_fused_args {
+  const fc_c2* xin;     // [(p*Cin + c)][R][n_in] slots     output of K1p
+  const float2* kspec;  // bin-major kernel spectrum [group][line][o][i][N] (fc_fused.cuh)
+  fc_c2* yout;          // [(p*Cout + o)][R][n_out] slots   input of K4p
+  const float2* tw;
+  int32_t tw_len;
+  int32_t BP, Cin, Cout, G;  // batch pairs = ceil(B/2)
+  int32_t n_in, n_out, nbs;
+  int32_t n_items;  // BP * n_seg: (batch pair, segment) items per (group, bin); NP of them per unit
+  int32_t n_seg, seg_V, seg_off;
+  int32_t prefetch_dist;
+  int64_t R, Rk, n_units;
+  fc_imap imap;
+  fc_omap omap;
+};
+
+// Per-bin contraction over the CI input channels of the group, in place (X -> Y) in the CTA's pair lines. A thread
+// owns one bin of one pair item: the CI signal values (CI slots -> 4*CI registers) are loaded once, every kernel value
+// is the broadcast operand of 4 FFMA2 (two complex multiply-accumulates), and the four partial sums per output channel
+// are independent chains. The loop over output channels is unrolled: every kernel-spectrum load is the thread's base
+// pointer plus a compile-time offset and ptxas hoists the loads of the following channels above the FFMA2s of this one.
+template <int N, int CI, int NP, int W>
+FC_DEV void fc_pair_contract(fc_c2* xy, const fc_pair_fused_args& a, int g, int rk, int tid) {
+  for (int idx = tid; idx < N * NP; idx += W * 32) {
+    const int n = idx & (N - 1), pg = idx / N;
+    fc_c2* xb = xy + (size_t)(pg * CI) * N + n;  // line (pg, c) at xy + (pg*CI + c)*N
+    fc_c2 x[CI];
+#pragma unroll
+    for (int i = 0; i < CI; ++i) x[i] = xb[(size_t)i * N];
+    const float2* kp = a.kspec + ((int64_t)g * a.Rk + rk) * ((int64_t)CI * CI * N) + n;
+#pragma unroll
+    for (int o = 0; o < CI; ++o) {
+      fc_p2 rr = p2_make(0.f, 0.f), ii = rr, ri = rr, ir = rr;  // sum x.re*k.re, x.im*k.im, x.re*k.im, x.im*k.re
+#pragma unroll
+      for (int i = 0; i < CI; ++i) {
+        const float2 k = __ldg(kp + (o * CI + i) * N);
+        rr = p2_fmas(x[i].re, k.x, rr);
+        ii = p2_fmas(x[i].im, k.y, ii);
+        ri = p2_fmas(x[i].re, k.y, ri);
+        ir = p2_fmas(x[i].im, k.x, ir);
+      }
+      xb[(size_t)o * N] = c2_make(p2_sub(rr, ii), p2_add(ri, ir));
+    }
+  }
+}
+
+// N: transform length of the fused axis. CI: channels per group (in and out; full groups only). NP: pair items per CTA.
+// W: warps. PLAIN: identity gather map with all N points stored, a plain crop on store, a single segment.
+// Shared memory: NP*CI pair lines of N slots; a line is its warp's exchange buffer during the transforms and carries the
+// spectrum in natural order between the phases.
+template <int N, int CI, int NP, int W, bool PLAIN, int OCC>
+__global__ void __launch_bounds__(W * 32, OCC) fc_pair_fused_kernel(fc_pair_fused_args a) {
+  fc_grid_dep_sync();
+  constexpr int E = N / 32;
+  FC_DYN_SMEM(smem_raw);
+  fc_c2* xy = reinterpret_cast<fc_c2*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const fc_omap om = a.omap;
+  const int out_lim = om.Lout < om.lim ? om.Lout : om.lim;
+  // zero padding without zero-stuffing / subsampling: dense position u holds source u - pad for u in [u_lo, u_hi)
+  const bool simple_in = a.imap.mode == FC_PAD_CONSTANT && a.imap.up == 1 && a.imap.sub == 1;
+  const int u_lo = a.imap.pad > 0 ? a.imap.pad : 0;
+  const int u_hi = a.imap.ext < a.imap.L + a.imap.pad ? a.imap.ext : a.imap.L + a.imap.pad;
+  const int n_units = (int)a.n_units, R = (int)a.R, Rk = (int)a.Rk, nsx = R / Rk;  // (host: n_units < 2^31)
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int bs = unit % a.nbs;
+    const int gr = unit / a.nbs;
+    // lines of the other axis: when that axis is segmented (Rk < R) the segments sharing kernel line rk run back to
+    // back, so the kernel-spectrum slice of (g, rk) is read from HBM once and from L2 afterwards
+    int r, rk, g;
+    if (nsx == 1) {
+      g = gr / R;
+      r = rk = gr - g * R;
+    } else {
+      const int t = gr / nsx;
+      g = t / Rk;
+      rk = t - g * Rk;
+      r = (gr - t * nsx) * Rk + rk;
+    }
+    const int it0 = bs * NP;
+    // ---- phase 1: forward transform of every (pair item, input channel) line of this bin
+#pragma unroll 1
+    for (int tk = w; tk < CI * NP; tk += W) {  // warp-uniform
+      const int pg = tk / CI, i = tk - pg * CI;
+      fc_c2* line0 = xy + (size_t)(pg * CI + i) * N;
+      fc_c2 v[1][E];
+      const int item = it0 + pg;
+      const bool active = item < a.n_items;
+      const int it = active ? item : it0;
+      const int bp = PLAIN ? it : it / a.n_seg, sg = PLAIN ? 0 : it - bp * a.n_seg;
+      const fc_c2* src = a.xin + (((int64_t)bp * a.Cin + g * CI + i) * R + r) * a.n_in;
+      if (PLAIN) {
+#pragma unroll
+        for (int q = 0; q < E; ++q) v[0][q] = active ? c2_ld_stream(src + lane + 32 * q) : c2_zero();
+      } else if (simple_in) {
+        const int ub = sg * a.seg_V - a.seg_off + lane;
+        src -= a.imap.pad;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const int u = ub + 32 * q;
+          v[0][q] = (active && u >= u_lo && u < u_hi) ? c2_ldg(src + u) : c2_zero();
+        }
+      } else {
+        const int ub = sg * a.seg_V - a.seg_off + lane;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          const int s = fc_imap_src(a.imap, ub + 32 * q);
+          v[0][q] = (active && s >= 0) ? c2_ldg(src + s) : c2_zero();
+        }
+      }
+      fc_pfft<N, 32, 1, N>(v, line0, a.tw, a.tw_len, lane);  // the line itself is the exchange buffer
+#pragma unroll
+      for (int q = 0; q < E; ++q) line0[lane + 32 * q] = v[0][q];
+    }
+    fc_named_bar_sync(1, W * 32);
+    // ---- L2 prefetch for the unit that runs `prefetch_dist` units later (the next wave on this SM)
+    if (a.prefetch_dist > 0) {
+      const int un = unit + a.prefetch_dist;
+      if (un < n_units) {
+        const int bsn = un % a.nbs;
+        const int grn = un / a.nbs;
+        int rn, rkn, gn;
+        if (nsx == 1) {
+          gn = grn / R;
+          rn = rkn = grn - gn * R;
+        } else {
+          const int t = grn / nsx;
+          gn = t / Rk;
+          rkn = t - gn * Rk;
+          rn = (grn - t * nsx) * Rk + rkn;
+        }
+        if (a.n_seg == 1) {  // (segments of one batch pair share their input line: nothing to pull ahead)
+          const int per_line = (a.n_in * 16 + 127) / 128;  // 128-byte lines per input pair line
+          for (int idx = tid; idx < NP * CI * per_line; idx += W * 32) {
+            const int ln = idx / per_line, seg = idx - ln * per_line;
+            const int pl = ln / CI, i = ln - pl * CI;
+            if (bsn * NP + pl < a.BP)
+              fc_prefetch_l2(a.xin + (((int64_t)(bsn * NP + pl) * a.Cin + gn * CI + i) * a.R + rn) * a.n_in + seg * 8);
+          }
+        }
+        if (bsn == 0) {  // and, once per bin, its slice of the kernel spectrum (one contiguous block)
+          const float2* ks = a.kspec + ((int64_t)gn * a.Rk + rkn) * ((int64_t)CI * CI * N);
+          for (int idx = tid; idx < CI * CI * (N / 16); idx += W * 32) fc_prefetch_l2(ks + idx * 16);
+        }
+      }
+    }
+    // ---- phase 2: per-bin contraction over the input channels of the group, in place (X -> Y)
+    fc_pair_contract<N, CI, NP, W>(xy, a, g, rk, tid);
+    fc_named_bar_sync(1, W * 32);
+    // ---- phase 3: inverse transform of every (pair item, output channel) line, crop / stride on store
+#pragma unroll 1
+    for (int tk = w; tk < CI * NP; tk += W) {  // warp-uniform
+      const int pg = tk / CI, o = tk - pg * CI;
+      const int item = it0 + pg;
+      fc_c2* line0 = xy + (size_t)(pg * CI + o) * N;
+      fc_c2 v[1][E];
+#pragma unroll
+      for (int q = 0; q < E; ++q) v[0][q] = c2_swap(line0[lane + 32 * q]);
+      FC_SYNCWARP();  // the line becomes the exchange buffer: every lane must have read its inputs
+      fc_pfft<N, 32, 1, N>(v, line0, a.tw, a.tw_len, lane);
+      if (PLAIN) {
+        if (item < a.n_items) {  // PLAIN: items are batch pairs
+          fc_c2* dst = a.yout + (((int64_t)item * a.Cout + g * CI + o) * R + r) * a.n_out;
+#pragma unroll
+          for (int q = 0; q < E; ++q) {
+            const int n = lane + 32 * q;
+            if (n < out_lim) dst[n] = c2_swap(v[0][q]);  // PLAIN: Lout <= lim
+          }
+        }
+      } else {
+        // general crop / stride / lattice map: stage the line in shared memory, then output-driven coalesced stores
+#pragma unroll
+        for (int q = 0; q < E; ++q) line0[lane + 32 * q] = c2_swap(v[0][q]);
+        FC_SYNCWARP();
+        if (item < a.n_items) {
+          const int bp = item / a.n_seg, sg = item - bp * a.n_seg;
+          fc_c2* dst = a.yout + (((int64_t)bp * a.Cout + g * CI + o) * R + r) * a.n_out;
+          // this item owns the dense outputs n in [n_lo, n_hi), i.e. the outputs j with n(j) = (j*os + ob) / og in that
+          // range: a contiguous run of j because n(j) is monotone
+          const int n_lo = sg * a.seg_V, n_hi = n_lo + a.seg_V;
+          const int c_lo = n_lo * om.og - om.ob, c_hi = n_hi * om.og - om.ob;
+          int j_lo = c_lo > 0 ? (c_lo + om.os - 1) / om.os : 0;
+          int j_hi = c_hi > 0 ? (c_hi + om.os - 1) / om.os : 0;
+          if (j_hi > om.Lout) j_hi = om.Lout;
+          const fc_c2* ln = line0 + (a.seg_off - n_lo);
+#pragma unroll 4
+          for (int j = j_lo + lane; j < j_hi; j += 32) {
+            const int tt = j * om.os + om.ob;
+            const int n = om.og == 1 ? tt : om.og == 2 ? (tt >> 1) : tt / om.og;
+            dst[j] = (tt == n * om.og && n < om.lim) ? ln[n] : c2_zero();
+          }
+        }
+      }
+    }
+    fc_named_bar_sync(1, W * 32);
+  }
+}

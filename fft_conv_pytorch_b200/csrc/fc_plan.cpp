@@ -10,6 +10,7 @@
 //   * stride/dilation lattices with a common factor g are reduced by g (polyphase): only the populated
 //     lattice is transformed, the remaining outputs are bias only.
 #include "fc_plan.h"
+#include "fc_tune.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -68,9 +69,9 @@ void finish_pass(fc_pass& p) {
   int budget = rfast ? 2048 : 4096;
   if (rfast && 16 * p.M > budget) budget = 16 * p.M;
   if (budget > 8192) budget = 8192;
-  static const int env_flat = std::getenv("FFTCONV_B200_TILE_FLAT") ? std::atoi(std::getenv("FFTCONV_B200_TILE_FLAT")) : 0;  // experiments
+  static const int env_flat = fc_tune_int("TILE_FLAT", 0);  // experiments
   if (!rfast && env_flat > 0) budget = env_flat;
-  static const int env_rfast = std::getenv("FFTCONV_B200_TILE_RFAST") ? std::atoi(std::getenv("FFTCONV_B200_TILE_RFAST")) : 0;  // experiments
+  static const int env_rfast = fc_tune_int("TILE_RFAST", 0);  // experiments
   if (rfast && env_rfast > 0) budget = env_rfast;
   if (p.M > budget) budget = p.M;
   int T = 1;
@@ -476,12 +477,12 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   if (P.padding_mode < 0 || P.padding_mode > 3) return fail(FC_EINVAL, "unknown padding_mode");
   if (P.transposed && P.padding_mode != FC_PAD_CONSTANT) return fail(FC_EINVAL, "fft_conv_transpose has no padding_mode");
   pl->nd = nd;
-  static const int env_threads = std::getenv("FFTCONV_B200_THREADS") ? std::atoi(std::getenv("FFTCONV_B200_THREADS")) : 0;  // experiments
+  static const int env_threads = fc_tune_int("THREADS", 0);  // experiments
   pl->threads = P.threads > 0 ? P.threads : env_threads > 0 ? env_threads : 256;
   if (pl->threads % 32 || pl->threads > 1024) return fail(FC_EINVAL, "threads must be a multiple of 32, <= 1024");
   const bool poly = !(P.flags & FC_FLAG_NO_POLYPHASE);
   const int Ig_ = P.cin / P.groups, Og_ = P.cout / P.groups;
-  static const char* env_seg = std::getenv("FFTCONV_B200_SEG");  // experiments: "Ny,Nx" forces the segment lengths (0 = automatic)
+  static const char* env_seg = fc_tune_str("SEG");  // experiments: "Ny,Nx" forces the segment lengths (0 = automatic)
   int force_seg[2] = {0, 0};
   if (env_seg) std::sscanf(env_seg, "%d,%d", &force_seg[0], &force_seg[1]);
   // segments need the fused axis kernel (fc_plan_build_program: fuse_mid)
@@ -767,7 +768,24 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   I.algo_bytes_s2 = 4 * (int64_t)P.cout * Ig * k_vol + I.kspec_bytes;
   I.algo_bytes_s3 = I.xspec_bytes + I.kspec_bytes + I.yspec_bytes;
   I.algo_bytes_s4 = I.yspec_bytes + 4 * I.out_elems + 4 * (int64_t)P.cout;
+  pl->pair = 0;
   fc_plan_build_program(pl);
+  if (pl->pair) {
+    // The packed batch-pair kernels keep both spectra as 16-byte slots {re0, re1, im0, im1} of the batch items 2p and
+    // 2p + 1: an odd batch is rounded up to whole pairs. (The tensor-core operands never coexist with a fused program.)
+    const int64_t bp2 = 2 * (int64_t)((P.batch + 1) / 2);
+    I.xspec_bytes = I.xspec_bytes / P.batch * bp2;
+    I.yspec_bytes = I.yspec_bytes / P.batch * bp2;
+    // K1p writes and K4p reads the scratch buffers in the pair layout as well (whole pairs there too)
+    sA = (sA + P.batch - 1) / P.batch * bp2;
+    sB = (sB + P.batch - 1) / P.batch * bp2;
+    pl->scratch_bytes = sA + sB;
+    pl->off_yspec = align_up(pl->off_xspec + I.xspec_bytes, 256);
+    pl->off_sA = align_up(pl->off_yspec + I.yspec_bytes, 256);
+    pl->off_sB = align_up(pl->off_sA + sA, 256);
+    I.workspace_bytes = align_up(pl->off_sB + sB, 256) + 256;
+    I.kspec_workspace_bytes = I.workspace_bytes;
+  }
   if (I.fused) {
     // The fused axis kernel reads the kernel spectrum bin-major: [group][line r][o_local][i][n], i.e. the Og*Ig channel
     // pairs of one (group, line) are adjacent lines (fc_fused_contract). The last pass of the kernel program writes it.
@@ -779,7 +797,8 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     k.out_rs = OI * Nl;
   }
   if (I.segments > 1 && !I.fused) return fail(FC_EUNSUPPORTED, "internal: segmented plan without the fused axis kernel");
-  if (nd == 2 && pl->ax[1].seg_n > 1 && (pl->prog.front().type != FC_L_FAST_R2C || pl->prog.back().type != FC_L_FAST_C2R))
+  if (nd == 2 && pl->ax[1].seg_n > 1 && !((pl->prog.front().type == FC_L_FAST_R2C && pl->prog.back().type == FC_L_FAST_C2R) ||
+                                       (pl->prog.front().type == FC_L_PAIR_R2C && pl->prog.back().type == FC_L_PAIR_C2R)))
     return fail(FC_EUNSUPPORTED, "internal: segmented rows without the transposing row kernels");
   return FC_OK;
 }
@@ -961,7 +980,7 @@ void fc_plan_build_program(fc_plan* pl) {
       L.fused.plain = im.mode == FC_PAD_CONSTANT && im.pad == 0 && im.up == 1 && im.sub == 1 && im.L >= fs.pass.N && im.ext >= fs.pass.N &&
                       om.og == 1 && om.os == 1 && om.ob == 0 && om.Lout <= om.lim && Ig == L.fused.ci && Og == L.fused.ci && L.fused.n_seg == 1;
     }
-    if (const char* tune = std::getenv("FFTCONV_B200_TUNE")) {  // A/B timing knobs: "nb=1,warps=4"
+    if (const char* tune = fc_tune_str("TUNE")) {  // A/B timing knobs: "nb=1,warps=4"
       const char* q;
       if (L.fused.ci == 8) {
       if ((q = std::strstr(tune, "nb="))) L.fused.nb = std::atoi(q + 3) >= 2 && fs.pass.N <= 512 && items >= 2 ? 2 : 1;
@@ -1050,6 +1069,43 @@ void fc_plan_build_program(fc_plan* pl) {
   }
   pl->info.n_launches = (int)pl->prog.size();
   pl->info.fused = fuse_mid ? 1 : 0;
+
+  // ---- packed batch pairs (fc_pair.cuh): the whole fused 2-d program K1 -> KB -> K4 on 16-byte slots
+  pl->pair = 0;
+  if (fuse_mid && !(flags & FC_FLAG_NO_PAIR) && pl->prog.size() == 3 && pl->prog[0].type == FC_L_FAST_R2C && pl->prog[2].type == FC_L_FAST_C2R &&
+      !pl->use_tc) {
+    fc_launch& A = pl->prog[0];
+    fc_launch& Bk = pl->prog[1];
+    fc_launch& C = pl->prog[2];
+    const int N = Bk.fused.N;
+    auto pair_len = [](int M) { return M == 128 || M == 256 || M == 512 || M == 1024; };
+    const bool ok = Ig == Og && (Ig == 8 || Ig == 16) && pair_len(A.pass.M) && pair_len(C.pass.M) && (int64_t)N * Ig * 16 <= 128 * 1024;
+    if (ok) {
+      pl->pair = 1;
+      const int BP = (P.batch + 1) / 2;
+      auto retile_pair = [&](fc_pass& p, int channels) {
+        const int T = fc_pair_tile_lines(p.M);
+        p.T = T;
+        p.log2T = ilog2(T);
+        p.n_outer = (int64_t)BP * channels;
+        p.tiles_per_outer = (p.R + T - 1) / T * p.seg_n;
+        p.n_tiles = p.tiles_per_outer * p.n_outer;
+      };
+      A.type = FC_L_PAIR_R2C;
+      retile_pair(A.pass, P.cin);
+      A.name = "pair_r2c_N" + std::to_string(A.pass.N);
+      Bk.type = FC_L_PAIR_FUSED;
+      const int64_t items = (int64_t)BP * Bk.fused.n_seg;
+      Bk.fused.ci = Ig;
+      Bk.fused.nb = (N * Ig <= 2048 && items >= 2) ? 2 : 1;  // pair items per CTA
+      Bk.fused.warps = 8;
+      Bk.fused.occ = (int64_t)Bk.fused.nb * N * Ig * 16 <= 64 * 1024 ? 2 : 1;
+      Bk.name = "pair_fused_N" + std::to_string(N) + (Bk.fused.n_seg > 1 ? "_seg" + std::to_string(Bk.fused.n_seg) : "");
+      C.type = FC_L_PAIR_C2R;
+      retile_pair(C.pass, P.cout);
+      C.name = "pair_c2r_N" + std::to_string(C.pass.N);
+    }
+  }
 }
 
 std::string fc_plan_to_string(const fc_plan* pl) {

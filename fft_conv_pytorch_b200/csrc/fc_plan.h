@@ -18,6 +18,11 @@ enum {
 // Lines per tile of the transposing fast kernels K1 / K4 (must match the instantiations in fc_api.cu).
 inline int fc_fast_tile_lines(int M) { return M >= 256 ? 16 : 4096 / M; }
 
+// The pair pipeline (fc_pair.cuh): pair lines per warp group and per tile of K1p / K4p (must match the instantiations
+// in fc_api.cu: 8 warps per CTA).
+inline int fc_pair_nlp(int M) { return M <= 256 ? 2 : 1; }
+inline int fc_pair_tile_lines(int M) { return fc_pair_nlp(M) * 8 * (M >= 256 ? 1 : 256 / M); }
+
 struct fc_step {
   fc_pass pass;
   int src;  // FC_BUF_*
@@ -25,7 +30,8 @@ struct fc_step {
 };
 
 // One kernel launch of fc_conv.
-enum { FC_L_PASS = 0, FC_L_FAST_R2C = 1, FC_L_FAST_C2R = 2, FC_L_CONTRACT = 3, FC_L_FUSED = 4, FC_L_TC_X = 5, FC_L_TC_GEMM = 6, FC_L_TC_Y = 7, FC_L_FAST_C2C = 8, FC_L_COL_R2C = 9, FC_L_COL_C2R = 10, FC_L_PLANE_FWD = 11, FC_L_PLANE_INV = 12 };
+enum { FC_L_PASS = 0, FC_L_FAST_R2C = 1, FC_L_FAST_C2R = 2, FC_L_CONTRACT = 3, FC_L_FUSED = 4, FC_L_TC_X = 5, FC_L_TC_GEMM = 6, FC_L_TC_Y = 7, FC_L_FAST_C2C = 8, FC_L_COL_R2C = 9, FC_L_COL_C2R = 10, FC_L_PLANE_FWD = 11, FC_L_PLANE_INV = 12,
+       FC_L_PAIR_R2C = 13, FC_L_PAIR_FUSED = 14, FC_L_PAIR_C2R = 15 };
 
 // Geometry of the fused "last forward axis -> contraction -> first inverse axis" kernel (fc_fused.cuh).
 struct fc_fused_desc {
@@ -99,6 +105,7 @@ struct fc_plan {
   int64_t off_xspec, off_yspec, off_sA, off_sB;
   int64_t off_xtc, off_ytc;  // tensor-core contraction operands (use_tc)
   int use_tc;
+  int pair;  // 1: fc_conv runs the packed batch-pair kernels (fc_pair.cuh); the spectrum buffers hold ceil(B/2) pair images per channel
   int64_t scratch_bytes;
 };
 

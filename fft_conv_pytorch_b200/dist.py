@@ -24,10 +24,13 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
     """Broadcast weight/bias from `src` so every rank convolves with the same kernel."""
     if not (dist.is_available() and dist.is_initialized()):
         return
-    for p in module.parameters():
-        dist.broadcast(p.data, src=src)
-        # in-place update of the storage: bump the version so a cached kernel spectrum is rebuilt
-        p.data.add_(0)
+    with torch.no_grad():
+        for p in module.parameters():
+            dist.broadcast(p.detach(), src=src)
+            # The collective writes the storage without touching the version counter the spectrum cache checks
+            # (and `p.data` has a counter of its own, so an edit through it would not either): an in-place op on a
+            # detached alias shares the parameter's counter and invalidates a spectrum cached before the broadcast.
+            p.detach().add_(0)
 
 
 def broadcast_kernel_spectrum(entry, kernel: torch.Tensor, device: torch.device, src: int = 0) -> torch.Tensor:

@@ -33,11 +33,19 @@ _lock = threading.RLock()
 _plans: "OrderedDict[tuple, _PlanEntry]" = OrderedDict()
 _PLAN_CACHE_MAX = 64
 _kspec_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
-_KSPEC_CACHE_MAX_BYTES = 64 << 30
 _kspec_cache_bytes = 0
+_kspec_cap = {}  # device index -> byte cap of the spectrum cache (a quarter of the device memory)
 _launch_counter = 0  # kernels queued by this module (bench.py reports it)
-# FC_FLAG_* bits OR-ed into every plan (A/B timing of the specialised kernels: 1 = generic kernels only)
-_DEFAULT_FLAGS = int(os.environ.get("FFTCONV_B200_FLAGS", "0"))
+# FC_FLAG_* bits OR-ed into every plan (set_default_flags: A/B timing of the specialised kernels, 1 = generic kernels only)
+_DEFAULT_FLAGS = 0
+
+
+def set_default_flags(flags: int) -> int:
+    """OR `flags` (FC_FLAG_*) into every plan created from now on; returns the previous value. For tests and A/B
+    timing; no environment variable is consulted anywhere in the call path."""
+    global _DEFAULT_FLAGS
+    old, _DEFAULT_FLAGS = _DEFAULT_FLAGS, int(flags)
+    return old
 
 
 def launches() -> int:
@@ -49,17 +57,20 @@ class _PlanEntry:
 
     def __init__(self, plan: L.Plan):
         self.plan = plan
-        self.const = {}  # device index -> uint8 tensor
+        self.const = {}  # device index -> (uint8 tensor, (event, stream) of the fill)
 
     def const_for(self, device: torch.device) -> Tensor:
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        t = self.const.get(idx)
-        if t is None:
-            lib = self.plan.lib
-            t = torch.empty(int(self.plan.info.const_bytes), dtype=torch.uint8, device=device)
-            stream = torch.cuda.current_stream(device).cuda_stream
-            L.check(lib, lib.fc_plan_init_const(self.plan.handle, ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(stream)), "fc_plan_init_const")
-            self.const[idx] = t
+        hit = self.const.get(idx)
+        if hit is not None:
+            return _serve_spectrum(hit[0], hit[1], device)
+        lib = self.plan.lib
+        t = torch.empty(int(self.plan.info.const_bytes), dtype=torch.uint8, device=device)
+        cur = torch.cuda.current_stream(device)
+        L.check(lib, lib.fc_plan_init_const(self.plan.handle, ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(cur.cuda_stream)), "fc_plan_init_const")
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.const[idx] = (t, (ev, cur.cuda_stream))
         return t
 
 
@@ -96,8 +107,39 @@ def get_plan(
         e = _PlanEntry(L.Plan(L.load(), prob))
         _plans[key] = e
         while len(_plans) > _PLAN_CACHE_MAX:
-            _plans.popitem(last=False)
+            _, old = _plans.popitem(last=False)
+            _drop_plan_spectra(old.plan)
         return e
+
+
+def _drop_plan_spectra(plan) -> None:
+    """An evicted plan takes its cached kernel spectra with it (they are laid out for that plan only)."""
+    with _lock:
+        for k in [k for k, v in _kspec_cache.items() if v[4] is plan]:
+            _drop_kspec(k)
+
+
+def _kspec_cache_cap(dev_idx: int) -> int:
+    cap = _kspec_cap.get(dev_idx)
+    if cap is None:
+        try:
+            cap = int(torch.cuda.get_device_properties(dev_idx).total_memory) // 4
+        except Exception:
+            cap = 8 << 30
+        _kspec_cap[dev_idx] = cap
+    return cap
+
+
+def _serve_spectrum(spec: Tensor, built, device: torch.device) -> Tensor:
+    """A cached spectrum was produced on the stream that was current at its first use; a consumer on another stream
+    waits for that work (one event wait, nothing when the stream is the same)."""
+    ev, stream_id = built
+    if ev is None:
+        return spec
+    cur = torch.cuda.current_stream(device)
+    if cur.cuda_stream != stream_id and not torch.cuda.is_current_stream_capturing():
+        cur.wait_event(ev)
+    return spec
 
 
 def clear_caches(plans: bool = True) -> None:
@@ -131,21 +173,24 @@ def kernel_spectrum(entry: _PlanEntry, kernel: Tensor, device: torch.device, use
     global _kspec_cache_bytes, _launch_counter
     plan = entry.plan
     dev_idx = device.index if device.index is not None else (torch.cuda.current_device() if device.type == "cuda" else -1)
+    # id(plan) alone could be recycled for a later plan once this one is evicted and freed: the entry therefore holds
+    # the plan itself (so the id stays taken while the entry lives) and a hit also requires `hit_plan is plan`
     key = (id(plan), id(kernel), dev_idx)
     if use_cache:
         with _lock:
             hit = _kspec_cache.get(key)
             if hit is not None:
-                ref, ver, ptr, spec = hit
-                if ref() is kernel and ver == kernel._version and ptr == kernel.data_ptr():
+                ref, ver, ptr, spec, hit_plan, built = hit
+                if hit_plan is plan and ref() is kernel and ver == kernel._version and ptr == kernel.data_ptr():
                     _kspec_cache.move_to_end(key)
-                    return spec
+                    return _serve_spectrum(spec, built, device)
                 _drop_kspec(key)
     lib = plan.lib
     const = entry.const_for(device)
     kspec = torch.empty(int(plan.info.kspec_bytes) // 4, dtype=torch.float32, device=device)
     ws = torch.empty(int(plan.info.kspec_workspace_bytes), dtype=torch.uint8, device=device)
-    stream = torch.cuda.current_stream(device).cuda_stream
+    cur = torch.cuda.current_stream(device)
+    stream = cur.cuda_stream
     w = kernel.detach().to(device=device).contiguous()
     L.check(lib, lib.fc_kernel_spectrum(plan.handle, _ptr(const), _ptr(w), _ptr(kspec), _ptr(ws), ctypes.c_void_p(stream)), "fc_kernel_spectrum")
     _launch_counter += int(plan.info.n_launches_kspec)
@@ -155,9 +200,12 @@ def kernel_spectrum(entry: _PlanEntry, kernel: Tensor, device: torch.device, use
                 ref = weakref.ref(kernel, lambda _r, k=key: _drop_kspec(k))
             except TypeError:
                 return kspec
-            _kspec_cache[key] = (ref, kernel._version, kernel.data_ptr(), kspec)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            _kspec_cache[key] = (ref, kernel._version, kernel.data_ptr(), kspec, plan, (ev, stream))
             _kspec_cache_bytes += kspec.numel() * 4
-            while _kspec_cache_bytes > _KSPEC_CACHE_MAX_BYTES and len(_kspec_cache) > 1:
+            cap = _kspec_cache_cap(dev_idx)
+            while _kspec_cache_bytes > cap and len(_kspec_cache) > 1:
                 _drop_kspec(next(iter(_kspec_cache)))
     return kspec
 
@@ -174,7 +222,13 @@ def install_kernel_spectrum(entry: _PlanEntry, kernel: Tensor, device: torch.dev
     with _lock:
         _drop_kspec(key)
         ref = weakref.ref(kernel, lambda _r, k=key: _drop_kspec(k))
-        _kspec_cache[key] = (ref, kernel._version, kernel.data_ptr(), kspec)
+        built = (None, None)
+        if device.type == "cuda":
+            cur = torch.cuda.current_stream(device)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            built = (ev, cur.cuda_stream)
+        _kspec_cache[key] = (ref, kernel._version, kernel.data_ptr(), kspec, plan, built)
         _kspec_cache_bytes += kspec.numel() * 4
 
 
@@ -280,10 +334,13 @@ def _run(transposed: bool, signal: Tensor, kernel: Tensor, bias: Optional[Tensor
                 ev_in.append(e)
         for c in range(n_chunks):
             a0, a1 = bounds[c], bounds[c + 1]
+            # a chunk runs on the kernel spectrum of the full-batch plan, so its plan must choose the same spectrum layout:
+            # the tensor-core layout depends on the batch (<= 32), so a full batch on the SIMT path keeps its chunks there
+            cflags = flags | (0 if int(plan.info.tensor_core) else L.FC_FLAG_NO_TC)
             sub = entry if a1 - a0 == B else get_plan(transposed, a1 - a0, cin, cout, groups, tuple(int(v) for v in signal.shape[2:]),
-                                                      tuple(int(v) for v in kernel.shape[2:]), stride_, padding_, dilation_, opad_, padding_mode, flags)
+                                                      tuple(int(v) for v in kernel.shape[2:]), stride_, padding_, dilation_, opad_, padding_mode, cflags)
             sp = sub.plan
-            if (sp.fft_size, int(sp.info.segments), int(sp.info.kspec_bytes)) != (plan.fft_size, int(plan.info.segments), int(plan.info.kspec_bytes)):
+            if _kspec_layout(sp) != _kspec_layout(plan):
                 raise RuntimeError("internal: the plan of a batch chunk does not share the kernel-spectrum layout of the full-batch plan")
             cur.wait_event(ev_in[c])
             L.check(lib, lib.fc_conv(sp.handle, _ptr(sub.const_for(dev)), ctypes.c_void_p(x_stage[a0:a1].data_ptr()), _ptr(kspec), _ptr(b_dev),
@@ -302,7 +359,13 @@ def _run(transposed: bool, signal: Tensor, kernel: Tensor, bias: Optional[Tensor
         return y_host
 
 
-_HOST_PIPELINE_CHUNKS = int(os.environ.get("FFTCONV_B200_HOST_CHUNKS", "6"))
+_HOST_PIPELINE_CHUNKS = 6  # batch chunks of the host-buffer pipeline (see _chunk_bounds)
+
+
+def _kspec_layout(plan) -> tuple:
+    """What two plans must agree on to share one kernel spectrum."""
+    i = plan.info
+    return (plan.fft_size, int(i.segments), int(i.kspec_bytes), int(i.tensor_core), int(i.fused))
 
 
 def _chunk_bounds(B: int, n_chunks: int):

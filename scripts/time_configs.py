@@ -43,7 +43,13 @@ def timeit(fn, n, flush):
 
 
 def main():
-    only = sys.argv[1:] or [k for k in CFG if k != "c5_full"]
+    argv = sys.argv[1:]
+    tag = ""
+    if argv and argv[0].startswith("--flags="):  # FC_FLAG_* bits OR-ed into every plan (A/B runs), e.g. --flags=256: no batch pairs
+        Fn.set_default_flags(int(argv[0].split("=")[1]))
+        tag = "_flags" + argv[0].split("=")[1]
+        argv = argv[1:]
+    only = argv or [k for k in CFG if k != "c5_full"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     out = {}
     for name in only:
@@ -109,7 +115,7 @@ def main():
             r["kernels_error"] = repr(e)[:200]
         Fn.clear_caches()
         torch.cuda.empty_cache()
-        if os.environ.get("FFTCONV_B200_CTILE") or os.environ.get("FFTCONV_SKIP_REF"):
+        if os.environ.get("FFTCONV_SKIP_REF"):
             out[name] = r
             print(name, json.dumps(r), flush=True)
             continue
@@ -133,7 +139,7 @@ def main():
         del x, w, b
         torch.cuda.empty_cache()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "time_configs.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"time_configs{tag}.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -50,7 +50,7 @@ void fc_emul_launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bo
   fc_emul_smem = nullptr;
 }
 
-// ---- named barrier stand-in (see fc_async.cuh)
+// ---- named barrier stand-in (see fc_kernels.cuh)
 namespace {
 std::mutex g_named_m;
 std::map<std::pair<int, int>, std::unique_ptr<std::barrier<>>> g_named;
