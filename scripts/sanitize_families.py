@@ -27,11 +27,11 @@ CASES = [
     ("generic_2d", (2, 3, 40, 36), (4, 3, 5, 3), False, dict(padding=1), L.FC_FLAG_NO_FUSED),
     ("k1k4_group_c2c_contract", (4, 8, 100, 100), (8, 8, 7, 7), False, {}, L.FC_FLAG_NO_PAIR),
     ("fused_plain", (2, 8, 256, 256), (8, 8, 9, 9), False, {}, L.FC_FLAG_NO_PAIR),
-    ("fused_general_seg", (2, 16, 300, 300), (16, 8, 9, 9), True, dict(stride=2, dilation=2, groups=2, padding=2), L.FC_FLAG_NO_PAIR),
+    ("fused_general_seg", (1, 16, 560, 560), (16, 8, 9, 9), True, dict(stride=2, dilation=2, groups=2, padding=2), L.FC_FLAG_NO_PAIR),
     ("pair_plain", (4, 8, 256, 256), (8, 8, 9, 9), False, {}, 0),
-    ("pair_general_odd_batch", (3, 8, 200, 180), (8, 8, 5, 7), False, dict(padding=(2, 3)), 0),
-    ("pair_seg_lattice", (2, 32, 300, 300), (32, 16, 9, 9), True, dict(stride=2, dilation=2, groups=2, padding=2), 0),
-    ("pair_long_rows", (2, 8, 200, 1500), (8, 8, 5, 33), False, {}, 0),
+    ("pair_general_odd_batch", (3, 8, 200, 180), (8, 8, 5, 7), False, dict(padding=(1, 2)), 0),
+    ("pair_seg_lattice", (2, 32, 560, 560), (32, 16, 9, 9), True, dict(stride=2, dilation=2, groups=2, padding=2), 0),
+    ("pair_long_rows", (2, 8, 200, 1700), (8, 8, 5, 301), False, {}, 0),
     ("plane_3d", (2, 8, 40, 40, 40), (8, 8, 5, 5, 5), False, {}, 0),
     ("column_1d", (2, 4, 40000), (4, 4, 129), False, {}, 0),
     ("c2c_1d_segments", (1, 8, 32768), (8, 8, 1025), False, {}, 0),
