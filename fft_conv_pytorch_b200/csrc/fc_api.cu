@@ -110,7 +110,7 @@ thread_local int g_num_sms = 148;  // SM count of the calling thread's current d
 #define FC_PAIR_ROW_ALL(X) X(128, 1, 8, 4) X(128, 2, 8, 2) X(256, 1, 8, 4) X(256, 2, 8, 2) X(512, 1, 8, 2) X(1024, 1, 8, 1)
 #define FC_PAIR_FUSED_ALL(X) \
   X(256, 8, 2, 8, true, 2) X(256, 8, 2, 8, false, 2) X(256, 8, 1, 8, true, 2) X(256, 8, 1, 8, false, 2) \
-  X(512, 8, 1, 8, true, 2) X(512, 8, 1, 8, false, 2) X(1024, 8, 1, 8, true, 1) X(1024, 8, 1, 8, false, 1) \
+  X(512, 8, 1, 8, true, 2) X(512, 8, 1, 8, false, 2) X(512, 8, 1, 8, true, 3) X(512, 8, 1, 4, true, 3) X(512, 8, 2, 16, true, 1) X(512, 8, 2, 16, false, 1) X(1024, 8, 1, 8, true, 1) X(1024, 8, 1, 8, false, 1) \
   X(256, 16, 1, 8, true, 2) X(256, 16, 1, 8, false, 2) X(512, 16, 1, 8, true, 1) X(512, 16, 1, 8, false, 1)
 
 void fused_set_attr() {
@@ -664,12 +664,22 @@ int launch_pair_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in,
   a.n_units = (int64_t)P.groups * f.R * a.nbs;
   a.imap = f.imap;
   a.omap = f.omap;
+  {
+    static const int kpf = fc_tune_int("KPF", 0);
+    a.k_pf = kpf;
+    static const int abl = fc_tune_int("ABL", 0);
+    a.abl = abl;
+    static const int dns = fc_tune_int("DESYNC", 0);
+    a.desync_ns = dns;
+    a.desync_mod = g_num_sms;
+  }
   const size_t smem = (size_t)f.nb * f.ci * f.N * sizeof(fc_c2);
   {  // distance (in units) to the CTA of the next wave on the same SM: what this CTA prefetches into L2
     int64_t per_sm = (int64_t)(228 * 1024) / (int64_t)(smem + 1024 + 256);
     if (per_sm > f.occ) per_sm = f.occ;
     if (per_sm < 1) per_sm = 1;
     a.prefetch_dist = (int)(g_num_sms * per_sm);
+    a.desync_grp = (int)per_sm;
   }
   int64_t grid = a.n_units;
   const int64_t cap = (int64_t)g_num_sms * 16;

@@ -295,7 +295,12 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
         li.in_base = o * p.in_os + r * p.in_rs;
       }
       // (bin-major kernel spectrum of the fused plans: outer items split into groups of out_oq, see fc_types.h)
-      li.out_base = (p.out_oq > 0 ? (o / p.out_oq) * p.out_osA + (o % p.out_oq) * p.out_os : o * p.out_os) + r * p.out_rs;
+      if (p.out_oq > 0) {
+        const int64_t q = o % p.out_oq;
+        li.out_base = (o / p.out_oq) * p.out_osA + (p.out_il > 1 ? (q / p.out_il) * p.out_il * p.out_os + q % p.out_il : q * p.out_os) + r * p.out_rs;
+      } else {
+        li.out_base = o * p.out_os + r * p.out_rs;
+      }
       li.r = r;
       li.valid = valid;
       li.bias_idx = (int)(o % (p.cout > 0 ? p.cout : 1));

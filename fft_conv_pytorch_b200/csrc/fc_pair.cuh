@@ -20,6 +20,8 @@
 // Replaces (reference functional.py) :60-62 / :126-139 (padding, zero-stuffing: gather maps), :70 / :157 rfftn of the
 // signal, :73 / :160 complex_matmul, :75 / :162 irfftn, :76-87 / :163-174 crop, stride, bias.
 #pragma once
+#include <type_traits>
+
 #include "fc_fused.cuh"
 
 // ------------------------------------------------------------------------------------------------ packed pairs
@@ -116,6 +118,13 @@ FC_DEV fc_c2 c2_ld_stream(const fc_c2* p) {
   return c2_make(t.x, t.y);
 }
 FC_DEV void c2_st_stream(fc_c2* p, fc_c2 v) { __stcs(reinterpret_cast<ulonglong2*>(p), make_ulonglong2(v.re, v.im)); }
+#endif
+
+#ifdef FC_CPU_EMUL
+FC_DEV void fc_prefetch_l1(const void*) {}
+#else
+// Pull one 128-byte line into L1 (CCTL.E.PF1): no register is tied up and nothing waits for it.
+FC_DEV void fc_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #endif
 
 // XOR swizzle of the slot index inside a pair line. 16-byte accesses are served a quarter warp at a time, so an access
@@ -601,43 +610,103 @@ struct fc_pair_fused_args {
   int32_t n_items;  // BP * n_seg: (batch pair, segment) items per (group, bin); NP of them per unit
   int32_t n_seg, seg_V, seg_off;
   int32_t prefetch_dist;
+  int32_t desync_ns, desync_mod, desync_grp;  // start-up delay of CTA group g = blockIdx / desync_mod of the first wave (g < desync_grp CTAs per SM): g * desync_ns
+  int32_t abl;   // FC_TUNING builds only: phase ablation bits for timing experiments (results are wrong by construction)
+  int32_t k_pf;  // output channels of kernel-spectrum lines the contraction keeps in flight towards L1 ahead of its loads (0: off)
   int64_t R, Rk, n_units;
   fc_imap imap;
   fc_omap omap;
 };
 
+#ifdef FC_TUNING
+#define FC_ABL(a, bit) (((a).abl & (bit)) != 0)
+#else
+#define FC_ABL(a, bit) false
+#endif
+
 // Per-bin contraction over the CI input channels of the group, in place (X -> Y) in the CTA's pair lines. A thread
-// owns one bin of one pair item: the CI signal values (CI slots -> 4*CI registers) are loaded once, every kernel value
-// is the broadcast operand of 4 FFMA2 (two complex multiply-accumulates), and the four partial sums per output channel
-// are independent chains. The loop over output channels is unrolled: every kernel-spectrum load is the thread's base
-// pointer plus a compile-time offset and ptxas hoists the loads of the following channels above the FFMA2s of this one.
-template <int N, int CI, int NP, int W>
-FC_DEV void fc_pair_contract(fc_c2* xy, const fc_pair_fused_args& a, int g, int rk, int tid) {
-  for (int idx = tid; idx < N * NP; idx += W * 32) {
-    const int n = idx & (N - 1), pg = idx / N;
-    fc_c2* xb = xy + (size_t)(pg * CI) * N + n;  // line (pg, c) at xy + (pg*CI + c)*N
-    fc_c2 x[CI];
+// owns one bin of IPT pair items: the signal values (CI slots -> 4*CI registers per item) are loaded once, every kernel
+// value is the broadcast operand of 4 FFMA2 per item (two complex multiply-accumulates), and the four partial sums per
+// output channel are independent chains. The kernel values of two input channels of a bin are adjacent in the
+// spectrum ([o][i/2][n][i%2], fc_pass::out_il): one 16-byte load per channel pair, so the loads the register file
+// can keep in flight carry twice the bytes (this phase is bound by the latency of these loads). The loop over output
+// channels is unrolled: every load is the thread's base pointer plus a compile-time offset and ptxas hoists the loads
+// of the following channels above the FFMA2s of this one. IPT = 2 reads the kernel spectrum once for two pair items.
+#ifndef FC_KPRE
+#define FC_KPRE 8  // kernel-spectrum loads (16 bytes each) a contraction thread issues before the barrier that ends phase 1
+#endif
+
+// The first FC_KPRE kernel-spectrum values of the thread's first bin: requested before the phase barrier, so that their
+// latency runs while the CTA waits for its slowest transform (the registers of the transform are free by then).
+template <int N, int CI, int NP, int IPT, int W>
+FC_DEV void fc_pair_contract_preload(float4 (&kpre)[FC_KPRE > 0 ? FC_KPRE : 1], const fc_pair_fused_args& a, int g, int rk, int tid) {
+  if (FC_KPRE > 0 && tid < N * (NP / IPT)) {
+    const float4* kp = reinterpret_cast<const float4*>(a.kspec + ((int64_t)g * a.Rk + rk) * ((int64_t)CI * CI * N)) + (tid & (N - 1));
 #pragma unroll
-    for (int i = 0; i < CI; ++i) x[i] = xb[(size_t)i * N];
-    const float2* kp = a.kspec + ((int64_t)g * a.Rk + rk) * ((int64_t)CI * CI * N) + n;
-#pragma unroll
-    for (int o = 0; o < CI; ++o) {
-      fc_p2 rr = p2_make(0.f, 0.f), ii = rr, ri = rr, ir = rr;  // sum x.re*k.re, x.im*k.im, x.re*k.im, x.im*k.re
-#pragma unroll
-      for (int i = 0; i < CI; ++i) {
-        const float2 k = __ldg(kp + (o * CI + i) * N);
-        rr = p2_fmas(x[i].re, k.x, rr);
-        ii = p2_fmas(x[i].im, k.y, ii);
-        ri = p2_fmas(x[i].re, k.y, ri);
-        ir = p2_fmas(x[i].im, k.x, ir);
-      }
-      xb[(size_t)o * N] = c2_make(p2_sub(rr, ii), p2_add(ri, ir));
-    }
+    for (int j = 0; j < FC_KPRE; ++j) kpre[j] = FC_ABL(a, 2) ? make_float4(1.f, 0.5f, 0.25f, 2.f) : __ldg(kp + j * N);
   }
 }
 
-// N: transform length of the fused axis. CI: channels per group (in and out; full groups only). NP: pair items per CTA.
-// W: warps. PLAIN: identity gather map with all N points stored, a plain crop on store, a single segment.
+template <int N, int CI, int NP, int IPT, int W>
+FC_DEV void fc_pair_contract(fc_c2* xy, const fc_pair_fused_args& a, int g, int rk, int tid, const float4 (&kpre)[FC_KPRE > 0 ? FC_KPRE : 1]) {
+  static_assert(NP % IPT == 0 && CI % 2 == 0, "items per thread divide the items of a CTA; channel pairs");
+  static_assert(FC_KPRE <= CI * CI / 2, "preloaded values are the first ones of a bin");
+  auto body = [&](int idx, auto first) {
+    constexpr bool FIRST = decltype(first)::value;
+    const int n = idx & (N - 1), pg = (idx / N) * IPT;
+    fc_c2* xb = xy + (size_t)(pg * CI) * N + n;  // line (pg + t, c) at xb + ((t*CI + c)*N
+    fc_c2 x[IPT][CI];
+#pragma unroll
+    for (int t = 0; t < IPT; ++t)
+#pragma unroll
+      for (int i = 0; i < CI; ++i) x[t][i] = xb[(size_t)(t * CI + i) * N];
+    const float4* kp = reinterpret_cast<const float4*>(a.kspec + ((int64_t)g * a.Rk + rk) * ((int64_t)CI * CI * N)) + n;
+#pragma unroll
+    for (int o = 0; o < CI; ++o) {
+      if (a.k_pf > 0) {
+        // software prefetch: the lines of output channel o + k_pf (of this thread's next bin once the channels run out)
+        const int on = o + a.k_pf;
+        const float4* pp = on < CI ? kp + on * (CI / 2) * N : kp + (on - CI) * (CI / 2) * N + W * 32;
+        if (on < CI || idx + W * 32 < N * (NP / IPT)) {
+#pragma unroll
+          for (int i2 = 0; i2 < CI / 2; ++i2) fc_prefetch_l1(pp + i2 * N);
+        }
+      }
+      fc_p2 rr[IPT], ii[IPT], ri[IPT], ir[IPT];  // sum x.re*k.re, x.im*k.im, x.re*k.im, x.im*k.re
+#pragma unroll
+      for (int t = 0; t < IPT; ++t) rr[t] = ii[t] = ri[t] = ir[t] = p2_make(0.f, 0.f);
+#pragma unroll
+      for (int i2 = 0; i2 < CI / 2; ++i2) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int j = o * (CI / 2) + i2;
+        float4 k;
+        if (FIRST && j < FC_KPRE)
+          k = kpre[j < FC_KPRE ? j : 0];
+        else
+          k = FC_ABL(a, 2) ? make_float4(1.f, 0.5f, 0.25f, 2.f) : __ldg(kp + j * N);
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) {
+          rr[t] = p2_fmas(x[t][2 * i2].re, k.x, rr[t]);
+          ii[t] = p2_fmas(x[t][2 * i2].im, k.y, ii[t]);
+          ri[t] = p2_fmas(x[t][2 * i2].re, k.y, ri[t]);
+          ir[t] = p2_fmas(x[t][2 * i2].im, k.x, ir[t]);
+          rr[t] = p2_fmas(x[t][2 * i2 + 1].re, k.z, rr[t]);
+          ii[t] = p2_fmas(x[t][2 * i2 + 1].im, k.w, ii[t]);
+          ri[t] = p2_fmas(x[t][2 * i2 + 1].re, k.w, ri[t]);
+          ir[t] = p2_fmas(x[t][2 * i2 + 1].im, k.z, ir[t]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < IPT; ++t) xb[(size_t)(t * CI + o) * N] = c2_make(p2_sub(rr[t], ii[t]), p2_add(ri[t], ir[t]));
+    }
+  };
+  if (tid < N * (NP / IPT)) body(tid, std::true_type());
+  for (int idx = tid + W * 32; idx < N * (NP / IPT); idx += W * 32) body(idx, std::false_type());
+}
+
+// N: transform length of the fused axis. CI: channels per group (in and out; full groups only). NP: pair items per CTA
+// (NP = 2: a contraction thread takes both, reading the kernel spectrum once for four batch items). W: warps. PLAIN: identity gather map with all N points stored, a plain crop on store, a single segment.
 // Shared memory: NP*CI pair lines of N slots; a line is its warp's exchange buffer during the transforms and carries the
 // spectrum in natural order between the phases.
 template <int N, int CI, int NP, int W, bool PLAIN, int OCC>
@@ -654,6 +723,18 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_pair_fused_kernel(fc_pair_fuse
   const int u_lo = a.imap.pad > 0 ? a.imap.pad : 0;
   const int u_hi = a.imap.ext < a.imap.L + a.imap.pad ? a.imap.ext : a.imap.L + a.imap.pad;
   const int n_units = (int)a.n_units, R = (int)a.R, Rk = (int)a.Rk, nsx = R / Rk;  // (host: n_units < 2^31)
+#ifndef FC_CPU_EMUL
+  // The CTAs that share an SM start together and, their units being equal, would run their three phases in lockstep:
+  // load latency, transforms and contraction of both at the same moments. Delaying every second CTA of the first wave
+  // by a fraction of a unit puts one CTA's transforms under the other's kernel-spectrum loads for the rest of the grid.
+  if (a.desync_ns > 0) {
+    const int grp = blockIdx.x / a.desync_mod;
+    if (grp > 0 && grp < a.desync_grp) {
+      const unsigned total = (unsigned)a.desync_ns * (unsigned)grp;
+      for (unsigned waited = 0; waited < total; waited += 1000) __nanosleep(1000);
+    }
+  }
+#endif
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
     const int bs = unit % a.nbs;
     const int gr = unit / a.nbs;
@@ -670,6 +751,12 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_pair_fused_kernel(fc_pair_fuse
       r = (gr - t * nsx) * Rk + rk;
     }
     const int it0 = bs * NP;
+    if (a.k_pf > 0) {  // the kernel-spectrum lines the contraction reads first travel to L1 while the transforms run
+      const float4* kp = reinterpret_cast<const float4*>(a.kspec + ((int64_t)g * a.Rk + rk) * ((int64_t)CI * CI * N)) + (tid & (N - 1));
+      for (int o = 0; o < a.k_pf; ++o)
+#pragma unroll
+        for (int i2 = 0; i2 < CI / 2; ++i2) fc_prefetch_l1(kp + (o * (CI / 2) + i2) * N);
+    }
     // ---- phase 1: forward transform of every (pair item, input channel) line of this bin
 #pragma unroll 1
     for (int tk = w; tk < CI * NP; tk += W) {  // warp-uniform
@@ -683,7 +770,7 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_pair_fused_kernel(fc_pair_fuse
       const fc_c2* src = a.xin + (((int64_t)bp * a.Cin + g * CI + i) * R + r) * a.n_in;
       if (PLAIN) {
 #pragma unroll
-        for (int q = 0; q < E; ++q) v[0][q] = active ? c2_ld_stream(src + lane + 32 * q) : c2_zero();
+        for (int q = 0; q < E; ++q) v[0][q] = (active && !FC_ABL(a, 8)) ? c2_ld_stream(src + lane + 32 * q) : c2_zero();
       } else if (simple_in) {
         const int ub = sg * a.seg_V - a.seg_off + lane;
         src -= a.imap.pad;
@@ -700,10 +787,12 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_pair_fused_kernel(fc_pair_fuse
           v[0][q] = (active && s >= 0) ? c2_ldg(src + s) : c2_zero();
         }
       }
-      fc_pfft<N, 32, 1, N>(v, line0, a.tw, a.tw_len, lane);  // the line itself is the exchange buffer
+      if (!FC_ABL(a, 1)) fc_pfft<N, 32, 1, N>(v, line0, a.tw, a.tw_len, lane);  // the line itself is the exchange buffer
 #pragma unroll
       for (int q = 0; q < E; ++q) line0[lane + 32 * q] = v[0][q];
     }
+    float4 kpre[FC_KPRE > 0 ? FC_KPRE : 1];
+    fc_pair_contract_preload<N, CI, NP, NP, W>(kpre, a, g, rk, tid);
     fc_named_bar_sync(1, W * 32);
     // ---- L2 prefetch for the unit that runs `prefetch_dist` units later (the next wave on this SM)
     if (a.prefetch_dist > 0) {
@@ -737,7 +826,7 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_pair_fused_kernel(fc_pair_fuse
       }
     }
     // ---- phase 2: per-bin contraction over the input channels of the group, in place (X -> Y)
-    fc_pair_contract<N, CI, NP, W>(xy, a, g, rk, tid);
+    if (!FC_ABL(a, 32)) fc_pair_contract<N, CI, NP, NP, W>(xy, a, g, rk, tid, kpre);
     fc_named_bar_sync(1, W * 32);
     // ---- phase 3: inverse transform of every (pair item, output channel) line, crop / stride on store
 #pragma unroll 1
@@ -749,9 +838,9 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_pair_fused_kernel(fc_pair_fuse
 #pragma unroll
       for (int q = 0; q < E; ++q) v[0][q] = c2_swap(line0[lane + 32 * q]);
       FC_SYNCWARP();  // the line becomes the exchange buffer: every lane must have read its inputs
-      fc_pfft<N, 32, 1, N>(v, line0, a.tw, a.tw_len, lane);
+      if (!FC_ABL(a, 4)) fc_pfft<N, 32, 1, N>(v, line0, a.tw, a.tw_len, lane);
       if (PLAIN) {
-        if (item < a.n_items) {  // PLAIN: items are batch pairs
+        if (item < a.n_items && !FC_ABL(a, 16)) {  // PLAIN: items are batch pairs
           fc_c2* dst = a.yout + (((int64_t)item * a.Cout + g * CI + o) * R + r) * a.n_out;
 #pragma unroll
           for (int q = 0; q < E; ++q) {

@@ -795,6 +795,10 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     k.out_osA = k.R * OI * Nl;
     k.out_os = Nl;
     k.out_rs = OI * Nl;
+    if (pl->pair) {  // [group][line][o][i/2][n][i%2]: the values of two input channels of a bin are adjacent (fc_pair_contract)
+      k.out_il = 2;
+      k.out_es = 2;
+    }
   }
   if (I.segments > 1 && !I.fused) return fail(FC_EUNSUPPORTED, "internal: segmented plan without the fused axis kernel");
   if (nd == 2 && pl->ax[1].seg_n > 1 && !((pl->prog.front().type == FC_L_FAST_R2C && pl->prog.back().type == FC_L_FAST_C2R) ||
@@ -1079,7 +1083,9 @@ void fc_plan_build_program(fc_plan* pl) {
     fc_launch& C = pl->prog[2];
     const int N = Bk.fused.N;
     auto pair_len = [](int M) { return M == 128 || M == 256 || M == 512 || M == 1024; };
-    const bool ok = Ig == Og && (Ig == 8 || Ig == 16) && pair_len(A.pass.M) && pair_len(C.pass.M) && (int64_t)N * Ig * 16 <= 128 * 1024;
+    // default: groups of 8 channels (BASELINE c2; with 16 the one-line kernels measured faster: c5 2.03 vs 2.34 ms)
+    const bool want = (flags & FC_FLAG_PAIR) || Ig == 8;
+    const bool ok = want && Ig == Og && (Ig == 8 || Ig == 16) && pair_len(A.pass.M) && pair_len(C.pass.M) && (int64_t)N * Ig * 16 <= 128 * 1024;
     if (ok) {
       pl->pair = 1;
       const int BP = (P.batch + 1) / 2;
@@ -1100,6 +1106,15 @@ void fc_plan_build_program(fc_plan* pl) {
       Bk.fused.nb = (N * Ig <= 2048 && items >= 2) ? 2 : 1;  // pair items per CTA
       Bk.fused.warps = 8;
       Bk.fused.occ = (int64_t)Bk.fused.nb * N * Ig * 16 <= 64 * 1024 ? 2 : 1;
+      if (const char* t = fc_tune_str("PAIRKB")) {  // tuning builds: "np,warps,occ" (must name an instantiation of fc_api.cu)
+        int np = Bk.fused.nb, wp = 8, oc = Bk.fused.occ;
+        std::sscanf(t, "%d,%d,%d", &np, &wp, &oc);
+        if (np <= items) {
+          Bk.fused.nb = np;
+          Bk.fused.warps = wp;
+          Bk.fused.occ = oc;
+        }
+      }
       Bk.name = "pair_fused_N" + std::to_string(N) + (Bk.fused.n_seg > 1 ? "_seg" + std::to_string(Bk.fused.n_seg) : "");
       C.type = FC_L_PAIR_C2R;
       retile_pair(C.pass, P.cout);

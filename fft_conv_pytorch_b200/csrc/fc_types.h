@@ -79,6 +79,10 @@ struct fc_pass {
   // generic pass only: when out_oq > 0 the output base of outer item o is (o / out_oq)*out_osA + (o % out_oq)*out_os
   // (the bin-major kernel spectrum of the fused plans: the out_oq = Og*Ig channel pairs of a group are adjacent lines)
   int64_t out_oq, out_osA;
+  // ... and when out_il > 1 the out_oq lines of a group are interleaved out_il at a time: line q = o % out_oq starts at
+  // (q / out_il) * out_il * out_os + q % out_il and its elements are out_es = out_il apart (the pair kernels read the
+  // kernel values of two input channels of a bin with one 16-byte load)
+  int64_t out_il;
   // R2C input base: base(o) = ((o/o_c2)/o_q)*o_sA + ((o/o_c2)%o_q)*o_sB + (o%o_c2)*o_sC   (replaces in_os)
   int64_t o_c2, o_q, o_sA, o_sB, o_sC;
   fc_imap imap;

@@ -15,14 +15,15 @@ import numpy as np
 from fft_conv_pytorch_b200 import _lib as L
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libfftconv_emul.so")
+_SO = os.environ.get("FFTCONV_EMUL_SO") or os.path.join(_HERE, "libfftconv_emul.so")  # (a sanitizer build: scripts/emul_sanitize.sh)
 _lib = None
 
 
 def lib():
     global _lib
     if _lib is None:
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+        if not os.environ.get("FFTCONV_EMUL_SO"):
+            subprocess.check_call(["make", "-C", _HERE, "-s"])
         _lib = L.bind(ctypes.CDLL(_SO))
     return _lib
 

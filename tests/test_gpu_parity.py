@@ -508,3 +508,131 @@ def test_module_backward_trains():
     r(x).square().mean().backward()
     assert rel_err(m.weight.grad.cpu().numpy(), r.weight.grad.cpu().numpy()) < TOL
     assert rel_err(m.bias.grad.cpu().numpy(), r.bias.grad.cpu().numpy()) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ round 2 additions
+def _reference_fft_conv():
+    """The unmodified reference (baseline/_ref travels to the GPU box with the snapshot); None when it is absent."""
+    import os
+    import sys
+    import warnings
+
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "fft_conv_pytorch")):
+        return None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    warnings.filterwarnings("ignore")
+    from fft_conv_pytorch.functional import fft_conv as ref_fft_conv
+
+    return ref_fft_conv
+
+
+@pytest.mark.parametrize("name,xs,ws", [("c1", (1, 8, 32768), (8, 8, 1025)), ("c2", (8, 8, 512, 512), (8, 8, 65, 65)),
+                                        ("c3", (4, 8, 64, 64, 64), (8, 8, 17, 17, 17))])
+def test_baseline_c1_c2_c3_against_the_reference_itself(name, xs, ws):
+    """North star: 'max relative error <= 1e-4 against torch's fft_conv and also against direct F.conv': the reference's
+    own fft_conv evaluated in float64 on the same GPU on identical inputs."""
+    ref_fft_conv = _reference_fft_conv()
+    if ref_fft_conv is None:
+        pytest.skip("baseline/_ref is not present")
+    x, w, b = _seeded(xs, ws, ws[0])
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    with torch.no_grad():
+        y = fcp.fft_conv(xd, wd, bd)
+        ref = ref_fft_conv(xd.double(), wd.double(), bd.double())
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < TOL
+
+
+def test_baseline_c4_full_tensor_slice():
+    """c4: every output of the first 8 output channels against cuDNN's direct convolution (fp32, TF32 off)."""
+    x, w, b = _seeded((16, 256, 65536), (256, 256, 4097), 256)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    with torch.no_grad():
+        y = fcp.fft_conv(xd, wd, bd)
+        ref = F.conv1d(xd, wd[:8].contiguous(), bd[:8].contiguous())
+    d = (y[:, :8].double() - ref.double()).abs().max().item() / ref.double().abs().max().item()
+    assert d < TOL, d
+
+
+def test_baseline_c5_full_tensor_one_item():
+    """c5: every output of one batch item against cuDNN's direct transposed convolution (fp32, TF32 off)."""
+    x, w, b = _seeded((4, 64, 1024, 1024), (64, 16, 31, 31), 64)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    with torch.no_grad():
+        y = fcp.fft_conv_transpose(xd, wd, bd, stride=2, dilation=2, groups=4)
+        ref = F.conv_transpose2d(xd[1:2], wd, bd, stride=2, dilation=2, groups=4)
+    d = (y[1:2].double() - ref.double()).abs().max().item() / ref.double().abs().max().item()
+    assert d < TOL, d
+
+
+_PAIR_CASES = [
+    # x, w, transposed, kwargs: shapes the packed batch-pair kernels cover (full groups of 8 or 16 channels)
+    ((8, 8, 512, 512), (8, 8, 65, 65), False, {}),                                                   # BASELINE c2
+    ((3, 8, 200, 180), (8, 8, 5, 7), False, dict(padding=(1, 2))),                                   # odd batch, padding
+    ((1, 16, 300, 260), (16, 8, 9, 3), False, dict(groups=2, stride=(2, 1))),                        # single item, groups of 8
+    ((2, 32, 560, 560), (32, 16, 9, 9), True, dict(stride=2, dilation=2, groups=2, padding=2)),      # 16 per group, segments, lattice
+    ((5, 8, 700, 520), (8, 8, 31, 17), False, {}),                                                   # row and column segments
+    ((2, 8, 200, 1700), (8, 8, 5, 301), False, {}),                                                  # 2048-point rows
+    ((4, 16, 256, 256), (16, 16, 9, 9), False, dict(padding=4)),                                     # 16 per group, two items per CTA
+]
+
+
+@pytest.mark.parametrize("xs,ws,tr,kw", _PAIR_CASES)
+def test_pair_kernels_match_one_line_kernels_and_torch(xs, ws, tr, kw):
+    from fft_conv_pytorch_b200 import _lib as L
+
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(*xs, generator=g).cuda()
+    w = torch.randn(*ws, generator=g).cuda()
+    cout = ws[1] * kw.get("groups", 1) if tr else ws[0]
+    b = torch.randn(cout, generator=g).cuda()
+    fn = fcp.fft_conv_transpose if tr else fcp.fft_conv
+    out = {}
+    try:
+        for name, flags in (("pair", L.FC_FLAG_PAIR), ("plain", L.FC_FLAG_NO_PAIR)):
+            Fn.set_default_flags(flags)
+            Fn.clear_caches()
+            with torch.no_grad():
+                out[name] = fn(x, w, b, **kw)
+            if name == "pair":
+                e = Fn._plans[next(reversed(Fn._plans))]
+                assert "pair_fused" in e.plan.describe(), e.plan.describe()
+    finally:
+        Fn.set_default_flags(0)
+        Fn.clear_caches()
+    nd = len(xs) - 2
+    with torch.no_grad():
+        ref = getattr(F, ("conv_transpose%dd" if tr else "conv%dd") % nd)(x.double(), w.double(), b.double(), **kw)
+    scale = ref.abs().max().item()
+    assert (out["pair"].double() - ref).abs().max().item() / scale < TOL
+    assert (out["pair"] - out["plain"]).abs().max().item() / scale < 2e-6
+
+
+def test_host_pipeline_chunks_keep_the_full_batch_spectrum_layout():
+    """a full batch > 32 builds a pass-order kernel spectrum (SIMT contraction); its batch chunks would
+    qualify for the tensor-core layout on their own and must not pick it."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(40, 32, 2048, generator=g)
+    w = torch.randn(128, 32, 9, generator=g)
+    b = torch.randn(128, generator=g)
+    with torch.no_grad():
+        y = fcp.fft_conv(x.pin_memory(), w.cuda(), b.cuda())
+        ref = F.conv1d(x.cuda(), w.cuda(), b.cuda())
+    assert not y.is_cuda
+    assert rel_err(y.numpy(), ref.cpu().numpy()) < TOL
+
+
+def test_two_devices_in_one_process():
+    """the dynamic shared-memory opt-in and the SM count are per device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 8, 300, 300, generator=g)
+    w = torch.randn(8, 8, 9, 9, generator=g)
+    ref = F.conv2d(x.double(), w.double()).numpy()
+    for d in (0, 1):
+        with torch.no_grad():
+            y = fcp.fft_conv(x.to(f"cuda:{d}"), w.to(f"cuda:{d}"))
+        assert rel_err(y.cpu().numpy(), ref) < TOL
