@@ -422,6 +422,8 @@ def bench_ours(args, cfg_name):
     from fft_conv_pytorch_b200 import functional as Fn
 
     ctx = Ctx(args)
+    if args.plan_flags:
+        Fn.set_default_flags(args.plan_flags)
     cfg = CONFIGS[cfg_name]
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
     warmup = max(args.warmup, 3)  # timing rule: at least 3 untimed steps (reported as `warmup`; `warmup_requested` is the flag)
@@ -603,6 +605,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="headline only: skip the per-config table, the strong-scaling records and the GPU reference")
     ap.add_argument("--flush", default="write", choices=["write", "write+read"],
                     help="L2 flush between timed steps: a 256 MiB memset; write+read adds a read of a second buffer so no dirty flush lines remain (measured: same result)")
+    ap.add_argument("--plan-flags", type=int, default=0, help="FC_FLAG_* bits OR-ed into every plan (A/B runs: 256 = no batch-pair kernels)")
     ap.add_argument("--no-graph", action="store_true", help="queue the kernels from Python every step instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

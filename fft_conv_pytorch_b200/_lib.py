@@ -21,6 +21,7 @@ FC_FLAG_NO_FAST_C2C = 64
 FC_FLAG_NO_SEGMENT = 128
 FC_FLAG_NO_PAIR = 256
 FC_FLAG_PAIR = 512
+FC_FLAG_NO_YSTAGE = 1024
 
 _I3 = ctypes.c_int32 * FC_MAX_ND
 

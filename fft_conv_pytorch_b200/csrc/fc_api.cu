@@ -109,9 +109,17 @@ thread_local int g_num_sms = 148;  // SM count of the calling thread's current d
 // KBp: X(N, channels per group, pair items per CTA, warps, plain, CTAs per SM).
 #define FC_PAIR_ROW_ALL(X) X(128, 1, 8, 4) X(128, 2, 8, 2) X(256, 1, 8, 4) X(256, 2, 8, 2) X(512, 1, 8, 2) X(1024, 1, 8, 1)
 #define FC_PAIR_FUSED_ALL(X) \
-  X(256, 8, 2, 8, true, 2) X(256, 8, 2, 8, false, 2) X(256, 8, 1, 8, true, 2) X(256, 8, 1, 8, false, 2) \
-  X(512, 8, 1, 8, true, 2) X(512, 8, 1, 8, false, 2) X(512, 8, 1, 8, true, 3) X(512, 8, 1, 4, true, 3) X(512, 8, 2, 16, true, 1) X(512, 8, 2, 16, false, 1) X(1024, 8, 1, 8, true, 1) X(1024, 8, 1, 8, false, 1) \
-  X(256, 16, 1, 8, true, 2) X(256, 16, 1, 8, false, 2) X(512, 16, 1, 8, true, 1) X(512, 16, 1, 8, false, 1)
+  X(256, 8, 2, 8, true, 2, 32) X(256, 8, 2, 8, false, 2, 32) X(256, 8, 1, 8, true, 2, 32) X(256, 8, 1, 8, false, 2, 32) \
+  X(512, 8, 1, 8, true, 2, 32) X(512, 8, 1, 8, false, 2, 32) X(512, 8, 1, 16, true, 2, 64) X(512, 8, 1, 16, false, 2, 64) \
+  X(512, 8, 2, 16, true, 1, 32) X(512, 8, 2, 16, false, 1, 32) X(1024, 8, 1, 8, true, 1, 32) X(1024, 8, 1, 8, false, 1, 32) \
+  X(1024, 8, 1, 16, true, 1, 64) X(1024, 8, 1, 16, false, 1, 64) \
+  X(256, 16, 1, 8, true, 2, 32) X(256, 16, 1, 8, false, 2, 32) X(512, 16, 1, 8, true, 1, 32) X(512, 16, 1, 8, false, 1, 32) \
+  X(512, 16, 1, 16, true, 1, 64) X(512, 16, 1, 16, false, 1, 64)
+
+// y-stage variants of K1p / K4p (16-line tiles): X(M, pair lines per warp group, warps, CTAs per SM, radix)
+#define FC_PAIR_ROW_YS_ALL(X) X(128, 1, 8, 4, 8) X(128, 1, 8, 4, 4) X(256, 1, 16, 2, 8) X(256, 1, 16, 2, 4)
+// fc_pair_fused64_kernel: X(sub-transform length, channels per group, CTAs per SM)
+#define FC_PAIR_FUSED64_ALL(X) X(64, 8, 4) X(64, 8, 3) X(64, 8, 2) X(128, 8, 2) X(128, 8, 1)
 
 void fused_set_attr() {
 #ifndef FC_CPU_EMUL
@@ -163,10 +171,19 @@ void init_once() {
   cudaFuncSetAttribute(fc_pair_c2r_kernel<MM, NLL, NWW, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   FC_PAIR_ROW_ALL(FC_PAIR_ROW_ATTR)
 #undef FC_PAIR_ROW_ATTR
-#define FC_PAIR_FUSED_ATTR(NN, CC, NPP, WW, PL, OC) \
-  cudaFuncSetAttribute(fc_pair_fused_kernel<NN, CC, NPP, WW, PL, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+#define FC_PAIR_FUSED_ATTR(NN, CC, NPP, WW, PL, OC, TP) \
+  cudaFuncSetAttribute(fc_pair_fused_kernel<NN, CC, NPP, WW, PL, OC, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   FC_PAIR_FUSED_ALL(FC_PAIR_FUSED_ATTR)
 #undef FC_PAIR_FUSED_ATTR
+#define FC_PAIR_ROW_YS_ATTR(MM, NLL, NWW, OC, YY)                                                                          \
+  cudaFuncSetAttribute(fc_pair_r2c_kernel<MM, NLL, NWW, OC, YY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); \
+  cudaFuncSetAttribute(fc_pair_c2r_kernel<MM, NLL, NWW, OC, YY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  FC_PAIR_ROW_YS_ALL(FC_PAIR_ROW_YS_ATTR)
+#undef FC_PAIR_ROW_YS_ATTR
+#define FC_PAIR_FUSED64_ATTR(SS, CC, OC) \
+  cudaFuncSetAttribute(fc_pair_fused64_kernel<SS, CC, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  FC_PAIR_FUSED64_ALL(FC_PAIR_FUSED64_ATTR)
+#undef FC_PAIR_FUSED64_ATTR
   fused_set_attr();
   cudaFuncSetAttribute(fc_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   cudaFuncSetAttribute(fc_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
@@ -582,6 +599,34 @@ int launch_pair_r2c(const fc_plan* pl, const fc_pass& p, const void* in, void* o
   a.tw = tw;
   a.B = pl->prob.batch;
   a.C = pl->prob.cin;
+  {
+    static const int abl1 = fc_tune_int("ABL1", 0);
+    a.abl = abl1;
+  }
+  if (p.ystage > 0) {  // y-stage variant: the plan fixed the 16-line tiling
+    if (p.n_tiles < 1) return FC_OK;
+    const size_t smem = (size_t)16 * (p.M + (p.ystage == 8 ? 4 : 2)) * sizeof(fc_c2);  // line pitch of the y-stage tiles (fc_pair.cuh)
+    static const int ys_occ = fc_tune_int("YSOCC", 0);
+    bool done = false;
+#define FC_PAIR_YS_LAUNCH(MM, NLL, NWW, OC, YY)                                  \
+  if (!done && p.M == MM && p.ystage == YY) {                                    \
+    int64_t per_sm = (int64_t)(224 * 1024) / (int64_t)(smem + 1024);            \
+    if (per_sm > OC) per_sm = OC;                                                \
+    if (ys_occ > 0 && per_sm > ys_occ) per_sm = ys_occ;                          \
+    if (per_sm < 1) per_sm = 1;                                                  \
+    int64_t grid = (int64_t)g_num_sms * per_sm;                                  \
+    if (grid > p.n_tiles) grid = p.n_tiles;                                      \
+    dim3 g((unsigned)grid), b(NWW * 32);                                         \
+    auto k = fc_pair_r2c_kernel<MM, NLL, NWW, OC, YY>;                            \
+    FC_LAUNCH(k, g, b, smem, st, a);                                             \
+    done = true;                                                                 \
+  }
+    FC_PAIR_ROW_YS_ALL(FC_PAIR_YS_LAUNCH)
+#undef FC_PAIR_YS_LAUNCH
+    if (!done) return set_err(FC_EUNSUPPORTED, "no y-stage pair row kernel for this line length");
+    rec_mark();
+    return check_cuda("pair row (y stage) launch");
+  }
   const pair_row_cfg c = pair_row_config(p.M);
   pair_retile(a.p, c.nlp);
   if (a.p.n_tiles < 1) return FC_OK;
@@ -616,6 +661,30 @@ int launch_pair_c2r(const fc_plan* pl, const fc_pass& p, const void* in, void* o
   a.bias = bias;
   a.B = pl->prob.batch;
   a.C = pl->prob.cout;
+  if (p.ystage > 0) {  // y-stage variant: the plan fixed the 16-line tiling
+    if (p.n_tiles < 1) return FC_OK;
+    const size_t smem = (size_t)16 * (p.M + (p.ystage == 8 ? 4 : 2)) * sizeof(fc_c2);  // line pitch of the y-stage tiles (fc_pair.cuh)
+    static const int ys_occ = fc_tune_int("YSOCC", 0);
+    bool done = false;
+#define FC_PAIR_YS_LAUNCH(MM, NLL, NWW, OC, YY)                                  \
+  if (!done && p.M == MM && p.ystage == YY) {                                    \
+    int64_t per_sm = (int64_t)(224 * 1024) / (int64_t)(smem + 1024);            \
+    if (per_sm > OC) per_sm = OC;                                                \
+    if (ys_occ > 0 && per_sm > ys_occ) per_sm = ys_occ;                          \
+    if (per_sm < 1) per_sm = 1;                                                  \
+    int64_t grid = (int64_t)g_num_sms * per_sm;                                  \
+    if (grid > p.n_tiles) grid = p.n_tiles;                                      \
+    dim3 g((unsigned)grid), b(NWW * 32);                                         \
+    auto k = fc_pair_c2r_kernel<MM, NLL, NWW, OC, YY>;                            \
+    FC_LAUNCH(k, g, b, smem, st, a);                                             \
+    done = true;                                                                 \
+  }
+    FC_PAIR_ROW_YS_ALL(FC_PAIR_YS_LAUNCH)
+#undef FC_PAIR_YS_LAUNCH
+    if (!done) return set_err(FC_EUNSUPPORTED, "no y-stage pair row kernel for this line length");
+    rec_mark();
+    return check_cuda("pair row (y stage) launch");
+  }
   const pair_row_cfg c = pair_row_config(p.M);
   pair_retile(a.p, c.nlp);
   if (a.p.n_tiles < 1) return FC_OK;
@@ -669,6 +738,8 @@ int launch_pair_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in,
     a.k_pf = kpf;
     static const int abl = fc_tune_int("ABL", 0);
     a.abl = abl;
+    static const int ksh = fc_tune_int("KSHARE", 0);
+    a.k_share = ksh;
     static const int dns = fc_tune_int("DESYNC", 0);
     a.desync_ns = dns;
     a.desync_mod = g_num_sms;
@@ -687,9 +758,9 @@ int launch_pair_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in,
   if (grid < 1) return FC_OK;
   dim3 g((unsigned)grid), b((unsigned)f.warps * 32);
   bool ok = false;
-#define FC_PAIR_FUSED_CASE(NN, CC, NPP, WW, PL, OC)                                                                      \
+#define FC_PAIR_FUSED_CASE(NN, CC, NPP, WW, PL, OC, TP)                                                                  \
   if (!ok && f.N == NN && f.ci == CC && f.nb == NPP && f.warps == WW && (f.plain != 0) == PL && f.occ == OC) { \
-    auto k = fc_pair_fused_kernel<NN, CC, NPP, WW, PL, OC>;                                                              \
+    auto k = fc_pair_fused_kernel<NN, CC, NPP, WW, PL, OC, TP>;                                                          \
     FC_LAUNCH(k, g, b, smem, st, a);                                                                                      \
     ok = true;                                                                                                            \
   }
@@ -698,6 +769,46 @@ int launch_pair_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in,
   if (!ok) return set_err(FC_EUNSUPPORTED, "no pair fused kernel instantiation for this shape");
   rec_mark();
   return check_cuda("pair fused launch");
+}
+
+int launch_pair_fused64(const fc_plan* pl, const fc_fused_desc& f, const void* in, const float2* kspec, void* out, const float2* tw, cudaStream_t st) {
+  const fc_problem& P = pl->prob;
+  fc_pair_fused64_args a;
+  a.xin = (const fc_c2*)in;
+  a.kspec = kspec;
+  a.yout = (fc_c2*)out;
+  a.tw = tw;
+  a.tw_len = pl->tw_len;
+  a.BP = (P.batch + 1) / 2;
+  a.Cin = P.cin;
+  a.Cout = P.cout;
+  a.G = P.groups;
+  a.YS = f.ystage;
+  const int S = f.ystage_S, npi = 256 / S;
+  a.nbs = (a.BP + npi - 1) / npi;
+  a.R = f.R;
+  a.Rk = f.Rk > 0 ? f.Rk : f.R;
+  a.n_units = (int64_t)P.groups * f.R * f.ystage * a.nbs;
+  const size_t smem = (size_t)256 * f.ci * sizeof(fc_c2) + (size_t)f.ci * f.ci * S * 8 + 16;
+  static const int occ_t = fc_tune_int("KB64OCC", 0);
+  const int occ = occ_t > 0 ? occ_t : (S == 64 ? 3 : 2);
+  int64_t grid = a.n_units;
+  const int64_t cap = (int64_t)g_num_sms * 32;
+  if (grid > cap) grid = cap;
+  if (grid < 1) return FC_OK;
+  dim3 g((unsigned)grid), b(256);
+  bool ok = false;
+#define FC_PAIR_FUSED64_CASE(SS, CC, OC)                  \
+  if (!ok && S == SS && f.ci == CC && occ == OC) {        \
+    auto k = fc_pair_fused64_kernel<SS, CC, OC>;          \
+    FC_LAUNCH(k, g, b, smem, st, a);                      \
+    ok = true;                                            \
+  }
+  FC_PAIR_FUSED64_ALL(FC_PAIR_FUSED64_CASE)
+#undef FC_PAIR_FUSED64_CASE
+  if (!ok) return set_err(FC_EUNSUPPORTED, "no 64-point fused kernel instantiation for this shape");
+  rec_mark();
+  return check_cuda("pair fused64 launch");
 }
 
 // ---- tensor-core contraction (fc_tc.cuh)
@@ -920,6 +1031,9 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
         break;
       case FC_L_PAIR_FUSED:
         rc = launch_pair_fused(plan, L.fused, buf_ptr(b, L.src), (const float2*)d_kspec, buf_ptr(b, L.dst), tw, st);
+        break;
+      case FC_L_PAIR_FUSED64:
+        rc = launch_pair_fused64(plan, L.fused, buf_ptr(b, L.src), (const float2*)d_kspec, buf_ptr(b, L.dst), tw, st);
         break;
       case FC_L_PLANE_FWD:
       case FC_L_PLANE_INV:

@@ -480,7 +480,9 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
         if (!li.valid) continue;
         float2 val = fc_scale(res[l * pitch + fc_swz(k)], p.scale);
         if (p.conj_out) val = fc_conj(val);
-        y[li.out_base + (int64_t)k * p.out_es] = val;
+        const int64_t off = p.out_split > 1 ? (int64_t)(k & (p.out_split - 1)) * p.out_split_stride + (int64_t)(k / (int)p.out_split) * p.out_es
+                                            : (int64_t)k * p.out_es;
+        y[li.out_base + off] = val;
       }
     } else if (KIND == FC_C2C_INV) {
       float2* y = reinterpret_cast<float2*>(a.out);

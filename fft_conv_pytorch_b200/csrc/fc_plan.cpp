@@ -779,6 +779,17 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     // K1p writes and K4p reads the scratch buffers in the pair layout as well (whole pairs there too)
     sA = (sA + P.batch - 1) / P.batch * bp2;
     sB = (sB + P.batch - 1) / P.batch * bp2;
+    if (pl->prog[1].fused.ystage > 0) {
+      // K1p stores and K4p reads all N positions of the fused axis per bin (rows beyond the signal are zero), for every
+      // row segment
+      const fc_pass& k1p = pl->prog[0].pass;
+      const fc_pass& k4p = pl->prog[2].pass;
+      const int64_t need_x = k1p.n_outer * k1p.out_os * 16, need_y = k4p.n_outer * k4p.in_os * 16;
+      if (pl->prog[0].dst == FC_BUF_SA) sA = std::max(sA, need_x);
+      if (pl->prog[0].dst == FC_BUF_SB) sB = std::max(sB, need_x);
+      if (pl->prog[0].dst == FC_BUF_SPEC) I.xspec_bytes = std::max(I.xspec_bytes, need_x);
+      I.yspec_bytes = std::max(I.yspec_bytes, need_y);
+    }
     pl->scratch_bytes = sA + sB;
     pl->off_yspec = align_up(pl->off_xspec + I.xspec_bytes, 256);
     pl->off_sA = align_up(pl->off_yspec + I.yspec_bytes, 256);
@@ -798,6 +809,13 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     if (pl->pair) {  // [group][line][o][i/2][n][i%2]: the values of two input channels of a bin are adjacent (fc_pair_contract)
       k.out_il = 2;
       k.out_es = 2;
+      const int ys = pl->prog[1].fused.ystage;
+      if (ys > 0) {  // [group][line][k1][o][i/2][k2][i%2], bin n = k1 + ys*k2 (fc_pair_fused64_kernel)
+        const int S = pl->prog[1].fused.ystage_S;
+        k.out_os = S;
+        k.out_split = ys;
+        k.out_split_stride = OI * S;
+      }
     }
   }
   if (I.segments > 1 && !I.fused) return fail(FC_EUNSUPPORTED, "internal: segmented plan without the fused axis kernel");
@@ -968,6 +986,8 @@ void fc_plan_build_program(fc_plan* pl) {
     L.dst = FC_BUF_SPEC;  // the product-spectrum buffer is free in the fused program; fs.src and bs.dst may alias
     L.spec_is_y = 1;
     L.fused.N = fs.pass.N;
+    L.fused.ystage = 0;
+    L.fused.ystage_S = 0;
     L.fused.n_in = fs.pass.n_in;
     L.fused.n_out = bs.pass.n_out;
     L.fused.n_seg = seg_ax ? seg_ax->seg_n : 1;
@@ -1083,8 +1103,9 @@ void fc_plan_build_program(fc_plan* pl) {
     fc_launch& C = pl->prog[2];
     const int N = Bk.fused.N;
     auto pair_len = [](int M) { return M == 128 || M == 256 || M == 512 || M == 1024; };
-    // default: groups of 8 channels (BASELINE c2; with 16 the one-line kernels measured faster: c5 2.03 vs 2.34 ms)
-    const bool want = (flags & FC_FLAG_PAIR) || Ig == 8;
+    // opt-in (FC_FLAG_PAIR): at BASELINE c2 the whole step measured 138.6 us on this program (y stage, S = 128) against 132.1 us on
+    // the one-line kernels, although its fused kernel is faster (57 / 44 us against 71 us): profiles/r2_c2_paths_same_box.txt
+    const bool want = (flags & FC_FLAG_PAIR) != 0;
     const bool ok = want && Ig == Og && (Ig == 8 || Ig == 16) && pair_len(A.pass.M) && pair_len(C.pass.M) && (int64_t)N * Ig * 16 <= 128 * 1024;
     if (ok) {
       pl->pair = 1;
@@ -1119,6 +1140,49 @@ void fc_plan_build_program(fc_plan* pl) {
       C.type = FC_L_PAIR_C2R;
       retile_pair(C.pass, P.cout);
       C.name = "pair_c2r_N" + std::to_string(C.pass.N);
+      // y stage: N = 64*YS; K1p / K4p run the radix-YS stage of the fused axis, the fused kernel 64-point sub-problems
+      // that share the kernel spectrum across eight batch items (fc_pair_fused64_kernel)
+      // N = YS * S: radix YS <= 4 keeps the stage in K1p / K4p cheap (64-byte runs of 4 adjacent n2 per tile, a radix-4
+      // butterfly); measured at BASELINE c2: S = 64 / YS = 8 makes K1p 63 us and K4p 47 us against 44 / 33 us
+      int S = N >= 512 ? 128 : 64;
+      if (const char* t = fc_tune_str("YSS")) S = std::atoi(t) == 64 ? 64 : 128;
+      if (N / S < 4) S = 64;
+      const int YS = N / S;
+      auto ys_row = [](int M) { return M == 128 || M == 256; };  // K1p / K4p variants with 16-line tiles
+      Bk.fused.ystage = 0;
+      // identity gather on the fused axis (rows beyond the signal are zero), plain crop, one segment
+      const fc_imap& imy = Bk.fused.imap;
+      const fc_omap& omy = Bk.fused.omap;
+      const bool plain_y = imy.mode == FC_PAD_CONSTANT && imy.pad == 0 && imy.up == 1 && imy.sub == 1 && omy.og == 1 && omy.os == 1 && omy.ob == 0 &&
+                           omy.Lout <= omy.lim && Bk.fused.n_seg == 1;
+      if (!(flags & FC_FLAG_NO_YSTAGE) && plain_y && (YS == 8 || YS == 4) && Ig == 8 && ys_row(A.pass.M) && ys_row(C.pass.M) &&
+          A.pass.R <= N && C.pass.R <= N && C.pass.row_og == 1) {
+        Bk.fused.ystage = YS;
+        Bk.fused.ystage_S = S;
+        Bk.type = FC_L_PAIR_FUSED64;
+        Bk.name = "pair_fused64_N" + std::to_string(N);
+        auto ys_pass = [&](fc_pass& p, bool fwd) {
+          p.ystage = YS;
+          p.ystage_N = N;
+          p.ystage_S = S;
+          p.T = 16;
+          p.log2T = 4;
+          p.tiles_per_outer = (int64_t)(N / 16) * p.seg_n;
+          p.n_tiles = p.tiles_per_outer * p.n_outer;
+          const int64_t lines = (int64_t)(p.M + 1) * p.seg_n;  // bins of this kernel's own axis per pair image
+          if (fwd) {
+            p.out_es = N;
+            p.out_os = lines * N;
+          } else {
+            p.in_es = N;
+            p.in_os = lines * N;
+          }
+        };
+        ys_pass(A.pass, true);
+        ys_pass(C.pass, false);
+        A.name += "_ys" + std::to_string(YS);
+        C.name += "_ys" + std::to_string(YS);
+      }
     }
   }
 }

@@ -31,7 +31,7 @@ struct fc_step {
 
 // One kernel launch of fc_conv.
 enum { FC_L_PASS = 0, FC_L_FAST_R2C = 1, FC_L_FAST_C2R = 2, FC_L_CONTRACT = 3, FC_L_FUSED = 4, FC_L_TC_X = 5, FC_L_TC_GEMM = 6, FC_L_TC_Y = 7, FC_L_FAST_C2C = 8, FC_L_COL_R2C = 9, FC_L_COL_C2R = 10, FC_L_PLANE_FWD = 11, FC_L_PLANE_INV = 12,
-       FC_L_PAIR_R2C = 13, FC_L_PAIR_FUSED = 14, FC_L_PAIR_C2R = 15 };
+       FC_L_PAIR_R2C = 13, FC_L_PAIR_FUSED = 14, FC_L_PAIR_C2R = 15, FC_L_PAIR_FUSED64 = 16 };
 
 // Geometry of the fused "last forward axis -> contraction -> first inverse axis" kernel (fc_fused.cuh).
 struct fc_fused_desc {
@@ -47,6 +47,9 @@ struct fc_fused_desc {
   // [s*seg_V - seg_off, s*seg_V - seg_off + N) and owns the dense outputs [s*seg_V, (s+1)*seg_V), which sit at local
   // index seg_off .. seg_off + seg_V - 1 of its circular result
   int32_t n_seg, seg_V, seg_off;
+  int32_t ystage_S; // ... and the length of the sub-transforms the fused kernel is left with (64 or 128); N = ystage * ystage_S
+  int32_t ystage; // pair program only: radix of the stage of this axis' transform that runs in K1p / K4p (0: none); the fused
+                  // kernel is then fc_pair_fused64_kernel on independent 64-point sub-problems
   int64_t R;      // lines (bins of the other axes) per (batch, channel)
   int64_t Rk;     // ... per kernel-spectrum channel pair: line r multiplies kernel line r % Rk (Rk < R when the other
                   // axis is segmented: all its segments share one kernel spectrum)

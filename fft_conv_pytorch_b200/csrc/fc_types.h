@@ -83,6 +83,13 @@ struct fc_pass {
   // (q / out_il) * out_il * out_os + q % out_il and its elements are out_es = out_il apart (the pair kernels read the
   // kernel values of two input channels of a bin with one 16-byte load)
   int64_t out_il;
+  // ... and when out_split > 1 (a power of two) element k of a forward C2C line goes to
+  // (k % out_split) * out_split_stride + (k / out_split) * out_es: the bins k1 + out_split*k2 of one residue k1 form a
+  // contiguous chunk per (group, line) — the kernel-spectrum layout of the 64-bin sub-problems of fc_pair_fused64_kernel
+  int64_t out_split, out_split_stride;
+  // K1p / K4p: radix of the stage of the *other* axis' transform that runs in their transposed store / load (0: none;
+  // fc_pair.cuh "y stage"): a tile is then the pair lines {n2 + 64*n1} of 16/ystage adjacent n2
+  int32_t ystage, ystage_N, ystage_S;  // radix, transform length N = ystage * S, sub-transform length S (64 or 128)
   // R2C input base: base(o) = ((o/o_c2)/o_q)*o_sA + ((o/o_c2)%o_q)*o_sB + (o%o_c2)*o_sC   (replaces in_os)
   int64_t o_c2, o_q, o_sA, o_sB, o_sC;
   fc_imap imap;

@@ -81,7 +81,8 @@ enum {
   FC_FLAG_NO_FAST_C2C = 64, /* keep contiguous complex axis passes on the generic block-level kernel */
   FC_FLAG_NO_SEGMENT = 128, /* never split the first axis of a 2-d problem into overlap-save segments */
   FC_FLAG_NO_PAIR = 256,    /* keep the fused 2-d program on the one-line-per-item kernels (no packed batch pairs) */
-  FC_FLAG_PAIR = 512        /* run it on the packed batch-pair kernels wherever they apply (default: where they measured faster) */
+  FC_FLAG_PAIR = 512,       /* run it on the packed batch-pair kernels wherever they apply (default: where they measured faster) */
+  FC_FLAG_NO_YSTAGE = 1024  /* pair program: keep the whole transform of the fused axis inside the fused kernel */
 };
 
 typedef struct fc_plan fc_plan; /* opaque */

@@ -1,0 +1,12 @@
+mkdir -p gpurun_out
+O=gpurun_out/r2j_ystage.txt
+: > $O
+python scripts/kb_probe.py c2 >> $O 2>&1
+FFTCONV_B200_KB64OCC=1 python scripts/kb_probe.py c2 >> $O 2>&1
+FFTCONV_B200_YSS=64 python scripts/kb_probe.py c2 >> $O 2>&1
+python scripts/kb_probe.py c2 >> $O 2>&1
+python scripts/kb_probe.py img256 >> $O 2>&1
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/r2j_pytest.log 2>&1; tail -2 gpurun_out/r2j_pytest.log >> $O
+python bench.py --quick --no-cpu-baseline --steps 100 > gpurun_out/r2j_bench.log 2>&1
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph --quick > gpurun_out/plain2.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fc_pair' -s 9 -c 3 -o gpurun_out/r2j_prof_ystage_c2 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph --quick > gpurun_out/ncu_full.log 2>&1

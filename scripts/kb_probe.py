@@ -21,6 +21,7 @@ CFG = {
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 15
 xs, ws, tr, kw = CFG[name]
+Fn.set_default_flags(int(os.environ.get("FFTCONV_B200_PROBE_FLAGS", "0")))
 dev = torch.device("cuda", 0)
 x = torch.randn(*xs, device=dev)
 w = torch.randn(*ws, device=dev)
