@@ -511,7 +511,7 @@ def bench_ours(args, cfg_name):
     torch.cuda.reset_peak_memory_stats(dev)
 
     # ---- every BASELINE shape (rank 0's GPU; N = 1 runs) and the strong-scaling records (all ranks)
-    cfg_rows, strong = [], {}
+    cfg_rows, strong, alternatives = [], {}, []
     if not args.quick:
         if world == 1:
             for nm in ("c1", "c2", "c3", "c4", "c5"):
@@ -524,6 +524,22 @@ def bench_ours(args, cfg_name):
                     torch.cuda.empty_cache()
                 r.pop("ms_sum", None)
                 cfg_rows.append(r)
+        # the other programs the library has for the headline shape (opt-in plan flags), same shape, same method
+        if world == 1:
+            for label, fl in (("packed batch pairs + y stage: K1p/K4p run one radix-4 stage of the fused axis, 128-point fused kernel with "
+                               "bulk-copied kernel-spectrum chunks (FC_FLAG_PAIR)", 512),
+                              ("packed batch pairs, whole fused-axis transform in the fused kernel (FC_FLAG_PAIR | FC_FLAG_NO_YSTAGE)", 512 | 1024)):
+                try:
+                    Fn.set_default_flags(args.plan_flags | fl)
+                    r = time_config(ctx, "c2", cfg, cfg["x"][0], steps=5, warmup=2, with_ref=False)
+                    r.pop("ms_sum", None)
+                    r["program"] = label
+                    alternatives.append(r)
+                except Exception as e:  # noqa: BLE001
+                    alternatives.append({"program": label, "error": repr(e)[:160]})
+                finally:
+                    Fn.set_default_flags(args.plan_flags)
+                    Fn.clear_caches()
         # strong scaling: fixed global batch split over the ranks; N = 1 is the T1 of the efficiency T1 / (N * T_N)
         for nm, gb in (("c5", C5_GLOBAL_BATCH), ("c2", CONFIGS["c2"]["x"][0]), ("c3", CONFIGS["c3"]["x"][0])):
             c = CONFIGS[nm]
@@ -575,6 +591,8 @@ def bench_ours(args, cfg_name):
             line["gpu_reference"] = gpu_ref
         if cfg_rows:
             line["configs"] = cfg_rows
+        if alternatives:
+            line["alternative_programs"] = alternatives
         if strong:
             line["strong"] = {"note": "fixed global batch split over the ranks, device time = max over ranks; efficiency = T1 / (N * T_N) "
                                       "against the N = 1 line of the same key", **strong}

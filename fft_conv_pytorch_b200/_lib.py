@@ -22,6 +22,7 @@ FC_FLAG_NO_SEGMENT = 128
 FC_FLAG_NO_PAIR = 256
 FC_FLAG_PAIR = 512
 FC_FLAG_NO_YSTAGE = 1024
+FC_FLAG_NO_ROW_FILL = 2048
 
 _I3 = ctypes.c_int32 * FC_MAX_ND
 

@@ -504,7 +504,8 @@ int launch_fast_c2c(const fc_pass& p, const void* in, void* out, const float2* t
   return check_cuda("fast c2c launch");
 }
 
-int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, const float2* kspec, void* out, const float2* tw, cudaStream_t st) {
+int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, const float2* kspec, void* out, const float2* tw, cudaStream_t st,
+                 float* d_y, const float* d_bias) {
   const fc_problem& P = pl->prob;
   fc_fused_args a;
   a.xin = (const float2*)in;
@@ -530,6 +531,24 @@ int launch_fused(const fc_plan* pl, const fc_fused_desc& f, const void* in, cons
   a.n_units = (int64_t)P.groups * f.R * a.nbs;
   a.imap = f.imap;
   a.omap = f.omap;
+  a.fill_y = nullptr;
+  a.fill_bias = nullptr;
+  a.fill_og = a.fill_ob = a.fill_Lrow = a.fill_Lcol = a.fill_cout = a.fill_rpu = 0;
+  a.fill_img_stride = a.fill_row_stride = a.fill_total = 0;
+  if (f.fill_rows && d_y && a.n_units > 0) {
+    const fc_pass& c2r = pl->prog.back().pass;  // the last kernel: geometry of the output rows
+    a.fill_y = d_y;
+    a.fill_bias = d_bias;
+    a.fill_og = c2r.row_og;
+    a.fill_ob = c2r.row_ob;
+    a.fill_Lrow = c2r.row_Lout;
+    a.fill_Lcol = c2r.omap.Lout;
+    a.fill_cout = P.cout;
+    a.fill_img_stride = c2r.out_os;
+    a.fill_row_stride = c2r.out_rs;
+    a.fill_total = (int64_t)P.batch * P.cout * c2r.row_Lout;
+    a.fill_rpu = (int32_t)((a.fill_total + a.n_units - 1) / a.n_units);
+  }
   const size_t smem = (size_t)f.nb * f.ci * f.N * sizeof(float2);
   {  // distance (in units) to the CTA of the next wave on the same SM: what this CTA prefetches into L2
     int64_t per_sm = (int64_t)(228 * 1024) / (int64_t)(smem + 1024 + 256);
@@ -1066,7 +1085,7 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
         rc = launch_tc_relayout(2, ws + plan->off_ytc, yspec, c.bins, c.batch, c.cin, c.cout, c.groups, st);
       } break;
       default:
-        rc = launch_fused(plan, L.fused, buf_ptr(b, L.src), (const float2*)d_kspec, buf_ptr(b, L.dst), tw, st);
+        rc = launch_fused(plan, L.fused, buf_ptr(b, L.src), (const float2*)d_kspec, buf_ptr(b, L.dst), tw, st, d_y, d_bias);
         break;
     }
     if (rc) return rc;

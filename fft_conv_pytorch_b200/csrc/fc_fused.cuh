@@ -17,7 +17,11 @@
 #pragma once
 #include "fc_kernels.cuh"
 
+#ifdef FC_RACE_SELFTEST  // scripts/emul_sanitize.sh selftest: drop the warp barriers, ThreadSanitizer must then report the races
+#define FC_SYNCWARP() ((void)0)
+#else
 #define FC_SYNCWARP() __syncwarp()
+#endif
 
 #ifdef FC_CPU_EMUL
 FC_DEV void fc_prefetch_l2(const void*) {}
@@ -531,8 +535,8 @@ __global__ void __launch_bounds__(NW * 32, OCC) fc_fast_c2r_kernel(fc_fast_c2r_a
           const int64_t jr = r * p.row_og + er - p.row_ob;
           if (jr < 0 || jr >= p.row_Lout) continue;
           float* yrow = a.out + o * p.out_os + jr * p.out_rs;
-          if (er != 0) {  // a row between the lattice rows: bias only
-            fc_fill_run<G>(yrow, j_lo, j_hi, b, gl);
+          if (er != 0) {  // a row between the lattice rows: bias only (written here unless the fused kernel did it)
+            if (!p.row_fill_skip) fc_fill_run<G>(yrow, j_lo, j_hi, b, gl);
             continue;
           }
           if (om.og == 2 && om.os == 1 && om.ob >= 0) {
@@ -723,6 +727,14 @@ struct fc_fused_args {
   int64_t n_units;
   fc_imap imap;
   fc_omap omap;
+  // Bias-only output rows of a row lattice (transposed convolution with gcd(stride, dilation) > 1: BASELINE c5 writes
+  // 4.55 GB of output, half of its rows nothing but the bias). They depend on no spectrum, so this kernel — which leaves
+  // DRAM mostly idle — streams them out as fire-and-forget 16-byte stores at the top of every unit, fill_rpu rows of the
+  // flat (image, row) list per unit, instead of the last kernel, whose own stores are its bottleneck.
+  float* fill_y;           // nullptr: nothing to fill
+  const float* fill_bias;  // nullable
+  int32_t fill_og, fill_ob, fill_Lrow, fill_Lcol, fill_cout, fill_rpu;
+  int64_t fill_img_stride, fill_row_stride, fill_total;
 };
 
 // Complex multiply-accumulate of one (float2) or two adjacent (float4) bins: acc += x * k.
@@ -888,6 +900,16 @@ __global__ void __launch_bounds__(W * 32, OCC) fc_fused_axis_kernel(fc_fused_arg
       r = (gr - t * nsx) * Rk + rk;
     }
     const int b0 = bs * NB;
+    if (a.fill_y) {  // bias-only rows of the output lattice: this unit's share, one row per warp at a time
+      const int64_t f_end = (int64_t)(unit + 1) * a.fill_rpu < a.fill_total ? (int64_t)(unit + 1) * a.fill_rpu : a.fill_total;
+      for (int64_t f = (int64_t)unit * a.fill_rpu + w; f < f_end; f += W) {
+        const int64_t m = f / a.fill_Lrow;
+        const int jr = (int)(f - m * a.fill_Lrow);
+        if ((jr + a.fill_ob) % a.fill_og == 0) continue;  // a lattice row: the last kernel writes it
+        const float bv = a.fill_bias ? __ldg(a.fill_bias + (int)(m % a.fill_cout)) : 0.f;
+        fc_fill_run<32>(a.fill_y + m * a.fill_img_stride + (int64_t)jr * a.fill_row_stride, 0, a.fill_Lcol, bv, lane);
+      }
+    }
     // ---- phase 1: forward transform of every (batch, input channel) line of this bin
     const int n_task1 = Ig * NBG;
 #pragma unroll 1

@@ -988,6 +988,7 @@ void fc_plan_build_program(fc_plan* pl) {
     L.fused.N = fs.pass.N;
     L.fused.ystage = 0;
     L.fused.ystage_S = 0;
+    L.fused.fill_rows = 0;
     L.fused.n_in = fs.pass.n_in;
     L.fused.n_out = bs.pass.n_out;
     L.fused.n_seg = seg_ax ? seg_ax->seg_n : 1;
@@ -1093,6 +1094,11 @@ void fc_plan_build_program(fc_plan* pl) {
   }
   pl->info.n_launches = (int)pl->prog.size();
   pl->info.fused = fuse_mid ? 1 : 0;
+  // bias-only rows of a row lattice: written by the fused kernel (DRAM idle there) instead of the last one (store-bound)
+  if (fuse_mid && pl->prog.size() == 3 && pl->prog[2].type == FC_L_FAST_C2R && pl->prog[2].pass.row_og > 1 && !(flags & FC_FLAG_NO_ROW_FILL)) {
+    pl->prog[1].fused.fill_rows = 1;
+    pl->prog[2].pass.row_fill_skip = 1;
+  }
 
   // ---- packed batch pairs (fc_pair.cuh): the whole fused 2-d program K1 -> KB -> K4 on 16-byte slots
   pl->pair = 0;

@@ -47,6 +47,7 @@ struct fc_fused_desc {
   // [s*seg_V - seg_off, s*seg_V - seg_off + N) and owns the dense outputs [s*seg_V, (s+1)*seg_V), which sit at local
   // index seg_off .. seg_off + seg_V - 1 of its circular result
   int32_t n_seg, seg_V, seg_off;
+  int32_t fill_rows; // 1: the fused kernel also writes the bias-only output rows of a row lattice (see fc_fused_args::fill_*)
   int32_t ystage_S; // ... and the length of the sub-transforms the fused kernel is left with (64 or 128); N = ystage * ystage_S
   int32_t ystage; // pair program only: radix of the stage of this axis' transform that runs in K1p / K4p (0: none); the fused
                   // kernel is then fc_pair_fused64_kernel on independent 64-point sub-problems

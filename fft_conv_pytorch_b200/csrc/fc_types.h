@@ -62,6 +62,7 @@ struct fc_pass {
   // C2R: lattice on the line (row) index: dense line r owns the output rows j with (j + row_ob) / row_og == r; only
   // the row with (j + row_ob) % row_og == 0 carries data, the others are bias only (polyphase-reduced transposed conv)
   int32_t row_og, row_ob, row_Lout;
+  int32_t row_fill_skip;  // C2R (fast kernel): the bias-only rows between the lattice rows are written by the fused kernel
   // overlap-save segments along the line of an R2C / C2R pass (fast kernels K1 / K4 only; seg_n == 1: none). A line of
   // the pass is then a (row, segment) pair: segment s reads the dense positions s*seg_V - seg_off + [0, N) of its row and
   // its half spectrum is stored at bin offset s*(N/2+1); on the way back it owns the dense outputs s*seg_V + [0, seg_V),

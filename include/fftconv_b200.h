@@ -82,7 +82,8 @@ enum {
   FC_FLAG_NO_SEGMENT = 128, /* never split the first axis of a 2-d problem into overlap-save segments */
   FC_FLAG_NO_PAIR = 256,    /* keep the fused 2-d program on the one-line-per-item kernels (no packed batch pairs) */
   FC_FLAG_PAIR = 512,       /* run it on the packed batch-pair kernels wherever they apply (default: where they measured faster) */
-  FC_FLAG_NO_YSTAGE = 1024  /* pair program: keep the whole transform of the fused axis inside the fused kernel */
+  FC_FLAG_NO_YSTAGE = 1024, /* pair program: keep the whole transform of the fused axis inside the fused kernel */
+  FC_FLAG_NO_ROW_FILL = 2048 /* transposed row lattices: leave the bias-only rows to the last kernel (A/B timing) */
 };
 
 typedef struct fc_plan fc_plan; /* opaque */

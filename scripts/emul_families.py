@@ -24,6 +24,10 @@ CASES = [
     ("pair_general_odd_batch", (3, 8, 200, 180), (8, 8, 5, 7), False, dict(padding=(1, 2)), L.FC_FLAG_PAIR),
     ("pair_seg_lattice_16", (2, 32, 560, 300), (32, 16, 9, 9), True, dict(stride=2, dilation=2, groups=2, padding=2), L.FC_FLAG_PAIR),
     ("pair_long_rows", (2, 8, 140, 1700), (8, 8, 5, 301), False, {}, L.FC_FLAG_PAIR),
+    ("pair_ystage4_s64", (3, 8, 130, 250), (8, 8, 7, 3), False, {}, L.FC_FLAG_PAIR),
+    ("pair_ystage4_s128_rowseg", (2, 8, 300, 600), (8, 8, 9, 5), False, {}, L.FC_FLAG_PAIR),
+    ("pair_ystage8_s128", (2, 8, 600, 140), (8, 8, 9, 5), False, {}, L.FC_FLAG_PAIR | L.FC_FLAG_NO_SEGMENT),
+    ("fused_bias_rows", (2, 16, 130, 136), (16, 4, 5, 5), True, dict(groups=2, stride=2, dilation=2, padding=1), 0),
     ("plane_3d", (1, 8, 40, 40, 40), (8, 8, 5, 5, 5), False, {}, 0),
     ("column_1d", (1, 4, 40000), (4, 4, 129), False, {}, 0),
     ("fused_1d_split", (1, 8, 32768), (8, 8, 1025), False, {}, 0),

@@ -381,3 +381,38 @@ def test_segmented_plans_refuse_the_stage_calls():
     rc = lb.fc_contract(p.handle, emul._ptr(buf), emul._ptr(buf), emul._ptr(buf), None)
     assert rc == -2 and b"FC_FLAG_NO_SEGMENT" in lb.fc_last_error()
     assert emul.plan_for((1, 2, 530, 40), (2, 2, 9, 3), flags=L.FC_FLAG_NO_SEGMENT).info.segments == 1
+
+
+@pytest.mark.parametrize("xs,ws,kw,flags,expect", [
+    ((3, 8, 200, 180), (8, 8, 5, 7), dict(padding=(1, 2)), L.FC_FLAG_PAIR, "pair_fused_N256"),              # packed batch pairs, odd batch
+    ((2, 8, 130, 250), (8, 8, 7, 3), {}, L.FC_FLAG_PAIR, "pair_fused64_N256"),                               # y stage, 64-point sub-problems
+    ((3, 8, 300, 140), (8, 8, 9, 5), {}, L.FC_FLAG_PAIR, "pair_fused64_N512"),                               # y stage, 128-point sub-problems
+])
+def test_pair_programs_on_the_emulation(xs, ws, kw, flags, expect):
+    """The packed batch-pair kernels (fc_pair.cuh) and the y-stage program, same source on host threads."""
+    from oracle import fftconv_oracle as O
+
+    rng = np.random.RandomState(2)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = rng.standard_normal(ws).astype(np.float32)
+    b = rng.standard_normal(ws[0]).astype(np.float32)
+    y, plan = emul.conv(x, w, b, flags=flags, **kw)
+    assert expect in plan.describe()
+    assert not np.isnan(y).any()
+    assert rel_err(y, O.fft_conv(x, w, b, **kw)) < 1e-5
+
+
+def test_bias_only_rows_come_from_the_fused_kernel():
+    """Transposed row lattice: the bias-only rows are written by the fused kernel (default) or by the last one (flag)."""
+    from oracle import fftconv_oracle as O
+
+    rng = np.random.RandomState(4)
+    x = rng.standard_normal((2, 16, 130, 136)).astype(np.float32)
+    w = rng.standard_normal((16, 4, 5, 5)).astype(np.float32)
+    b = rng.standard_normal(8).astype(np.float32)
+    kw = dict(groups=2, stride=2, dilation=2, padding=1)
+    ref = O.fft_conv_transpose(x, w, b, **kw)
+    for flags in (0, L.FC_FLAG_NO_ROW_FILL):
+        y, plan = emul.conv(x, w, b, transposed=True, flags=flags, **kw)
+        assert "fused_axis" in plan.describe() and not np.isnan(y).any()
+        assert rel_err(y, ref) < 1e-5

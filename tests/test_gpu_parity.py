@@ -576,7 +576,43 @@ _PAIR_CASES = [
     ((5, 8, 700, 520), (8, 8, 31, 17), False, {}),                                                   # row and column segments
     ((2, 8, 200, 1700), (8, 8, 5, 301), False, {}),                                                  # 2048-point rows
     ((4, 16, 256, 256), (16, 16, 9, 9), False, dict(padding=4)),                                     # 16 per group, two items per CTA
+    ((16, 8, 256, 256), (8, 8, 31, 31), False, {}),                                                  # y stage with 64-point sub-problems
+    ((10, 8, 300, 600), (8, 8, 9, 5), False, {}),                                                    # y stage + row segments, item blocks
+    ((3, 16, 700, 200), (16, 8, 5, 5), False, dict(groups=2)),                                       # y stage, N = 1024 when unsegmented
 ]
+
+
+def test_y_stage_program_is_what_the_pair_flag_runs_at_c2():
+    from fft_conv_pytorch_b200 import _lib as L
+
+    e = Fn.get_plan(False, 8, 8, 8, 1, (512, 512), (65, 65), (1, 1), (0, 0), (1, 1), (0, 0), "constant", L.FC_FLAG_PAIR)
+    d = e.plan.describe()
+    assert "pair_r2c_N512_ys4" in d and "pair_fused64_N512" in d and "pair_c2r_N512_ys4" in d, d
+
+
+def test_bias_only_rows_written_by_the_fused_kernel_match():
+    """BASELINE c5 geometry at reduced size: stride = dilation = 2 row lattice, rows filled by the fused kernel or the last one."""
+    from fft_conv_pytorch_b200 import _lib as L
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 32, 300, 280, generator=g).cuda()
+    w = torch.randn(32, 8, 7, 7, generator=g).cuda()
+    b = torch.randn(32, generator=g).cuda()
+    kw = dict(stride=2, dilation=2, groups=4, padding=1, output_padding=1)
+    out = []
+    try:
+        for flags in (0, L.FC_FLAG_NO_ROW_FILL):
+            Fn.set_default_flags(flags)
+            Fn.clear_caches()
+            with torch.no_grad():
+                out.append(fcp.fft_conv_transpose(x, w, b, **kw))
+    finally:
+        Fn.set_default_flags(0)
+        Fn.clear_caches()
+    with torch.no_grad():
+        ref = F.conv_transpose2d(x.double(), w.double(), b.double(), **kw)
+    assert torch.equal(out[0], out[1])
+    assert (out[0].double() - ref).abs().max().item() / ref.abs().max().item() < TOL
 
 
 @pytest.mark.parametrize("xs,ws,tr,kw", _PAIR_CASES)
@@ -591,14 +627,17 @@ def test_pair_kernels_match_one_line_kernels_and_torch(xs, ws, tr, kw):
     fn = fcp.fft_conv_transpose if tr else fcp.fft_conv
     out = {}
     try:
-        for name, flags in (("pair", L.FC_FLAG_PAIR), ("plain", L.FC_FLAG_NO_PAIR)):
+        # pair: batch-pair kernels, with the y-stage program (64 / 128-point fused kernel) where it applies; pair_noys: the
+        # whole fused-axis transform inside the pair fused kernel; plain: the one-line-per-item kernels
+        for name, flags in (("pair", L.FC_FLAG_PAIR), ("pair_noys", L.FC_FLAG_PAIR | L.FC_FLAG_NO_YSTAGE), ("plain", L.FC_FLAG_NO_PAIR)):
             Fn.set_default_flags(flags)
             Fn.clear_caches()
             with torch.no_grad():
                 out[name] = fn(x, w, b, **kw)
-            if name == "pair":
-                e = Fn._plans[next(reversed(Fn._plans))]
-                assert "pair_fused" in e.plan.describe(), e.plan.describe()
+            if name != "plain":
+                d = Fn._plans[next(reversed(Fn._plans))].plan.describe()
+                assert "pair_fused" in d, d
+                assert name == "pair" or "pair_fused64" not in d
     finally:
         Fn.set_default_flags(0)
         Fn.clear_caches()
@@ -606,8 +645,9 @@ def test_pair_kernels_match_one_line_kernels_and_torch(xs, ws, tr, kw):
     with torch.no_grad():
         ref = getattr(F, ("conv_transpose%dd" if tr else "conv%dd") % nd)(x.double(), w.double(), b.double(), **kw)
     scale = ref.abs().max().item()
-    assert (out["pair"].double() - ref).abs().max().item() / scale < TOL
-    assert (out["pair"] - out["plain"]).abs().max().item() / scale < 2e-6
+    for name in ("pair", "pair_noys"):
+        assert (out[name].double() - ref).abs().max().item() / scale < TOL
+        assert (out[name] - out["plain"]).abs().max().item() / scale < 2e-6
 
 
 def test_host_pipeline_chunks_keep_the_full_batch_spectrum_layout():
