@@ -29,42 +29,47 @@ def _raw_conv(transposed: bool, x: Tensor, w: Tensor, b: Optional[Tensor], strid
         return Fn._run(transposed, x, w, b, stride, padding, opad, dilation, groups, "constant")
 
 
-def _swap(t: Tensor) -> Tensor:
-    """(A, B, *sp) -> (B, A, *sp), contiguous."""
-    return t.transpose(0, 1).contiguous()
-
-
 def _crop(t: Tensor, sizes: Tuple[int, ...]) -> Tensor:
     idx = (slice(None), slice(None)) + tuple(slice(0, s) for s in sizes)
     return t[idx]
 
 
+def _to_group_major(t: Tensor, groups: int, lead_is_channel: bool) -> Tensor:
+    """(B, G*c, *sp) -> (c, G*B, *sp) when lead_is_channel (a "signal" whose batch is the channel index and whose channels
+    are (group, batch)), else -> (G*c, B, *sp) (a "kernel" with B input channels per group). One contiguous copy."""
+    B = t.shape[0]
+    c = t.shape[1] // groups
+    sp = tuple(t.shape[2:])
+    v = t.reshape(B, groups, c, *sp)
+    tail = tuple(range(3, 3 + len(sp)))
+    if lead_is_channel:
+        return v.permute(2, 1, 0, *tail).reshape(c, groups * B, *sp)
+    return v.permute(1, 2, 0, *tail).reshape(groups * c, B, *sp)
+
+
 def _grad_weight_fwd(x: Tensor, gy: Tensor, ksize, stride, padding, dilation, groups: int) -> Tensor:
-    """grad_w[o, i, m] = sum_{b, j} gy[b, o, j] * xpad[b, i, j*s + m*d]  -> (Cout, Cin/g, *K)."""
-    B, cin = x.shape[:2]
-    cout = gy.shape[1]
+    """grad_w[o, i, m] = sum_{b, j} gy[b, o, j] * xpad[b, i, j*s + m*d]  -> (Cout, Cin/g, *K).
+
+    One grouped convolution for all groups: batch and channel roles swapped (signal (Cin/g, G*B, *L), kernel
+    (G*Cout/g, B, *Lout), groups = G, stride <-> dilation)."""
+    cin, cout = x.shape[1], gy.shape[1]
     ig, og = cin // groups, cout // groups
-    outs = []
-    for g in range(groups):
-        xs = _swap(x[:, g * ig:(g + 1) * ig])       # (ig, B, *L)      "batch" = input channel, "channels" = batch
-        gs = _swap(gy[:, g * og:(g + 1) * og])      # (og, B, *Lout)   kernel: out = output channel, in = batch
-        r = _raw_conv(False, xs, gs, None, dilation, padding, 0, stride, 1)  # (ig, og, *K')
-        outs.append(_swap(_crop(r, ksize)))         # (og, ig, *K)
-    return torch.cat(outs, 0)
+    xs = _to_group_major(x, groups, True)    # (ig, G*B, *L)
+    gs = _to_group_major(gy, groups, False)  # (G*og, B, *Lout)
+    r = _crop(_raw_conv(False, xs, gs, None, dilation, padding, 0, stride, groups), ksize)  # (ig, G*og, *K)
+    tail = tuple(range(3, 3 + len(ksize)))
+    return r.reshape(ig, groups, og, *ksize).permute(1, 2, 0, *tail).reshape(cout, ig, *ksize)
 
 
 def _grad_weight_tr(x: Tensor, gy: Tensor, ksize, stride, padding, dilation, groups: int) -> Tensor:
-    """grad_w[i, o, m] = sum_{b, q} x[b, i, q] * gypad[b, o, q*t + m*d]  -> (Cin, Cout/g, *K)."""
-    B, cin = x.shape[:2]
-    cout = gy.shape[1]
+    """grad_w[i, o, m] = sum_{b, q} x[b, i, q] * gypad[b, o, q*t + m*d]  -> (Cin, Cout/g, *K); one grouped convolution."""
+    cin, cout = x.shape[1], gy.shape[1]
     ig, og = cin // groups, cout // groups
-    outs = []
-    for g in range(groups):
-        gs = _swap(gy[:, g * og:(g + 1) * og])      # (og, B, *Lout)  signal
-        xs = _swap(x[:, g * ig:(g + 1) * ig])       # (ig, B, *L)     kernel
-        r = _raw_conv(False, gs, xs, None, dilation, padding, 0, stride, 1)  # (og, ig, *K')
-        outs.append(_swap(_crop(r, ksize)))         # (ig, og, *K)
-    return torch.cat(outs, 0)
+    gs = _to_group_major(gy, groups, True)  # (og, G*B, *Lout)  signal
+    xs = _to_group_major(x, groups, False)  # (G*ig, B, *L)      kernel
+    r = _crop(_raw_conv(False, gs, xs, None, dilation, padding, 0, stride, groups), ksize)  # (og, G*ig, *K)
+    tail = tuple(range(3, 3 + len(ksize)))
+    return r.reshape(og, groups, ig, *ksize).permute(1, 2, 0, *tail).reshape(cin, og, *ksize)
 
 
 class _FFTConvFn(torch.autograd.Function):

@@ -1066,23 +1066,27 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
         const fc_contract_desc& c = plan->contract;
         rc = launch_contract((const float2*)xspec, (const float2*)d_kspec, (float2*)yspec, c.bins, c.batch, c.cin, c.cout, c.groups, st);
       } break;
-      case FC_L_TC_X: {
+      case FC_L_TC_X: {  // batches [b0, b0 + nb) of the chunk: signal spectrum -> GEMM operand blobs
         const fc_contract_desc& c = plan->contract;
-        const int bp = tc_padded_batch(c.batch);
+        const int b0 = (int)L.pass.in_os, nb = (int)L.pass.n_outer;
+        const int bp = tc_padded_batch(nb);
         rc = FC_OK;
-        if (bp != c.batch) {
-          cudaError_t e = cudaMemsetAsync(ws + plan->off_xtc, 0, (size_t)(plan->off_ytc - plan->off_xtc), st);
+        if (bp != nb) {
+          const size_t xtc_bytes = (size_t)c.bins * c.groups * 2 * bp * 2 * (c.cin / c.groups) * 4;
+          cudaError_t e = cudaMemsetAsync(ws + plan->off_xtc, 0, xtc_bytes, st);
           if (e != cudaSuccess) rc = set_err((int)e, "tc operand memset failed");
         }
-        if (!rc) rc = launch_tc_relayout(1, xspec, ws + plan->off_xtc, c.bins, c.batch, c.cin, c.cout, c.groups, st);
+        if (!rc)
+          rc = launch_tc_relayout(1, (const float2*)xspec + (int64_t)b0 * c.cin * c.bins, ws + plan->off_xtc, c.bins, nb, c.cin, c.cout, c.groups, st);
       } break;
       case FC_L_TC_GEMM: {
         const fc_contract_desc& c = plan->contract;
-        rc = launch_tc_gemm(d_kspec, (const float*)(ws + plan->off_xtc), (float*)(ws + plan->off_ytc), c.bins, c.batch, c.cin, c.cout, c.groups, st);
+        rc = launch_tc_gemm(d_kspec, (const float*)(ws + plan->off_xtc), (float*)(ws + plan->off_ytc), c.bins, (int)L.pass.n_outer, c.cin, c.cout, c.groups, st);
       } break;
       case FC_L_TC_Y: {
         const fc_contract_desc& c = plan->contract;
-        rc = launch_tc_relayout(2, ws + plan->off_ytc, yspec, c.bins, c.batch, c.cin, c.cout, c.groups, st);
+        const int b0 = (int)L.pass.in_os, nb = (int)L.pass.n_outer;
+        rc = launch_tc_relayout(2, ws + plan->off_ytc, (float2*)yspec + (int64_t)b0 * c.cout * c.bins, c.bins, nb, c.cin, c.cout, c.groups, st);
       } break;
       default:
         rc = launch_fused(plan, L.fused, buf_ptr(b, L.src), (const float2*)d_kspec, buf_ptr(b, L.dst), tw, st, d_y, d_bias);

@@ -741,8 +741,11 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   // tensor-core contraction (fc_tc.cuh): wide channel groups, small batch
   {
     const int Og = P.cout / P.groups;
-    const int bp = P.batch <= 8 ? 8 : (P.batch + 7) / 8 * 8;
-    pl->use_tc = !(P.flags & (FC_FLAG_NO_TC | FC_FLAG_NO_FUSED)) && Ig >= 32 && (2 * Ig) % 32 == 0 && Og % 128 == 0 && bp <= 32;
+    // batches run through the GEMM in chunks of up to 32 (N = 2 * 32 accumulator columns per 128-row tile); the operand
+    // scratch is sized for one chunk, padded to a multiple of 8
+    const int bc = P.batch < 32 ? P.batch : 32;
+    const int bp = bc <= 8 ? 8 : (bc + 7) / 8 * 8;
+    pl->use_tc = !(P.flags & (FC_FLAG_NO_TC | FC_FLAG_NO_FUSED)) && Ig >= 32 && (2 * Ig) % 32 == 0 && Og % 128 == 0;
 #ifdef FC_CPU_EMUL
     pl->use_tc = 0;  // tcgen05 cannot run in the host emulation
 #endif
@@ -1027,20 +1030,26 @@ void fc_plan_build_program(fc_plan* pl) {
                    (int64_t)P.batch * P.cout * bs.pass.R * bs.pass.n_out);
     pl->prog.push_back(L);
   } else if (pl->use_tc) {
-    const int bp = P.batch <= 8 ? 8 : (P.batch + 7) / 8 * 8;
-    const int64_t xtc = pl->info.bins * P.groups * 2 * bp * 2 * Ig * 4, ytc = pl->info.bins * P.cout * 2 * bp * 4;
     const char* names[3] = {"tc_relayout_x", "tc_gemm_3xtf32", "tc_relayout_y"};
-    const int64_t bytes[3] = {pl->info.xspec_bytes + xtc, pl->info.kspec_bytes + xtc + ytc, ytc + pl->info.yspec_bytes};
-    for (int j = 0; j < 3; ++j) {
-      fc_launch L;
-      L.type = FC_L_TC_X + j;
-      std::memset(&L.pass, 0, sizeof(L.pass));
-      std::memset(&L.fused, 0, sizeof(L.fused));
-      L.src = L.dst = FC_BUF_SPEC;
-      L.spec_is_y = 0;
-      L.name = names[j];
-      L.bytes = bytes[j];
-      pl->prog.push_back(L);
+    for (int b0 = 0; b0 < P.batch; b0 += 32) {  // chunks of up to 32 batches: pass.in_os = first batch, pass.n_outer = batches of the chunk
+      const int nb = P.batch - b0 < 32 ? P.batch - b0 : 32;
+      const int bp = nb <= 8 ? 8 : (nb + 7) / 8 * 8;
+      const int64_t xtc = pl->info.bins * P.groups * 2 * bp * 2 * Ig * 4, ytc = pl->info.bins * P.cout * 2 * bp * 4;
+      const int64_t xs = pl->info.xspec_bytes / P.batch * nb, ys = pl->info.yspec_bytes / P.batch * nb;
+      const int64_t bytes[3] = {xs + xtc, pl->info.kspec_bytes + xtc + ytc, ytc + ys};
+      for (int j = 0; j < 3; ++j) {
+        fc_launch L;
+        L.type = FC_L_TC_X + j;
+        std::memset(&L.pass, 0, sizeof(L.pass));
+        std::memset(&L.fused, 0, sizeof(L.fused));
+        L.pass.in_os = b0;
+        L.pass.n_outer = nb;
+        L.src = L.dst = FC_BUF_SPEC;
+        L.spec_is_y = 0;
+        L.name = std::string(names[j]) + (P.batch > 32 ? "_b" + std::to_string(b0) : "");
+        L.bytes = bytes[j];
+        pl->prog.push_back(L);
+      }
     }
   } else {
     fc_launch L;

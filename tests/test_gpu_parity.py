@@ -651,8 +651,9 @@ def test_pair_kernels_match_one_line_kernels_and_torch(xs, ws, tr, kw):
 
 
 def test_host_pipeline_chunks_keep_the_full_batch_spectrum_layout():
-    """a full batch > 32 builds a pass-order kernel spectrum (SIMT contraction); its batch chunks would
-    qualify for the tensor-core layout on their own and must not pick it."""
+    """the batch chunks of the host pipeline run on the kernel spectrum of the full-batch plan, so both must
+    choose the same spectrum layout (round 1: a batch > 32 stayed on the SIMT layout while its chunks picked the
+    tensor-core one; now batches > 32 run the tensor-core GEMM in chunks of 32 and the layouts agree by construction)."""
     g = torch.Generator().manual_seed(5)
     x = torch.randn(40, 32, 2048, generator=g)
     w = torch.randn(128, 32, 9, generator=g)
@@ -676,3 +677,18 @@ def test_two_devices_in_one_process():
         with torch.no_grad():
             y = fcp.fft_conv(x.to(f"cuda:{d}"), w.to(f"cuda:{d}"))
         assert rel_err(y.cpu().numpy(), ref) < TOL
+
+
+def test_tensor_core_contraction_in_batch_chunks():
+    """Batches above 32 run the tcgen05 GEMM in chunks of up to 32 batches (here 32 + 8)."""
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(40, 32, 2048, generator=g).cuda()
+    w = torch.randn(128, 32, 9, generator=g).cuda()
+    b = torch.randn(128, generator=g).cuda()
+    e = Fn.get_plan(False, 40, 32, 128, 1, (2048,), (9,), (1,), (0,), (1,), (0,), "constant")
+    d = e.plan.describe()
+    assert int(e.plan.info.tensor_core) == 1 and "tc_gemm_3xtf32_b32" in d, d
+    with torch.no_grad():
+        y = fcp.fft_conv(x, w, b)
+        ref = F.conv1d(x.double(), w.double(), b.double())
+    assert (y.double() - ref).abs().max().item() / ref.abs().max().item() < TOL
