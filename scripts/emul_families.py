@@ -20,7 +20,7 @@ CASES = [
     ("k1k4_group_c2c_contract", (2, 8, 70, 70), (8, 8, 7, 7), False, {}, L.FC_FLAG_NO_PAIR),
     ("fused_plain", (2, 8, 256, 256), (8, 8, 9, 9), False, {}, L.FC_FLAG_NO_PAIR),
     ("fused_general_seg", (1, 16, 560, 300), (16, 8, 9, 9), True, dict(stride=2, dilation=2, groups=2, padding=2), L.FC_FLAG_NO_PAIR),
-    ("pair_plain", (4, 8, 256, 256), (8, 8, 9, 9), False, {}, L.FC_FLAG_PAIR),
+    ("pair_plain", (4, 8, 256, 256), (8, 8, 9, 9), False, {}, L.FC_FLAG_PAIR | L.FC_FLAG_NO_YSTAGE),
     ("pair_general_odd_batch", (3, 8, 200, 180), (8, 8, 5, 7), False, dict(padding=(1, 2)), L.FC_FLAG_PAIR),
     ("pair_seg_lattice_16", (2, 32, 560, 300), (32, 16, 9, 9), True, dict(stride=2, dilation=2, groups=2, padding=2), L.FC_FLAG_PAIR),
     ("pair_long_rows", (2, 8, 140, 1700), (8, 8, 5, 301), False, {}, L.FC_FLAG_PAIR),
