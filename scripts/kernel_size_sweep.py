@@ -100,19 +100,41 @@ def main():
                         row["reference_gpu_mem_mb"] = peak_mem(lambda: ref.fft_conv(x, w, b)) / 1e6
                     except Exception as e:
                         row["reference_gpu_error"] = str(e)[:120]
+            # forward + backward (the reference's own benchmark creates its inputs with requires_grad=True,
+            # generate_benchmark_plot.py:27): ours through autograd.py, torch's direct convolution, the reference on the GPU
+            def fwd_bwd(fn):
+                xg = x.detach().requires_grad_(True)
+                wg = w.detach().requires_grad_(True)
+                bg = b.detach().requires_grad_(True)
+
+                def run():
+                    xg.grad = wg.grad = bg.grad = None
+                    fn(xg, wg, bg).sum().backward()
+
+                return run
+
+            try:
+                row["ours_fwd_bwd_ms"], _ = timed(fwd_bwd(fcp.fft_conv), max(4, iters // 2))
+                row["direct_fwd_bwd_ms"], _ = timed(fwd_bwd(direct), max(4, iters // 2))
+                if ref is not None:
+                    row["reference_gpu_fwd_bwd_ms"], _ = timed(fwd_bwd(ref.fft_conv), max(4, iters // 2))
+            except Exception as e:  # noqa: BLE001
+                row["fwd_bwd_error"] = str(e)[:120]
             rows.append(row)
             print(json.dumps(row), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "kernel_size_sweep.json"), "w"), indent=1)
     with open(os.path.join(ROOT, "gpurun_out", "kernel_size_sweep.md"), "w") as f:
         f.write("| ndim | input | kernel | ours ms (cached spectrum) | ours ms (cold) | ours transposed ms | direct (cuDNN) ms | direct transposed ms | "
-                "reference fft_conv on GPU ms | ours MB | direct MB | reference MB | rel err vs direct |\n|" + "---|" * 13 + "\n")
+                "reference fft_conv on GPU ms | ours MB | direct MB | reference MB | rel err vs direct | ours fwd+bwd ms | direct fwd+bwd ms | "
+                "reference fwd+bwd ms |\n|" + "---|" * 16 + "\n")
         fmt = lambda v, p=3: "—" if v is None else f"{v:.{p}f}"
         for r in rows:
             f.write(f"| {r['ndim']} | {r['input_size']} | {r['kernel_size']} | {fmt(r.get('ours_ms'))} | {fmt(r.get('ours_cold_ms'))} | "
                     f"{fmt(r.get('ours_transpose_ms'))} | {fmt(r.get('direct_ms'))} | {fmt(r.get('direct_transpose_ms'))} | {fmt(r.get('reference_gpu_ms'))} | "
                     f"{fmt(r.get('ours_mem_mb'), 1)} | {fmt(r.get('direct_mem_mb'), 1)} | {fmt(r.get('reference_gpu_mem_mb'), 1)} | "
-                    f"{r.get('rel_err_vs_direct', float('nan')):.1e} |\n")
+                    f"{r.get('rel_err_vs_direct', float('nan')):.1e} | {fmt(r.get('ours_fwd_bwd_ms'))} | {fmt(r.get('direct_fwd_bwd_ms'))} | "
+                    f"{fmt(r.get('reference_gpu_fwd_bwd_ms'))} |\n")
 
 
 if __name__ == "__main__":
