@@ -14,6 +14,7 @@
 #include "fc_column.cuh"
 #include "fc_plane.cuh"
 #include "fc_tc.cuh"
+#include "fc_stream.cuh"
 #include "fc_plan.h"
 #include "fc_tune.h"
 
@@ -187,6 +188,8 @@ void init_once() {
   fused_set_attr();
   cudaFuncSetAttribute(fc_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   cudaFuncSetAttribute(fc_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+  cudaFuncSetAttribute(fc_stream_r2c_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_stream::smem_bytes(2));
+  cudaFuncSetAttribute(fc_stream_c2r_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_stream::smem_bytes(2));
   cudaGetLastError();
   sms_of[dev] = sms;
   g_num_sms = sms;
@@ -352,7 +355,74 @@ int64_t fast_grid(const fc_pass& p, const fast_cfg& c, size_t smem) {
   return grid > p.n_tiles ? p.n_tiles : grid;
 }
 
-int launch_fast_r2c(const fc_pass& p, const void* in, void* out, const float2* tw, cudaStream_t st) {
+#ifndef FC_CPU_EMUL
+// ---- streaming K1 / K4 (fc_stream.cuh): tensor-map encoder and eligibility
+typedef CUresult (*fc_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+fc_tmap_encode_fn tmap_encoder() {
+  static const fc_tmap_encode_fn fn = []() -> fc_tmap_encode_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return (fc_tmap_encode_fn)p;
+  }();
+  return fn;
+}
+
+// Tensor map of a transposed half spectrum [item][bin][row] (float2) seen as floats: box = 16 rows x 256 bins of one item,
+// 128-byte swizzle (the shared-memory layout fc_stream_* read and write).
+bool encode_spectrum_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t bins, int64_t items, int64_t bin_stride, int64_t item_stride) {
+  fc_tmap_encode_fn enc = tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)(2 * rows), (cuuint64_t)bins, (cuuint64_t)items};
+  const cuuint64_t strides[2] = {(cuuint64_t)bin_stride * 8, (cuuint64_t)item_stride * 8};
+  const cuuint32_t box[3] = {32, 256, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+bool stream_r2c_ok(const fc_pass& p, const void* in, const void* out) {
+  const fc_imap& im = p.imap;
+  return p.M == 256 && p.seg_n == 1 && p.ystage == 0 && p.twiddle == 0 && p.o_c2 == 1 && p.o_q == 1 && im.up == 1 && im.sub == 1 &&
+         im.pad >= 0 && (im.pad & 3) == 0 && im.L > 0 && (im.L & 3) == 0 && im.pad + im.L <= 2 * p.M && p.in_es == 1 && (p.in_rs & 3) == 0 &&
+         (p.o_sA & 3) == 0 && aligned16(in) && p.out_rs == 1 && (p.out_es & 1) == 0 && (p.out_os & 1) == 0 && (p.R & 1) == 0 && aligned16(out) &&
+         p.n_tiles < (1ll << 30) && p.n_outer < (1ll << 31);
+}
+
+bool stream_c2r_ok(const fc_pass& p, const void* in, const void* out) {
+  const fc_omap& om = p.omap;
+  return p.M == 256 && p.seg_n == 1 && p.ystage == 0 && p.twiddle == 0 && om.os == 1 && om.ob == 0 && om.og == 1 && !(om.Lout & 1) &&
+         !(p.out_rs & 1) && !(p.out_os & 1) && p.row_og == 1 && p.in_rs == 1 && (p.in_es & 1) == 0 && (p.in_os & 1) == 0 && (p.R & 1) == 0 &&
+         aligned16(in) && (reinterpret_cast<uintptr_t>(out) & 7) == 0 && p.n_tiles < (1ll << 30) && p.n_outer < (1ll << 31);
+}
+#endif
+
+int launch_fast_r2c(const fc_pass& p, const void* in, void* out, const float2* tw, cudaStream_t st, bool allow_stream) {
+#ifndef FC_CPU_EMUL
+  if (allow_stream && stream_r2c_ok(p, in, out)) {
+    fc_stream_r2c_args sa;
+    if (encode_spectrum_tmap(&sa.tmap, out, p.R, p.M + 1, p.n_outer, p.out_es, p.out_os)) {
+      sa.p = p;
+      sa.x = (const float*)in;
+      sa.out = (float2*)out;
+      sa.tw = tw;
+      sa.whole_tiles = (p.imap.pad == 0 && p.imap.L == 2 * p.M && p.in_rs == 2 * p.M && p.R % 16 == 0) ? 1 : 0;
+      int64_t grid = (int64_t)g_num_sms * 3;
+      if (grid > p.n_tiles) grid = p.n_tiles;
+      if (grid < 1) return FC_OK;
+      FC_LAUNCH(fc_stream_r2c_kernel<2>, dim3((unsigned)grid), dim3(256), (size_t)fc_stream::smem_bytes(2), st, sa);
+      rec_mark();
+      return check_cuda("streaming r2c launch");
+    }
+  }
+#endif
   fc_fast_r2c_args a;
   a.p = p;
   a.x = (const float*)in;
@@ -377,7 +447,26 @@ int launch_fast_r2c(const fc_pass& p, const void* in, void* out, const float2* t
   return check_cuda("fast r2c launch");
 }
 
-int launch_fast_c2r(const fc_pass& p, const void* in, void* out, const float2* tw, const float* bias, cudaStream_t st) {
+int launch_fast_c2r(const fc_pass& p, const void* in, void* out, const float2* tw, const float* bias, cudaStream_t st, bool allow_stream) {
+#ifndef FC_CPU_EMUL
+  if (allow_stream && stream_c2r_ok(p, in, out)) {
+    fc_stream_c2r_args sa;
+    if (encode_spectrum_tmap(&sa.tmap, in, p.R, p.M + 1, p.n_outer, p.in_es, p.in_os)) {
+      sa.p = p;
+      sa.p.has_bias = bias ? 1 : 0;
+      sa.in = (const float2*)in;
+      sa.out = (float*)out;
+      sa.tw = tw;
+      sa.bias = bias;
+      int64_t grid = (int64_t)g_num_sms * 3;
+      if (grid > p.n_tiles) grid = p.n_tiles;
+      if (grid < 1) return FC_OK;
+      FC_LAUNCH(fc_stream_c2r_kernel<2>, dim3((unsigned)grid), dim3(256), (size_t)fc_stream::smem_bytes(2), st, sa);
+      rec_mark();
+      return check_cuda("streaming c2r launch");
+    }
+  }
+#endif
   fc_fast_c2r_args a;
   a.p = p;
   a.p.has_bias = bias ? 1 : 0;
@@ -1034,10 +1123,10 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
         rc = launch_pass(plan, L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, d_bias, st);
         break;
       case FC_L_FAST_R2C:
-        rc = launch_fast_r2c(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, st);
+        rc = launch_fast_r2c(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, st, (plan->prob.flags & FC_FLAG_STREAM_R2C) != 0);
         break;
       case FC_L_FAST_C2R:
-        rc = launch_fast_c2r(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, d_bias, st);
+        rc = launch_fast_c2r(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, d_bias, st, !(plan->prob.flags & FC_FLAG_NO_STREAM));
         break;
       case FC_L_FAST_C2C:
         rc = launch_fast_c2c(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, st);

@@ -83,7 +83,9 @@ enum {
   FC_FLAG_NO_PAIR = 256,    /* keep the fused 2-d program on the one-line-per-item kernels (no packed batch pairs) */
   FC_FLAG_PAIR = 512,       /* run it on the packed batch-pair kernels wherever they apply (default: where they measured faster) */
   FC_FLAG_NO_YSTAGE = 1024, /* pair program: keep the whole transform of the fused axis inside the fused kernel */
-  FC_FLAG_NO_ROW_FILL = 2048 /* transposed row lattices: leave the bias-only rows to the last kernel (A/B timing) */
+  FC_FLAG_NO_ROW_FILL = 2048, /* transposed row lattices: leave the bias-only rows to the last kernel (A/B timing) */
+  FC_FLAG_NO_STREAM = 4096,  /* keep K4 on the register-path kernel (no tensor-map streaming, fc_stream.cuh; tests, A/B timing) */
+  FC_FLAG_STREAM_R2C = 8192  /* run K1 on the bulk-copy / tensor-map-store kernel too (measured equal to the register path at BASELINE c2) */
 };
 
 typedef struct fc_plan fc_plan; /* opaque */

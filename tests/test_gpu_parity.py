@@ -692,3 +692,41 @@ def test_tensor_core_contraction_in_batch_chunks():
         y = fcp.fft_conv(x, w, b)
         ref = F.conv1d(x.double(), w.double(), b.double())
     assert (y.double() - ref).abs().max().item() / ref.abs().max().item() < TOL
+
+
+# ---- streaming K1 / K4 (csrc/fc_stream.cuh: bulk-copy loads, tensor-map transposing copies) against the register-path
+# kernels: the arithmetic is the same, so the outputs must be bit-identical; and against F.conv2d in float64.
+_STREAM_CASES = [
+    ((2, 8, 512, 512), (8, 8, 65, 65), {}),                       # BASELINE c2 geometry, two batch items: whole 32 KB tiles
+    ((2, 8, 448, 448), (8, 8, 65, 65), dict(padding=32)),         # zero padding: per-row copies of 448 floats at offset 32
+    ((3, 4, 200, 448), (4, 4, 17, 33), dict(padding=(8, 16))),    # 216 rows: partial last tile
+    ((2, 8, 250, 500), (8, 8, 9, 13), {}),                        # 500-float rows (16-byte multiple), 250 rows
+    ((2, 8, 250, 498), (8, 8, 9, 13), {}),                        # 498-float rows: K1 stays on the register path, K4 streams
+    ((1, 8, 100, 512), (16, 8, 5, 5), {}),
+]
+
+
+@pytest.mark.parametrize("xs,ws,kw", _STREAM_CASES)
+def test_streaming_row_kernels_match_register_path_bitwise(xs, ws, kw):
+    from fft_conv_pytorch_b200 import _lib as L
+
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(*xs, generator=g).cuda()
+    w = torch.randn(*ws, generator=g).cuda()
+    b = torch.randn(ws[0], generator=g).cuda()
+    out = {}
+    try:
+        # default: K4 streams; both: K1 streams too; none: register-path K1 / K4
+        for name, flags in (("default", 0), ("both", L.FC_FLAG_STREAM_R2C), ("none", L.FC_FLAG_NO_STREAM)):
+            Fn.set_default_flags(flags)
+            Fn.clear_caches()
+            with torch.no_grad():
+                out[name] = fcp.fft_conv(x, w, b, **kw).clone()
+    finally:
+        Fn.set_default_flags(0)
+        Fn.clear_caches()
+    with torch.no_grad():
+        ref = F.conv2d(x.double(), w.double(), b.double(), **kw)
+    assert torch.equal(out["default"], out["none"])
+    assert torch.equal(out["both"], out["none"])
+    assert (out["default"].double() - ref).abs().max().item() / ref.abs().max().item() < TOL
