@@ -923,7 +923,7 @@ int launch_pair_fused64(const fc_plan* pl, const fc_fused_desc& f, const void* i
 int tc_padded_batch(int batch) { return batch <= 8 ? 8 : (batch + 7) / 8 * 8; }
 bool tc_supported(int batch, int cin, int cout, int groups) {
   const int I = cin / groups, O = cout / groups;
-  return I >= 32 && (2 * I) % 32 == 0 && O % 128 == 0 && tc_padded_batch(batch) <= 32;
+  return I >= 32 && (2 * I) % 32 == 0 && O % 128 == 0 && tc_padded_batch(batch) <= FC_TC_MAX_BATCH;
 }
 
 int launch_tc_relayout(int mode, const void* in, void* out, int64_t bins, int batch, int cin, int cout, int groups, cudaStream_t st) {
@@ -937,7 +937,6 @@ int launch_tc_relayout(int mode, const void* in, void* out, int64_t bins, int ba
   a.B = batch;
   a.Bp = tc_padded_batch(batch);
   a.Og = cout / groups;
-  a.MT = (a.Og % 256 == 0) ? 2 : 1;
   a.mode = mode;
   a.rows = mode == 0 ? cout * a.I : (mode == 1 ? batch * cin : cout * a.Bp);
   dim3 g((unsigned)((bins + 31) / 32), (unsigned)((a.rows + 31) / 32)), b(256);
@@ -961,7 +960,10 @@ int launch_tc_gemm(const float* A, const float* Bt, float* D, int64_t bins, int 
   a.I = cin / groups;
   a.B = tc_padded_batch(batch);
   const int N = 2 * a.B;
-  const int MT = (a.O % 256 == 0) ? 2 : 1;
+  // two 128-row tiles per pass (the Bt chunk is fetched once for both) while three stages and two accumulator sets fit:
+  // 3 * (2*MT*16 KB + 2*N*128 B) <= 223 KB and 2*MT*N <= 512 TMEM columns -> N <= 32 for MT = 2, N <= 160 for MT = 1
+  const int MT = (a.O % 256 == 0 && N <= 32) ? 2 : 1;
+  if (N > 2 * FC_TC_MAX_BATCH) return set_err(FC_EUNSUPPORTED, "tensor-core contraction: batch chunk too wide");
   const size_t stage = (size_t)2 * MT * 128 * 128 + 2 * (size_t)N * 128;
   const size_t smem = FC_TC_STAGES * stage + 1024;
   int64_t grid = a.n_items < g_num_sms ? a.n_items : g_num_sms;
@@ -1189,7 +1191,7 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
 int fc_conv_host(const fc_plan* plan, const void* d_const, const float* h_x, float* d_x_stage, const float* d_kspec, const float* d_bias,
                  float* d_y_stage, float* h_y, void* d_ws, void* stream) {
   if (!plan || !h_x || !d_x_stage || !d_y_stage || !h_y) return set_err(FC_ENULL, "fc_conv_host: NULL argument");
-  const fc_problem& P = plan->prob;
+  const fc_problem& P = plan->user_prob;  // the caller's tensors (a batch-segmented plan runs a windowed problem)
   int64_t in_elems = (int64_t)P.batch * P.cin;
   for (int i = 0; i < P.ndim; ++i) in_elems *= P.in_size[i];
   cudaError_t e = cudaMemcpyAsync(d_x_stage, h_x, (size_t)in_elems * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream);

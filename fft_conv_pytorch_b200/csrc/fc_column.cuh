@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(128, 4) fc_col_r2c_kernel(fc_col_args a) {
   const int64_t o = id / p.R, r = id - o * p.R;
   const int64_t o1 = o / p.o_c2, o2 = o - o1 * p.o_c2;
   const float* x = reinterpret_cast<const float*>(a.in) + (o1 / p.o_q) * p.o_sA + (o1 % p.o_q) * p.o_sB + o2 * p.o_sC;
-  const fc_imap im = p.imap;
+  fc_imap im = p.imap;
+  if (p.bseg_n > 1) im.pad -= (int)(o1 % p.bseg_n) * p.bseg_V;  // batch segment (o_c2 = bseg_c, o_q = bseg_n): its window of the line
   const int hi = (im.ext - im.pad < im.L) ? im.ext - im.pad : im.L;  // PLAIN: source index s = u - pad is live for 0 <= s < hi
   float2 z[M];
 #pragma unroll
@@ -170,6 +171,14 @@ __global__ void __launch_bounds__(128) fc_col_c2r_kernel(fc_col_args a) {
   const fc_omap om = p.omap;
   const float b = (p.has_bias && a.bias) ? __ldg(a.bias + (o % (p.cout > 0 ? p.cout : 1))) : 0.f;
   float* y = reinterpret_cast<float*>(a.out) + o * p.out_os;
+  int lout = om.Lout;
+  if (p.bseg_n > 1) {  // batch segment: its run of the user's output line
+    const int64_t ob = o / p.bseg_c;
+    const int sg = (int)(ob % p.bseg_n);
+    y = reinterpret_cast<float*>(a.out) + ((ob / p.bseg_n) * p.bseg_c + (o - ob * p.bseg_c)) * (int64_t)p.bseg_Lout + (int64_t)sg * p.bseg_Vo;
+    const int left = p.bseg_Lout - sg * p.bseg_Vo;
+    if (left < lout) lout = left;
+  }
   const bool plain = om.og == 1 && om.os == 1;
 #pragma unroll
   for (int n = 0; n < FC_COL_N; ++n) {
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(128) fc_col_c2r_kernel(fc_col_args a) {
     const int u = n * p.pos_n + (int)r;  // dense position
     if (plain) {
       const int j = u - om.ob;
-      if (j >= 0 && j < om.Lout) y[j] = ((u < om.lim) ? val : 0.f) + b;
+      if (j >= 0 && j < lout) y[j] = ((u < om.lim) ? val : 0.f) + b;
     } else {
       for (int e = 0; e < om.og; ++e) {  // dense sample u owns the outputs j with (j*os + ob) / og == u
         const int t = u * om.og + e - om.ob;
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(128) fc_col_c2r_kernel(fc_col_args a) {
           if (t % om.os) continue;
           j = t / om.os;
         }
-        if (j >= om.Lout) continue;
+        if (j >= lout) continue;
         y[j] = ((e == 0 && u < om.lim) ? val : 0.f) + b;
       }
     }

@@ -248,6 +248,8 @@ struct fc_line_info {
   int64_t r;  // line index inside the outer item (twiddle / composite position)
   int32_t valid;
   int32_t bias_idx;
+  int32_t shift;  // batch segments (fc_pass::bseg_*), R2C: dense offset of this item's segment, added to the gather position
+  int32_t lout;   // C2R: outputs of this line (omap.Lout, or what is left of the user's line for the last batch segment)
 };
 
 #define FC_MAX_T 128
@@ -304,6 +306,19 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
       li.r = r;
       li.valid = valid;
       li.bias_idx = (int)(o % (p.cout > 0 ? p.cout : 1));
+      li.shift = 0;
+      li.lout = p.omap.Lout;
+      if ((KIND == FC_R2C || KIND == FC_C2R) && p.bseg_n > 1) {
+        const int64_t ob = o / p.bseg_c;                  // (batch, segment) item
+        const int sg = (int)(ob % p.bseg_n);
+        if (KIND == FC_R2C) {
+          li.shift = sg * p.bseg_V;
+        } else {
+          li.out_base = ((ob / p.bseg_n) * p.bseg_c + (o - ob * p.bseg_c)) * (int64_t)p.bseg_Lout + (int64_t)sg * p.bseg_Vo + r * p.out_rs;
+          const int left = p.bseg_Lout - sg * p.bseg_Vo;
+          li.lout = left < p.omap.Lout ? left : p.omap.Lout;
+        }
+      }
       lines[lt] = li;
     }
     __syncthreads();
@@ -336,7 +351,11 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
             off[u] = 2 * (l * pitch + fc_swz(n >> 1)) + (n & 1);
             if (li.valid) {
               const int pos = n * p.pos_n + (int)li.r * p.pos_r;  // dense position < 2^25 (plan limit)
-              const int s = fc_imap_src(p.imap, pos);
+              int s = fc_imap_src(p.imap, pos);
+              if (p.bseg_n > 1) {  // batch segment (plain zero-padding gather): the segment's window of the channel's line
+                s = pos - p.imap.pad + li.shift;
+                if (pos >= p.imap.ext || s < 0 || s >= p.imap.L) s = -1;
+              }
               if (s >= 0) val[u] = __ldg(x + li.in_base + (int64_t)s * p.in_es);
             }
           }
@@ -540,7 +559,7 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
         const int u = n * p.pos_n + (int)li.r * p.pos_r;  // dense position < 2^25 (plan limit)
         if (p.row_og == 1 && om.og == 1 && om.os == 1) {  // plain crop: no division on the common path
           const int j = u - om.ob;
-          if (j >= 0 && j < om.Lout) y[li.out_base + (int64_t)j * p.out_es] = ((u < om.lim) ? val : 0.f) + b;
+          if (j >= 0 && j < li.lout) y[li.out_base + (int64_t)j * p.out_es] = ((u < om.lim) ? val : 0.f) + b;
         } else {
           for (int er = 0; er < p.row_og; ++er) {  // output rows owned by this dense line (one unless row lattice)
             const int jr = (int)li.r * p.row_og + er - p.row_ob;
@@ -554,7 +573,7 @@ __global__ void fc_pass_kernel(fc_pass_args a) {
                 if (t % om.os) continue;
                 j = t / om.os;
               }
-              if (j >= om.Lout) continue;
+              if (j >= li.lout) continue;
               const bool live = (e == 0) && (er == 0) && (u < om.lim);
               yrow[(int64_t)j * p.out_es] = (live ? val : 0.f) + b;
             }

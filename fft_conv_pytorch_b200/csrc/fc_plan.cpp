@@ -459,7 +459,113 @@ int64_t step_out_bytes(const fc_step& s) { return s.pass.n_outer * s.pass.out_os
 
 }  // namespace
 
+namespace {
+int plan_build_core(fc_plan* pl, const fc_problem* prob, std::string* msg);
+
+// ---- 1-d overlap-save with the segments as extra batch items ("batch segments").
+// A 1-d fft_conv of a long line is cut into S windows of Ns points that start V = Vo*stride positions apart; each window is
+// a *valid* convolution of its own and yields the Vo outputs [s*Vo, (s+1)*Vo) of the line. The plan is therefore the plan of
+// the problem (batch B*S, length Ns, padding 0): only its first pass (which reads window s of the user's line, zero padding
+// included) and its last pass (which writes run s of the user's output line) know about the segments (fc_pass::bseg_*).
+// What it buys: the kernel spectrum and the contraction's operand traffic shrink from N to Ns bins per channel pair
+// (BASELINE c4: 65536 -> 16384 points, kernel spectrum 17.2 -> 4.3 GB), and a line just above a power of two no longer
+// pays for the next one (33000 points, K = 64: 5 x 8192 instead of 65536).
+struct bseg_choice {
+  int Ns, S, V, Vo;
+};
+bool choose_batch_segments(const fc_problem& P, bseg_choice* c) {
+  if (P.ndim != 1 || P.transposed || (P.flags & (FC_FLAG_NO_SEGMENT | FC_FLAG_NO_FUSED))) return false;
+  if (P.batch < 1 || P.cin < 1 || P.cout < 1 || P.groups < 1 || P.cin % P.groups || P.cout % P.groups) return false;
+  const int64_t L = P.in_size[0], K = P.kernel_size[0], st = P.stride[0], d = P.dilation[0], pad = P.padding[0];
+  if (L < 1 || K < 1 || st < 1 || d < 1 || pad < 0) return false;
+  if (pad > 0 && P.padding_mode != FC_PAD_CONSTANT) return false;  // the windows see zeros outside the line
+  if (gcd_i((int)st, (int)d) != 1) return false;                    // (polyphase-reduced lattices keep the one-transform plan)
+  const int64_t Kd = (K - 1) * d + 1, Lp = L + 2 * pad;
+  if (Lp < Kd) return false;
+  const int64_t Lout = (Lp - Kd) / st + 1;
+  const int64_t N0 = next_pow2(std::max<int64_t>(Lp, 2));
+  // Cost in bytes moved, from the geometry and the channel counts only (never the batch: the batch chunks of the host
+  // pipeline must agree with the full-batch plan whose kernel spectrum they share): the transform passes move ~24 bytes
+  // per point and channel for a nominal batch of 16, the contraction reads the kernel spectrum once.
+  const double Ig = (double)(P.cin / P.groups);
+  auto cost = [&](double Ns, double S) { return S * Ns * (P.cin + P.cout) * 24.0 * 16.0 + (double)P.cout * Ig * (Ns / 2) * 8.0; };
+  double best = 0.75 * cost((double)N0, 1.0);  // a segmented plan has to be clearly cheaper
+  bool found = false;
+  for (int64_t Ns = 1024; Ns <= N0 / 2; Ns *= 2) {
+    if (Ns < 2 * Kd) continue;  // at least half of a window is output
+    const int64_t Vo = (Ns - Kd) / st + 1, S = (Lout + Vo - 1) / Vo;
+    if (S < 2 || (int64_t)P.batch * S > (1 << 20)) continue;
+    const double cst = cost((double)Ns, (double)S);
+    if (cst < best) {
+      best = cst;
+      found = true;
+      c->Ns = (int)Ns;
+      c->S = (int)S;
+      c->Vo = (int)Vo;
+      c->V = (int)(Vo * st);
+    }
+  }
+  return found;
+}
+}  // namespace
+
 int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
+  bseg_choice c;
+  if (prob && choose_batch_segments(*prob, &c)) {
+    const fc_problem& P = *prob;
+    fc_problem P2 = P;
+    P2.batch = P.batch * c.S;
+    P2.in_size[0] = c.Ns;
+    P2.padding[0] = 0;
+    P2.padding_mode = FC_PAD_CONSTANT;
+    std::string m2;
+    if (plan_build_core(pl, &P2, &m2) == FC_OK && !pl->prog.empty() &&
+        (pl->prog.front().type == FC_L_PASS || pl->prog.front().type == FC_L_COL_R2C) && pl->prog.front().pass.kind == FC_R2C &&
+        (pl->prog.back().type == FC_L_PASS || pl->prog.back().type == FC_L_COL_C2R) && pl->prog.back().pass.kind == FC_C2R &&
+        pl->ax[0].Lout == c.Vo && pl->ax[0].N == c.Ns) {
+      const int64_t Kd = (int64_t)(P.kernel_size[0] - 1) * P.dilation[0] + 1;
+      const int Lout = (int)(((int64_t)P.in_size[0] + 2 * P.padding[0] - Kd) / P.stride[0] + 1);
+      auto patch_in = [&](fc_pass& p) {
+        p.imap.L = P.in_size[0];
+        p.imap.pad = P.padding[0];
+        p.imap.mode = FC_PAD_CONSTANT;
+        p.o_c2 = P.cin;
+        p.o_q = c.S;
+        p.o_sA = (int64_t)P.cin * P.in_size[0];
+        p.o_sB = 0;
+        p.o_sC = P.in_size[0];
+        p.bseg_n = c.S;
+        p.bseg_c = P.cin;
+        p.bseg_V = c.V;
+      };
+      auto patch_out = [&](fc_pass& p) {
+        p.bseg_n = c.S;
+        p.bseg_c = P.cout;
+        p.bseg_Vo = c.Vo;
+        p.bseg_Lout = Lout;
+      };
+      patch_in(pl->sig_fwd.front().pass);
+      patch_in(pl->prog.front().pass);
+      patch_out(pl->inv.back().pass);
+      patch_out(pl->prog.back().pass);
+      pl->user_prob = P;
+      pl->bseg_n = c.S;
+      pl->info.out_size[0] = Lout;
+      pl->info.out_elems = (int64_t)P.batch * P.cout * Lout;
+      pl->info.segments = c.S;
+      return FC_OK;
+    }
+    // (no program this code can drive with segments: fall through to the one-transform plan)
+    *pl = fc_plan();
+  }
+  const int rc = plan_build_core(pl, prob, msg);
+  if (prob) pl->user_prob = *prob;
+  pl->bseg_n = 1;
+  return rc;
+}
+
+namespace {
+int plan_build_core(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   auto fail = [&](int code, const std::string& m) {
     if (msg) *msg = m;
     return code;
@@ -741,9 +847,9 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   // tensor-core contraction (fc_tc.cuh): wide channel groups, small batch
   {
     const int Og = P.cout / P.groups;
-    // batches run through the GEMM in chunks of up to 32 (N = 2 * 32 accumulator columns per 128-row tile); the operand
-    // scratch is sized for one chunk, padded to a multiple of 8
-    const int bc = P.batch < 32 ? P.batch : 32;
+    // batches run through the GEMM in chunks (fc_tc_chunk); the operand scratch is sized for one chunk, padded to a
+    // multiple of 8
+    const int bc = fc_tc_chunk(P.batch);
     const int bp = bc <= 8 ? 8 : (bc + 7) / 8 * 8;
     pl->use_tc = !(P.flags & (FC_FLAG_NO_TC | FC_FLAG_NO_FUSED)) && Ig >= 32 && (2 * Ig) % 32 == 0 && Og % 128 == 0;
 #ifdef FC_CPU_EMUL
@@ -827,6 +933,7 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     return fail(FC_EUNSUPPORTED, "internal: segmented rows without the transposing row kernels");
   return FC_OK;
 }
+}  // namespace
 
 namespace {
 
@@ -1031,8 +1138,9 @@ void fc_plan_build_program(fc_plan* pl) {
     pl->prog.push_back(L);
   } else if (pl->use_tc) {
     const char* names[3] = {"tc_relayout_x", "tc_gemm_3xtf32", "tc_relayout_y"};
-    for (int b0 = 0; b0 < P.batch; b0 += 32) {  // chunks of up to 32 batches: pass.in_os = first batch, pass.n_outer = batches of the chunk
-      const int nb = P.batch - b0 < 32 ? P.batch - b0 : 32;
+    const int bc = fc_tc_chunk(P.batch);
+    for (int b0 = 0; b0 < P.batch; b0 += bc) {  // batch chunks: pass.in_os = first batch, pass.n_outer = batches of the chunk
+      const int nb = P.batch - b0 < bc ? P.batch - b0 : bc;
       const int bp = nb <= 8 ? 8 : (nb + 7) / 8 * 8;
       const int64_t xtc = pl->info.bins * P.groups * 2 * bp * 2 * Ig * 4, ytc = pl->info.bins * P.cout * 2 * bp * 4;
       const int64_t xs = pl->info.xspec_bytes / P.batch * nb, ys = pl->info.yspec_bytes / P.batch * nb;
@@ -1046,7 +1154,7 @@ void fc_plan_build_program(fc_plan* pl) {
         L.pass.n_outer = nb;
         L.src = L.dst = FC_BUF_SPEC;
         L.spec_is_y = 0;
-        L.name = std::string(names[j]) + (P.batch > 32 ? "_b" + std::to_string(b0) : "");
+        L.name = std::string(names[j]) + (P.batch > bc ? "_b" + std::to_string(b0) : "");
         L.bytes = bytes[j];
         pl->prog.push_back(L);
       }
@@ -1205,6 +1313,9 @@ void fc_plan_build_program(fc_plan* pl) {
 std::string fc_plan_to_string(const fc_plan* pl) {
   std::ostringstream os;
   const fc_problem& P = pl->prob;
+  if (pl->bseg_n > 1)
+    os << "batch segments: user problem B=" << pl->user_prob.batch << " L=" << pl->user_prob.in_size[0] << " pad=" << pl->user_prob.padding[0]
+       << " -> " << pl->bseg_n << " windows of " << pl->ax[0].N << " points, " << pl->prog.back().pass.bseg_Vo << " outputs each, run as:\n";
   os << "fft_conv" << (P.transposed ? "_transpose" : "") << " nd=" << pl->nd << " B=" << P.batch << " Cin=" << P.cin
      << " Cout=" << P.cout << " groups=" << P.groups << " structure=" << pl->structure;
   if (pl->structure == FC_S_1D_SPLIT) os << " N1=" << pl->N1 << " N2=" << pl->N2;

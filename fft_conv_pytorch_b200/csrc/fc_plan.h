@@ -23,6 +23,15 @@ inline int fc_fast_tile_lines(int M) { return M >= 256 ? 16 : 4096 / M; }
 inline int fc_pair_nlp(int M) { return M <= 256 ? 2 : 1; }
 inline int fc_pair_tile_lines(int M) { return fc_pair_nlp(M) * 8 * (M >= 256 ? 1 : 256 / M); }
 
+// Tensor-core contraction (fc_tc.cuh): batches run through the GEMM in chunks of up to FC_TC_MAX_BATCH (N = 2 * 80 = 160
+// accumulator columns per 128-row tile: two sets in TMEM, three operand stages in shared memory), split evenly and padded to
+// a multiple of 8.
+#define FC_TC_MAX_BATCH 80
+inline int fc_tc_chunk(int batch) {
+  const int n = (batch + FC_TC_MAX_BATCH - 1) / FC_TC_MAX_BATCH;
+  return (batch + n - 1) / n;
+}
+
 struct fc_step {
   fc_pass pass;
   int src;  // FC_BUF_*
@@ -95,7 +104,9 @@ struct fc_axis {
 };
 
 struct fc_plan {
-  fc_problem prob;
+  fc_problem prob;       // the problem the program runs: the user's, or (batch segments) the windowed one with batch B * bseg_n
+  fc_problem user_prob;  // what the caller asked for (sizes of the caller's tensors)
+  int bseg_n;            // 1-d batch segments per line (fc_plan.cpp; 1: none)
   fc_plan_info info;
   int structure;
   int nd;

@@ -22,7 +22,7 @@
 // ("blobs"): a chunk is 32 consecutive fp32 of the K dimension (one 128-byte row per matrix row), rows in groups of 8
 // (1024 bytes), the eight 16-byte pieces of a row XOR-swizzled with the row index (UMMA SWIZZLE_128B, K-major). A
 // blob is contiguous, so one bulk async copy (cp.async.bulk) moves it into its pipeline stage at full DRAM efficiency.
-//   A blobs : [bin][group][pass][chunk] x (MT*128 rows x 32 fp32)          kernel spectrum, rows = output channels
+//   A blobs : [bin][group][tile][chunk] x (128 rows x 32 fp32)             kernel spectrum, rows = output channels (128 per tile)
 //   Bt blobs: [bin][group][chunk] x (N rows x 32 fp32)                     signal spectrum, rows = (batch, re/im); the
 //             raw values (the tensor core ignores the low 13 mantissa bits = the "hi" operand); like A's, the "lo" operand
 //             (value - truncated value) is derived in shared memory by the GEMM kernel, so it never crosses HBM
@@ -42,7 +42,6 @@ struct fc_tc_relayout_args {
   int32_t rows;  // mode 0: Cout*I, mode 1: B*Cin, mode 2: Cout*Bp (o-major, b inner)
   int32_t O;     // all output channels (G*Og)
   int32_t Og;    // output channels per group
-  int32_t MT;    // 128-row tiles per pass (1 or 2)
   int32_t B;     // real batch
   int32_t Bp;    // padded batch (N = 2*Bp rows of Bt per bin); rows b >= B must be zero-filled by the caller
   int32_t mode;
@@ -70,7 +69,7 @@ __global__ void fc_tc_relayout_kernel(fc_tc_relayout_args a) {
       if (a.mode == 0) {
         const int o = r / a.I, i = r - o * a.I;  // o over all groups
         const int g = o / a.Og, og = o - g * a.Og;
-        const int G = a.O / a.Og, prow = a.MT * 128, passes = a.Og / prow;
+        const int G = a.O / a.Og, prow = 128, passes = a.Og / prow;  // one blob per 128-row tile, whatever the GEMM's tiles per pass
         const int pass = og / prow, row = og - pass * prow;
         const int64_t blob = (((f * G + g) * passes + pass) * n_chunks);
         // K column i holds re, column I + i holds im
@@ -212,16 +211,16 @@ FC_DEV void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 // ------------------------------------------------------------------------------------------------ the GEMM kernel
 struct fc_tc_args {
-  const float* A;   // A blobs  [item][pass][chunk][MT*128 x 32]
+  const float* A;   // A blobs  [item][tile][chunk][128 x 32]
   const float* Bt;  // Bt blobs [item][chunk][N x 32]
   float* D;         // [item][O][N]   product (complex Y[f][g][o][b])
   int64_t n_items;  // bins * G
-  int32_t O, I, B;  // per group; O % 128 == 0, (2I) % 32 == 0, B = padded batch: N = 2B in {16, 32, 48, 64}
+  int32_t O, I, B;  // per group; O % 128 == 0, (2I) % 32 == 0, B = padded batch (multiple of 8): N = 2B <= 160 (MT = 1) or <= 32 (MT = 2)
 };
 
 // One CTA per SM, persistent over (bin, group) items; warp-specialised:
-//   producer (warp 8, one lane): for every chunk, waits until the stage is free and issues two bulk async copies
-//     (A blob, Bt blob) that complete on the stage's "full" mbarrier;
+//   producer (warp 8, one lane): for every chunk, waits until the stage is free and issues the bulk async copies
+//     (MT A blobs, one Bt blob) that complete on the stage's "full" mbarrier;
 //   splitters (warps 0-7): wait "full", derive the low parts of A and Bt in shared memory, fence to the async proxy and
 //     arrive on the stage's "ready" mbarrier; after the last chunk of an item they drain the accumulator
 //     (warps 0-3 / 4-7: the two 128-row tiles) from TMEM straight to global memory and release it ("acc_free");
@@ -284,7 +283,9 @@ __global__ void __launch_bounds__(FC_TC_THREADS, 1) fc_tc_gemm_kernel(fc_tc_args
         const int64_t item = blockIdx.x + (ip / passes) * gridDim.x;
         unsigned char* st = sbase + (size_t)s * stage_bytes;
         mbar_expect_tx(&bar_full[s], (uint32_t)(A_BYTES + B_BYTES));
-        bulk_g2s(st, a.A + (((item * passes + pass) * n_chunks + c) * (int64_t)(A_BYTES / 4)), A_BYTES, &bar_full[s]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)  // the 128-row tiles of this pass are n_chunks blobs apart
+          bulk_g2s(st + mt * 16384, a.A + ((((item * passes + pass) * MT + mt) * n_chunks + c) * (int64_t)4096), 16384, &bar_full[s]);
         bulk_g2s(st + 2 * A_BYTES, a.Bt + ((item * n_chunks + c) * (int64_t)(B_BYTES / 4)), B_BYTES, &bar_full[s]);
       }
     }

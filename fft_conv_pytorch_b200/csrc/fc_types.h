@@ -68,6 +68,12 @@ struct fc_pass {
   // its half spectrum is stored at bin offset s*(N/2+1); on the way back it owns the dense outputs s*seg_V + [0, seg_V),
   // found at local index seg_off + [0, seg_V). seg_V and seg_off are even.
   int32_t seg_n, seg_V, seg_off;
+  // 1-d overlap-save with the segments as extra batch items (fc_plan.cpp, "batch segments"; bseg_n <= 1: none): outer item
+  // o = (b*bseg_n + s)*bseg_c + c of the first R2C / last C2R pass. R2C: segment s reads its channel's line shifted by
+  // s*bseg_V dense positions (imap.pad - s*bseg_V takes the place of imap.pad; the base of the line comes from o_c2 / o_q /
+  // o_sA / o_sC as usual). C2R: it owns the outputs [s*bseg_Vo, (s+1)*bseg_Vo) of line (b*bseg_c + c) of the user's
+  // output, whose lines are bseg_Lout long (out_os is ignored).
+  int32_t bseg_n, bseg_c, bseg_V, bseg_Vo, bseg_Lout;
   float scale;        // forward passes: multiply on store (1/prod(N) folded into the kernel spectrum)
   int64_t twN;        // four-step twiddle modulus
   int64_t n_outer;

@@ -416,3 +416,48 @@ def test_bias_only_rows_come_from_the_fused_kernel():
         y, plan = emul.conv(x, w, b, transposed=True, flags=flags, **kw)
         assert "fused_axis" in plan.describe() and not np.isnan(y).any()
         assert rel_err(y, ref) < 1e-5
+
+
+# ---- 1-d overlap-save with the segments as extra batch items (fc_plan.cpp "batch segments")
+_BSEG_CASES = [
+    ((2, 3, 9000), (4, 3, 33), {}),
+    ((2, 3, 9000), (4, 3, 33), dict(padding=16)),
+    ((1, 4, 9001), (2, 2, 40), dict(padding=7, stride=3, groups=2)),
+    ((2, 2, 20000), (2, 2, 300), dict(padding=150, dilation=2)),
+    ((1, 2, 70000), (3, 2, 129), dict(padding=64)),
+    ((2, 2, 70001), (2, 2, 4100), dict(stride=2)),  # 16384-point windows: the four-step layout with the column kernels
+]
+
+
+@pytest.mark.parametrize("xs,ws,kw", _BSEG_CASES)
+def test_batch_segments_match_direct_convolution(xs, ws, kw):
+    import torch
+    import torch.nn.functional as F
+
+    rng = np.random.RandomState(1)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = rng.standard_normal(ws).astype(np.float32)
+    b = rng.standard_normal(ws[0]).astype(np.float32)
+    y, plan = emul.conv(x, w, b, **kw)
+    assert "batch segments" in plan.describe()
+    assert int(plan.info.segments) > 1 and plan.out_size == (y.shape[-1],)
+    ref = F.conv1d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), **kw).numpy()
+    assert y.shape == ref.shape and not np.isnan(y).any()
+    assert rel_err(y, ref) < 1e-5
+    y1, plan1 = emul.conv(x, w, b, flags=L.FC_FLAG_NO_SEGMENT, **kw)  # the one-transform plan of the same problem
+    assert "batch segments" not in plan1.describe()
+    assert rel_err(y, y1) < 1e-5
+
+
+def test_batch_segment_choice():
+    """BASELINE c4 runs as 5 windows of 16384 points (kernel spectrum 4x smaller); BASELINE c1 (8 channels) keeps one
+    transform; the choice never depends on the batch (the host pipeline's batch chunks share the kernel spectrum)."""
+    c4 = emul.plan_for((16, 256, 65536), (256, 256, 4097))
+    assert int(c4.info.segments) == 5 and c4.fft_size == (16384,) and c4.out_size == (61440,)
+    for B in (1, 3, 40):
+        p = emul.plan_for((B, 256, 65536), (256, 256, 4097))
+        assert (int(p.info.segments), p.fft_size, int(p.info.kspec_bytes)) == (5, (16384,), int(c4.info.kspec_bytes))
+    c1 = emul.plan_for((1, 8, 32768), (8, 8, 1025))
+    assert int(c1.info.segments) == 1 and c1.fft_size == (32768,)
+    just_above = emul.plan_for((4, 8, 33000), (8, 8, 64))
+    assert int(just_above.info.segments) > 1 and just_above.fft_size[0] <= 8192

@@ -730,3 +730,48 @@ def test_streaming_row_kernels_match_register_path_bitwise(xs, ws, kw):
     assert torch.equal(out["default"], out["none"])
     assert torch.equal(out["both"], out["none"])
     assert (out["default"].double() - ref).abs().max().item() / ref.abs().max().item() < TOL
+
+
+# ---- 1-d overlap-save with the segments as extra batch items (fc_plan.cpp "batch segments")
+_BSEG_GPU_CASES = [
+    ((2, 3, 9000), (4, 3, 33), dict(padding=16)),
+    ((1, 4, 9001), (2, 2, 40), dict(padding=7, stride=3, groups=2)),
+    ((2, 8, 70001), (8, 8, 4100), dict(stride=2)),                 # 16384-point windows, fused axis kernel
+    ((3, 64, 40000), (128, 64, 1000), dict(padding=500)),          # tensor-core contraction over (batch, window) items
+    ((2, 128, 66000), (256, 128, 3000), {}),                       # ... with 256 output channels, several GEMM chunks
+    ((4, 8, 33000), (8, 8, 64), {}),                               # a line just above a power of two
+]
+
+
+@pytest.mark.parametrize("xs,ws,kw", _BSEG_GPU_CASES)
+def test_batch_segments_match_one_transform_plan_and_torch(xs, ws, kw):
+    from fft_conv_pytorch_b200 import _lib as L
+
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(*xs, generator=g).cuda()
+    w = torch.randn(*ws, generator=g).cuda()
+    b = torch.randn(ws[0], generator=g).cuda()
+    out = {}
+    try:
+        for name, flags in (("seg", 0), ("one", L.FC_FLAG_NO_SEGMENT)):
+            Fn.set_default_flags(flags)
+            Fn.clear_caches()
+            with torch.no_grad():
+                out[name] = fcp.fft_conv(x, w, b, **kw).clone()
+            d = Fn._plans[next(reversed(Fn._plans))].plan.describe()
+            assert ("batch segments" in d) == (name == "seg"), d
+    finally:
+        Fn.set_default_flags(0)
+        Fn.clear_caches()
+    with torch.no_grad():
+        ref = F.conv1d(x.double(), w.double(), b.double(), **kw)
+    assert out["seg"].shape == ref.shape
+    assert (out["seg"].double() - ref).abs().max().item() / ref.abs().max().item() < TOL
+    assert (out["seg"] - out["one"]).abs().max().item() / ref.abs().max().item() < 2e-5
+
+
+def test_baseline_c4_runs_as_five_windows():
+    e = Fn.get_plan(False, 16, 256, 256, 1, (65536,), (4097,), (1,), (0,), (1,), (0,), "constant", 0)
+    d = e.plan.describe()
+    assert "5 windows of 16384 points" in d and "tc_gemm_3xtf32" in d, d
+    assert e.plan.out_size == (61440,)
