@@ -188,6 +188,10 @@ void init_once() {
   fused_set_attr();
   cudaFuncSetAttribute(fc_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   cudaFuncSetAttribute(fc_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+  cudaFuncSetAttribute(fc_tc_c2c_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  cudaFuncSetAttribute(fc_tc_c2c_inv_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  cudaFuncSetAttribute(fc_tc_c2c_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  cudaFuncSetAttribute(fc_tc_c2c_inv_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   cudaFuncSetAttribute(fc_stream_r2c_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_stream::smem_bytes(2));
   cudaFuncSetAttribute(fc_stream_c2r_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_stream::smem_bytes(2));
   cudaGetLastError();
@@ -980,6 +984,55 @@ int launch_tc_gemm(const float* A, const float* Bt, float* D, int64_t bins, int 
 #endif
 }
 
+// Last forward / first inverse pass writing / reading the GEMM operands directly (fc_tc_c2c_*_kernel).
+int launch_tc_c2c(bool inverse, const fc_plan* pl, const fc_pass& p, const void* lines, void* tc_buf, const float2* tw, cudaStream_t st) {
+#ifdef FC_CPU_EMUL
+  (void)inverse; (void)pl; (void)p; (void)lines; (void)tc_buf; (void)tw; (void)st;
+  return set_err(FC_EUNSUPPORTED, "tensor-core contraction is not available in the host emulation");
+#else
+  const fc_problem& P = pl->prob;
+  fc_tc_c2c_args a;
+  a.tw = tw;
+  a.tw_len = p.tw_len;
+  a.B = P.batch;
+  a.Bp = tc_padded_batch(P.batch);
+  a.G = P.groups;
+  a.I = P.cin / P.groups;
+  a.R = (int)p.R;
+  if (!inverse) {
+    a.in = (const float2*)lines;
+    a.out = (float2*)tc_buf;
+    a.C = P.cin;
+    a.os = p.in_os;
+    a.rs = p.in_rs;
+    a.n_tiles = (int64_t)P.batch * p.R * (P.cin / 32);
+  } else {
+    a.in = (const float2*)tc_buf;
+    a.out = (float2*)const_cast<void*>(lines);
+    a.C = P.cout;
+    a.os = p.out_os;
+    a.rs = p.out_rs;
+    a.n_tiles = (int64_t)((P.batch + 31) / 32) * P.cout * p.R;
+  }
+  const size_t smem = (size_t)32 * (p.N + 1) * sizeof(float2);
+  int64_t grid = (int64_t)g_num_sms * (p.N == 256 ? 3 : 1);
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (grid < 1) return FC_OK;
+  dim3 g((unsigned)grid), b(256);
+  if (p.N == 256) {
+    if (inverse) { auto k = fc_tc_c2c_inv_kernel<256>; FC_LAUNCH(k, g, b, smem, st, a); }
+    else { auto k = fc_tc_c2c_fwd_kernel<256>; FC_LAUNCH(k, g, b, smem, st, a); }
+  } else if (p.N == 512) {
+    if (inverse) { auto k = fc_tc_c2c_inv_kernel<512>; FC_LAUNCH(k, g, b, smem, st, a); }
+    else { auto k = fc_tc_c2c_fwd_kernel<512>; FC_LAUNCH(k, g, b, smem, st, a); }
+  } else {
+    return set_err(FC_EUNSUPPORTED, "no fused transform + operand layout kernel for this line length");
+  }
+  rec_mark();
+  return check_cuda("tc c2c launch");
+#endif
+}
+
 // Resolve a buffer id of a step to a pointer.
 struct Bufs {
   const void* user_in;
@@ -1170,6 +1223,20 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
         if (!rc)
           rc = launch_tc_relayout(1, (const float2*)xspec + (int64_t)b0 * c.cin * c.bins, ws + plan->off_xtc, c.bins, nb, c.cin, c.cout, c.groups, st);
       } break;
+      case FC_L_TC_FWD: {  // (single batch chunk) last forward pass -> Bt blobs
+        const fc_contract_desc& c = plan->contract;
+        const int bp = tc_padded_batch(c.batch);
+        rc = FC_OK;
+        if (bp != c.batch) {
+          const size_t xtc_bytes = (size_t)c.bins * c.groups * 2 * bp * 2 * (c.cin / c.groups) * 4;
+          cudaError_t e = cudaMemsetAsync(ws + plan->off_xtc, 0, xtc_bytes, st);
+          if (e != cudaSuccess) rc = set_err((int)e, "tc operand memset failed");
+        }
+        if (!rc) rc = launch_tc_c2c(false, plan, L.pass, buf_ptr(b, L.src), ws + plan->off_xtc, tw, st);
+      } break;
+      case FC_L_TC_INV:  // product D -> lines of the first inverse pass
+        rc = launch_tc_c2c(true, plan, L.pass, buf_ptr(b, L.dst), ws + plan->off_ytc, tw, st);
+        break;
       case FC_L_TC_GEMM: {
         const fc_contract_desc& c = plan->contract;
         rc = launch_tc_gemm(d_kspec, (const float*)(ws + plan->off_xtc), (float*)(ws + plan->off_ytc), c.bins, (int)L.pass.n_outer, c.cin, c.cout, c.groups, st);

@@ -1209,6 +1209,42 @@ void fc_plan_build_program(fc_plan* pl) {
     L.bytes = pass_bytes(p);
     pl->prog.push_back(L);
   }
+  // Tensor-core contraction with a single batch chunk between two contiguous complex passes: those passes write / read
+  // the GEMM's operand layouts themselves (fc_tc.cuh), and the two relayout kernels and their round trips go away.
+  if (pl->use_tc && allow && !(flags & FC_FLAG_NO_FAST_C2C) && Ig % 32 == 0 && fc_tc_chunk(P.batch) >= P.batch) {
+    int ix = -1;
+    for (size_t i = 0; i < pl->prog.size(); ++i)
+      if (pl->prog[i].type == FC_L_TC_X) ix = (int)i;
+    if (ix >= 1 && ix + 3 < (int)pl->prog.size() && pl->prog[ix + 1].type == FC_L_TC_GEMM && pl->prog[ix + 2].type == FC_L_TC_Y) {
+      fc_launch& F = pl->prog[ix - 1];
+      fc_launch& X = pl->prog[ix];
+      fc_launch& Y = pl->prog[ix + 2];
+      fc_launch& V = pl->prog[ix + 3];
+      const fc_pass& f = F.pass;
+      const fc_pass& v = V.pass;
+      auto tile_len = [](int n) { return n == 256 || n == 512; };
+      const bool f_ok = F.type == FC_L_FAST_C2C && f.kind == FC_C2C_FWD && tile_len(f.N) && plain_gather(f.imap) && f.imap.pad == 0 &&
+                        f.imap.L >= f.N && f.imap.ext >= f.N && f.scale == 1.f && !f.conj_out && f.out_os == f.R * (int64_t)f.N &&
+                        f.out_rs == f.N && f.n_outer == (int64_t)P.batch * P.cin;
+      const bool v_ok = V.type == FC_L_FAST_C2C && v.kind == FC_C2C_INV && tile_len(v.N) && v.omap.og == 1 && v.omap.os == 1 && v.omap.ob == 0 &&
+                        v.omap.Lout == v.N && v.omap.lim >= v.N && v.in_os == v.R * (int64_t)v.N && v.in_rs == v.N &&
+                        v.n_outer == (int64_t)P.batch * P.cout && v.R == f.R && v.N == f.N;
+      if (f_ok && v_ok) {
+        F.type = FC_L_TC_FWD;
+        F.name = "tc_c2c_fwd_N" + std::to_string(f.N);
+        F.bytes = F.bytes / 2 + X.bytes - pl->info.xspec_bytes;  // lines in, Bt blobs out
+        Y.type = FC_L_TC_INV;
+        Y.pass = v;
+        Y.src = V.src;
+        Y.dst = V.dst;
+        Y.spec_is_y = V.spec_is_y;
+        Y.name = "tc_c2c_inv_N" + std::to_string(v.N);
+        Y.bytes = Y.bytes - pl->info.yspec_bytes + V.bytes / 2;  // product in, lines out
+        pl->prog.erase(pl->prog.begin() + ix + 3);
+        pl->prog.erase(pl->prog.begin() + ix);
+      }
+    }
+  }
   pl->info.n_launches = (int)pl->prog.size();
   pl->info.fused = fuse_mid ? 1 : 0;
   // bias-only rows of a row lattice: written by the fused kernel (DRAM idle there) instead of the last one (store-bound)

@@ -16,6 +16,7 @@
 // a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo; the dropped a_lo*b_lo term is 2^-22 relative.
 #pragma once
 #include "fc_kernels.cuh"
+#include "fc_fused.cuh"
 
 // ------------------------------------------------------------------------------------------------ relayouts
 // The GEMM operands live in HBM as the exact shared-memory images of the K-chunks the tensor core consumes
@@ -107,6 +108,133 @@ __global__ void fc_tc_relayout_kernel(fc_tc_relayout_args a) {
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------ transforms fused with the relayouts
+// The relayout kernels above cost a full round trip of the spectra through HBM on either side of the GEMM (BASELINE c4:
+// 1.85 of 6.2 ms). When the neighbouring passes are contiguous complex transforms (the second pass of the four-step 1-d
+// layout) they do the relayout themselves:
+//   fc_tc_c2c_fwd_kernel  last forward pass: a tile is the lines of 32 consecutive input channels of one (batch item, line
+//                         index r); after the transforms the tile is read transposed (one bin, 32 channels = one 128-byte
+//                         K-chunk row) and goes straight into the Bt blobs: four 128-byte runs per bin (re / -im / im / re).
+//   fc_tc_c2c_inv_kernel  first inverse pass: a tile is the lines of 32 consecutive batch items of one (output channel,
+//                         line index r), gathered from the GEMM's product D[bin][o][Bp] in 256-byte runs (one bin, 32 batch
+//                         items), transformed and stored as contiguous lines.
+// Both reuse the warp engine of fc_fused.cuh (two lines per warp in registers, warp-private exchange lines inside the tile).
+struct fc_tc_c2c_args {
+  const float2* in;  // fwd: lines [(b*C + c)][R][N]; inv: D [R*N bins][O][Bp]
+  float2* out;       // fwd: Bt blobs (as float*); inv: lines [(b*O + o)] at out_os, line r at out_rs
+  const float2* tw;
+  int32_t tw_len;
+  int32_t B, Bp;     // batch items of this GEMM chunk and their padded count (N = 2*Bp rows of Bt)
+  int32_t C, I, G;   // channels of the tile axis (fwd: input channels, C = G*I; inv: C = all output channels)
+  int32_t R;         // lines per (batch, channel) item
+  int64_t os, rs;    // item and line stride (complex elements) of the line-ordered side
+  int64_t n_tiles;
+};
+
+#ifndef FC_CPU_EMUL
+template <int N>
+__global__ void __launch_bounds__(256, N == 256 ? 3 : 1) fc_tc_c2c_fwd_kernel(fc_tc_c2c_args a) {
+  fc_grid_dep_sync();
+  constexpr int E = N / 32, LP = N + 1, NL = 2;
+  FC_DYN_SMEM(smem);  // 32 lines of pitch N + 1 (odd: the transposed read of the store phase is conflict-free)
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  fc_wofs ofs;
+  ofs.init(lane);
+  const int cblks = a.C / 32, n_chunks = 2 * a.I / 32, Np = 2 * a.Bp;
+  float* xtc = reinterpret_cast<float*>(a.out);
+  for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const int cblk = (int)(t % cblks);
+    const int64_t t1 = t / cblks;
+    const int r = (int)(t1 % a.R), b = (int)(t1 / a.R);
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+      const int l0 = round * 16 + NL * w;
+      float2* line0 = smem + l0 * LP;
+      float2 v[NL][E];
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const float2* src = a.in + ((int64_t)b * a.C + cblk * 32 + l0 + l) * a.os + (int64_t)r * a.rs;
+#pragma unroll
+        for (int q = 0; q < E; ++q) v[l][q] = fc_ld_stream(src + lane + 32 * q);
+      }
+      fc_wfft<N, NL, LP>(v, line0, ofs, a.tw, a.tw_len, lane);
+      __syncwarp();
+#pragma unroll
+      for (int l = 0; l < NL; ++l)
+#pragma unroll
+        for (int q = 0; q < E; ++q) line0[l * LP + lane + 32 * q] = v[l][q];
+    }
+    __syncthreads();
+    {  // lane = channel of the block; K columns: channel i of the group -> column i (re block) and I + i (im block)
+      const int c0 = cblk * 32, g = c0 / a.I, i0 = c0 - g * a.I;
+      const int ch_re = i0 >> 5, ch_im = (a.I + i0) >> 5;
+      const int row0 = 2 * b, row1 = 2 * b + 1;
+      const int off0 = (row0 >> 3) * 256 + (row0 & 7) * 32 + ((((lane >> 2) ^ (row0 & 7)) << 2) | (lane & 3));
+      const int off1 = (row1 >> 3) * 256 + (row1 & 7) * 32 + ((((lane >> 2) ^ (row1 & 7)) << 2) | (lane & 3));
+      const int64_t blob = (int64_t)Np * 32;  // floats per Bt blob
+      for (int j = w; j < N; j += 8) {
+        const float2 z = smem[lane * LP + j];
+        const int64_t f = (int64_t)r * N + j;
+        float* bre = xtc + ((f * a.G + g) * n_chunks + ch_re) * blob;
+        float* bim = xtc + ((f * a.G + g) * n_chunks + ch_im) * blob;
+        bre[off0] = z.x;   // row 2b   = [ Xr | -Xi ]
+        bim[off0] = -z.y;
+        bre[off1] = z.y;   // row 2b+1 = [ Xi |  Xr ]
+        bim[off1] = z.x;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256, N == 256 ? 3 : 1) fc_tc_c2c_inv_kernel(fc_tc_c2c_args a) {
+  fc_grid_dep_sync();
+  constexpr int E = N / 32, LP = N + 1, NL = 2;
+  FC_DYN_SMEM(smem);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  fc_wofs ofs;
+  ofs.init(lane);
+  const int bblks = (a.B + 31) / 32;
+  for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const int bblk = (int)(t % bblks);
+    const int64_t t1 = t / bblks;
+    const int o = (int)(t1 % a.C), r = (int)(t1 / a.C);
+    const int b = bblk * 32 + lane;
+    {  // gather: bin j of the 32 batch items = one 256-byte run of D
+      const float2* d = a.in + (((int64_t)r * N) * a.C + o) * a.Bp + b;
+      const int64_t dstep = (int64_t)a.C * a.Bp;
+      for (int j = w; j < N; j += 8) {
+        const float2 z = b < a.B ? fc_ld_stream(d + j * dstep) : make_float2(0.f, 0.f);
+        smem[lane * LP + j] = fc_conj(z);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+      const int l0 = round * 16 + NL * w;
+      float2* line0 = smem + l0 * LP;
+      float2 v[NL][E];
+#pragma unroll
+      for (int l = 0; l < NL; ++l)
+#pragma unroll
+        for (int q = 0; q < E; ++q) v[l][q] = line0[l * LP + lane + 32 * q];
+      __syncwarp();
+      fc_wfft<N, NL, LP>(v, line0, ofs, a.tw, a.tw_len, lane);
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const int bb = bblk * 32 + l0 + l;
+        if (bb >= a.B) continue;
+        float2* dst = a.out + ((int64_t)bb * a.C + o) * a.os + (int64_t)r * a.rs;
+#pragma unroll
+        for (int q = 0; q < E; ++q) dst[lane + 32 * q] = fc_conj(v[l][q]);
+      }
+    }
+    __syncthreads();
+  }
+}
+#endif
 
 #ifndef FC_CPU_EMUL
 // ------------------------------------------------------------------------------------------------ tcgen05 helpers

@@ -680,18 +680,51 @@ def test_two_devices_in_one_process():
 
 
 def test_tensor_core_contraction_in_batch_chunks():
-    """Batches above 32 run the tcgen05 GEMM in chunks of up to 32 batches (here 32 + 8)."""
+    """Batches above 80 run the tcgen05 GEMM in even chunks of up to 80 batch items (here 2 x 45); up to 80 in one."""
     g = torch.Generator().manual_seed(6)
-    x = torch.randn(40, 32, 2048, generator=g).cuda()
-    w = torch.randn(128, 32, 9, generator=g).cuda()
-    b = torch.randn(128, generator=g).cuda()
-    e = Fn.get_plan(False, 40, 32, 128, 1, (2048,), (9,), (1,), (0,), (1,), (0,), "constant")
-    d = e.plan.describe()
-    assert int(e.plan.info.tensor_core) == 1 and "tc_gemm_3xtf32_b32" in d, d
-    with torch.no_grad():
-        y = fcp.fft_conv(x, w, b)
-        ref = F.conv1d(x.double(), w.double(), b.double())
-    assert (y.double() - ref).abs().max().item() / ref.abs().max().item() < TOL
+    for B, marker in ((90, "tc_gemm_3xtf32_b45"), (40, "tc_gemm_3xtf32")):
+        x = torch.randn(B, 32, 2048, generator=g).cuda()
+        w = torch.randn(128, 32, 9, generator=g).cuda()
+        b = torch.randn(128, generator=g).cuda()
+        e = Fn.get_plan(False, B, 32, 128, 1, (2048,), (9,), (1,), (0,), (1,), (0,), "constant")
+        d = e.plan.describe()
+        assert int(e.plan.info.tensor_core) == 1 and marker in d, d
+        with torch.no_grad():
+            y = fcp.fft_conv(x, w, b)
+            ref = F.conv1d(x.double(), w.double(), b.double())
+        assert (y.double() - ref).abs().max().item() / ref.abs().max().item() < TOL
+
+
+def test_transforms_next_to_the_tensor_core_gemm_write_its_operands():
+    """Four-step 1-d plans with one GEMM chunk: the contiguous complex passes on either side of the GEMM write the Bt blobs /
+    gather from the product themselves (no relayout kernels); same result as the program with the relayout kernels."""
+    from fft_conv_pytorch_b200 import _lib as L
+
+    g = torch.Generator().manual_seed(8)
+    # (transform lengths 64 x 256 unsegmented with a padded batch, 64 x 512, and 16384-point windows with two groups)
+    for xs, ws, kw, base in (((3, 64, 16384), (128, 64, 1000), {}, 0),
+                             ((5, 32, 32768), (256, 32, 33), {}, L.FC_FLAG_NO_SEGMENT),
+                             ((2, 64, 70001), (256, 32, 4100), dict(groups=2), 0)):
+        x = torch.randn(*xs, generator=g).cuda()
+        w = torch.randn(*ws, generator=g).cuda()
+        b = torch.randn(ws[0], generator=g).cuda()
+        out = {}
+        try:
+            for name, flags in (("fused", base), ("relayout", base | L.FC_FLAG_NO_FAST_C2C)):
+                Fn.set_default_flags(flags)
+                Fn.clear_caches()
+                with torch.no_grad():
+                    out[name] = fcp.fft_conv(x, w, b, **kw).clone()
+                d = Fn._plans[next(reversed(Fn._plans))].plan.describe()
+                assert "tc_gemm_3xtf32" in d, d
+                assert ("tc_c2c_fwd" in d and "tc_c2c_inv" in d and "tc_relayout" not in d) == (name == "fused"), d
+        finally:
+            Fn.set_default_flags(0)
+            Fn.clear_caches()
+        with torch.no_grad():
+            ref = F.conv1d(x.double(), w.double(), b.double(), **kw)
+        assert (out["fused"].double() - ref).abs().max().item() / ref.abs().max().item() < TOL
+        assert (out["fused"] - out["relayout"]).abs().max().item() / ref.abs().max().item() < 2e-5
 
 
 # ---- streaming K1 / K4 (csrc/fc_stream.cuh: bulk-copy loads, tensor-map transposing copies) against the register-path
