@@ -186,8 +186,9 @@ void init_once() {
   FC_PAIR_FUSED64_ALL(FC_PAIR_FUSED64_ATTR)
 #undef FC_PAIR_FUSED64_ATTR
   fused_set_attr();
-  cudaFuncSetAttribute(fc_tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-  cudaFuncSetAttribute(fc_tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+  cudaFuncSetAttribute(fc_tc_gemm_kernel<1, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+  cudaFuncSetAttribute(fc_tc_gemm_kernel<2, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+  cudaFuncSetAttribute(fc_tc_gemm_kernel<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   cudaFuncSetAttribute(fc_tc_c2c_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   cudaFuncSetAttribute(fc_tc_c2c_inv_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   cudaFuncSetAttribute(fc_tc_c2c_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -966,17 +967,23 @@ int launch_tc_gemm(const float* A, const float* Bt, float* D, int64_t bins, int 
   const int N = 2 * a.B;
   // two 128-row tiles per pass (the Bt chunk is fetched once for both) while three stages and two accumulator sets fit:
   // 3 * (2*MT*16 KB + 2*N*128 B) <= 223 KB and 2*MT*N <= 512 TMEM columns -> N <= 32 for MT = 2, N <= 160 for MT = 1
-  const int MT = (a.O % 256 == 0 && N <= 32) ? 2 : 1;
+  // ... and with N >= 96 two tiles per pass on two stages and one accumulator set (fc_tc.cuh, variants)
+  static const int wide2 = fc_tune_int("TC_WIDE2", 1);
+  const bool two = a.O % 256 == 0 && (N <= 32 || (N >= 96 && wide2));
+  const int MT = two ? 2 : 1, stages = (two && N > 32) ? 2 : 3;
   if (N > 2 * FC_TC_MAX_BATCH) return set_err(FC_EUNSUPPORTED, "tensor-core contraction: batch chunk too wide");
   const size_t stage = (size_t)2 * MT * 128 * 128 + 2 * (size_t)N * 128;
-  const size_t smem = FC_TC_STAGES * stage + 1024;
+  const size_t smem = stages * stage + 1024;
   int64_t grid = a.n_items < g_num_sms ? a.n_items : g_num_sms;
   dim3 g((unsigned)grid), b(FC_TC_THREADS);
-  if (MT == 2) {
-    auto k = fc_tc_gemm_kernel<2>;
+  if (MT == 2 && stages == 3) {
+    auto k = fc_tc_gemm_kernel<2, 3, 2>;
+    k<<<g, b, smem, st>>>(a);
+  } else if (MT == 2) {
+    auto k = fc_tc_gemm_kernel<2, 2, 1>;
     k<<<g, b, smem, st>>>(a);
   } else {
-    auto k = fc_tc_gemm_kernel<1>;
+    auto k = fc_tc_gemm_kernel<1, 3, 2>;
     k<<<g, b, smem, st>>>(a);
   }
   rec_mark();

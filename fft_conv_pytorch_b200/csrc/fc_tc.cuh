@@ -354,9 +354,14 @@ struct fc_tc_args {
 //     (warps 0-3 / 4-7: the two 128-row tiles) from TMEM straight to global memory and release it ("acc_free");
 //   MMA issuer (warp 9, one lane): waits "ready", issues the 3 x 4 x MT tcgen05.mma of the chunk into one of two
 //     accumulator sets in TMEM, commits them to the stage's "free" mbarrier and, on the last chunk, to "acc_full".
-#define FC_TC_STAGES 3
+// Variants: <MT, STAGES, NBUF> = tiles of 128 output rows per pass (the Bt chunk is fetched once per pass), operand stages
+// in shared memory, accumulator sets in TMEM:
+//   <2, 3, 2>  N <= 32            (BASELINE c4 unsegmented, 16 batch items)
+//   <1, 3, 2>  N <= 160           (one tile per pass: Bt crosses L2 -> SM once per 128 output rows)
+//   <2, 2, 1>  N <= 160, O % 256  (two tiles per pass on 2 x 104 KB stages and ONE 320-column accumulator set: the issuer
+//                                  waits for the drain of a pass before the next one starts)
 #define FC_TC_THREADS 320
-template <int MT /* 128-row tiles of O per pass: 1 or 2 */>
+template <int MT /* 128-row tiles of O per pass: 1 or 2 */, int FC_TC_STAGES = 3, int NBUF = 2>
 __global__ void __launch_bounds__(FC_TC_THREADS, 1) fc_tc_gemm_kernel(fc_tc_args a) {
   using namespace fc_tc;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -385,7 +390,8 @@ __global__ void __launch_bounds__(FC_TC_THREADS, 1) fc_tc_gemm_kernel(fc_tc_args
     fence_barrier_init();
   }
   const uint32_t acc_cols = (uint32_t)(MT * N);  // columns of one accumulator set
-  const uint32_t tmem_cols = (2 * acc_cols <= 32) ? 32 : (2 * acc_cols <= 64 ? 64 : (2 * acc_cols <= 128 ? 128 : (2 * acc_cols <= 256 ? 256 : 512)));
+  const uint32_t all_cols = NBUF * acc_cols;
+  const uint32_t tmem_cols = (all_cols <= 32) ? 32 : (all_cols <= 64 ? 64 : (all_cols <= 128 ? 128 : (all_cols <= 256 ? 256 : 512)));
   if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -423,9 +429,9 @@ __global__ void __launch_bounds__(FC_TC_THREADS, 1) fc_tc_gemm_kernel(fc_tc_args
       for (int64_t q = 0; q < total; ++q) {
         const int c = (int)(q % n_chunks);
         const int64_t ip = q / n_chunks;  // accumulator use
-        const int buf = (int)(ip & 1);
+        const int buf = (int)(ip % NBUF);
         const int s = (int)(q % FC_TC_STAGES);
-        if (c == 0 && ip >= 2) mbar_wait(&bar_acc_free[buf], (uint32_t)(((ip >> 1) - 1) & 1));  // set drained by the epilogue
+        if (c == 0 && ip >= NBUF) mbar_wait(&bar_acc_free[buf], (uint32_t)(((ip / NBUF) - 1) & 1));  // set drained by the epilogue
         mbar_wait(&bar_ready[s], (uint32_t)((q / FC_TC_STAGES) & 1));
         tc_fence_after();
         unsigned char* st = sbase + (size_t)s * stage_bytes;
@@ -478,10 +484,10 @@ __global__ void __launch_bounds__(FC_TC_THREADS, 1) fc_tc_gemm_kernel(fc_tc_args
       if (c == n_chunks - 1) {
         // ---- epilogue of this (item, pass): TMEM -> registers -> global
         const int64_t ip = q / n_chunks;
-        const int buf = (int)(ip & 1);
+        const int buf = (int)(ip % NBUF);
         const int pass = (int)(ip % passes);
         const int64_t item = blockIdx.x + (ip / passes) * gridDim.x;
-        mbar_wait(&bar_acc_full[buf], (uint32_t)((ip >> 1) & 1));
+        mbar_wait(&bar_acc_full[buf], (uint32_t)((ip / NBUF) & 1));
         tc_fence_after();
         const int mt = warp >> 2;  // warps 0-3: tile 0, warps 4-7: tile 1
         if (mt < MT) {
