@@ -808,3 +808,51 @@ def test_baseline_c4_runs_as_five_windows():
     d = e.plan.describe()
     assert "5 windows of 16384 points" in d and "tc_gemm_3xtf32" in d, d
     assert e.plan.out_size == (61440,)
+
+
+def test_batch_segments_through_every_call_path():
+    """1-d plans that run as batch segments: CPU tensors (one-shot and chunked host pipeline), several GEMM chunks,
+    a captured CUDA graph, the module, and the backward pass — all against torch's direct convolution."""
+    from fft_conv_pytorch_b200.graphs import GraphedConv
+
+    g = torch.Generator().manual_seed(31)
+    # host buffers in and out: B = 1 goes through fc_conv_host, B = 7 through the chunked pipeline (chunk plans share the spectrum)
+    for B in (1, 7):
+        x = torch.randn(B, 6, 34000, generator=g)
+        w = torch.randn(4, 3, 40, generator=g)
+        b = torch.randn(4, generator=g)
+        with torch.no_grad():
+            y = fcp.fft_conv(x, w, b, padding=20, groups=2)
+            ref = F.conv1d(x.double(), w.double(), b.double(), padding=20, groups=2)
+        assert not y.is_cuda and rel_err(y.numpy(), ref.numpy()) < TOL
+    e = Fn.get_plan(False, 7, 6, 4, 2, (34000,), (40,), (1,), (20,), (1,), (0,), "constant")
+    assert int(e.plan.info.segments) > 1
+    # (batch, window) items beyond one tensor-core GEMM chunk of 80
+    x = torch.randn(12, 64, 50000, generator=g).cuda()
+    w = torch.randn(128, 64, 1500, generator=g).cuda()
+    b = torch.randn(128, generator=g).cuda()
+    e = Fn.get_plan(False, 12, 64, 128, 1, (50000,), (1500,), (1,), (0,), (1,), (0,), "constant")
+    d = e.plan.describe()
+    assert "batch segments" in d and "tc_gemm_3xtf32_b" in d, d
+    with torch.no_grad():
+        y = fcp.fft_conv(x, w, b)
+        ref = F.conv1d(x[:, :, :20000], w, b)  # (cuDNN fp32, TF32 off: conftest) the first outputs of every line
+    assert (y[:, :, : ref.shape[-1]].double() - ref.double()).abs().max().item() / ref.double().abs().max().item() < TOL
+    # module under a captured graph
+    m = fcp.FFTConv1d(8, 8, 65, padding=32).cuda()
+    xs = torch.randn(3, 8, 33000, generator=g).cuda()
+    gc = GraphedConv(m, xs)
+    with torch.no_grad():
+        y = gc().clone()
+        ref = F.conv1d(xs.double(), m.weight.double(), m.bias.double(), padding=32)
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < TOL
+    # backward (the adjoint convolutions plan themselves)
+    x0 = torch.randn(2, 4, 20000, generator=g).cuda().requires_grad_()
+    w0 = torch.randn(6, 4, 33, generator=g).cuda().requires_grad_()
+    b0 = torch.randn(6, generator=g).cuda().requires_grad_()
+    x1, w1, b1 = (t.detach().clone().requires_grad_() for t in (x0, w0, b0))
+    gy = torch.randn(2, 6, 19968, generator=g).cuda()
+    (fcp.fft_conv(x0, w0, bias=b0) * gy).sum().backward()
+    (F.conv1d(x1, w1, bias=b1) * gy).sum().backward()
+    for a, r in ((w0.grad, w1.grad), (b0.grad, b1.grad), (x0.grad, x1.grad)):
+        assert rel_err(a.detach().cpu().numpy(), r.detach().cpu().numpy()) < TOL
