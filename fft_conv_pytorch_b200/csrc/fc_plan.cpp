@@ -489,9 +489,14 @@ bool choose_batch_segments(const fc_problem& P, bseg_choice* c) {
   // per point and channel for a nominal batch of 16, the contraction reads the kernel spectrum once.
   const double Ig = (double)(P.cin / P.groups);
   auto cost = [&](double Ns, double S) { return S * Ns * (P.cin + P.cout) * 24.0 * 16.0 + (double)P.cout * Ig * (Ns / 2) * 8.0; };
-  double best = 0.75 * cost((double)N0, 1.0);  // a segmented plan has to be clearly cheaper
+  // a segmented plan has to be clearly cheaper (FC_FLAG_SEGMENT: take the cheapest window length whatever the gain; A/B timing)
+  double best = (P.flags & FC_FLAG_SEGMENT) ? 1e300 : 0.75 * cost((double)N0, 1.0);
   bool found = false;
-  for (int64_t Ns = 1024; Ns <= N0 / 2; Ns *= 2) {
+  // Channel groups the fused axis kernel serves (<= 16 per group) keep the four-step layout and its specialised kernels:
+  // windows of at least 64 x 256 points. (Measured, profiles/r2b_batch_segments_probe.txt: 8 channels, 33000 points, K = 64
+  // runs 0.042 ms on one 65536-point transform against 0.055 ms on 17 windows of 2048 points through the generic passes.)
+  const bool fusable = P.cin / P.groups <= 16 && P.cout / P.groups <= 16;
+  for (int64_t Ns = fusable ? 16384 : 1024; Ns <= N0 / 2; Ns *= 2) {
     if (Ns < 2 * Kd) continue;  // at least half of a window is output
     const int64_t Vo = (Ns - Kd) / st + 1, S = (Lout + Vo - 1) / Vo;
     if (S < 2 || (int64_t)P.batch * S > (1 << 20)) continue;

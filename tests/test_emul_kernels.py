@@ -420,12 +420,14 @@ def test_bias_only_rows_come_from_the_fused_kernel():
 
 # ---- 1-d overlap-save with the segments as extra batch items (fc_plan.cpp "batch segments")
 _BSEG_CASES = [
-    ((2, 3, 9000), (4, 3, 33), {}),
-    ((2, 3, 9000), (4, 3, 33), dict(padding=16)),
-    ((1, 4, 9001), (2, 2, 40), dict(padding=7, stride=3, groups=2)),
-    ((2, 2, 20000), (2, 2, 300), dict(padding=150, dilation=2)),
+    # more than 16 channels per group: windows of 1024 ... 4096 points through the one-pass layout
+    ((2, 20, 9000), (4, 20, 33), {}),
+    ((2, 3, 9000), (18, 3, 33), dict(padding=16)),
+    ((1, 40, 9001), (4, 20, 40), dict(padding=7, stride=3, groups=2)),
+    ((1, 17, 20000), (2, 17, 300), dict(padding=150, dilation=2)),
+    # channel groups the fused axis kernel serves: windows of 16384 points, the four-step layout with the column kernels
     ((1, 2, 70000), (3, 2, 129), dict(padding=64)),
-    ((2, 2, 70001), (2, 2, 4100), dict(stride=2)),  # 16384-point windows: the four-step layout with the column kernels
+    ((2, 2, 70001), (2, 2, 4100), dict(stride=2)),
 ]
 
 
@@ -459,5 +461,7 @@ def test_batch_segment_choice():
         assert (int(p.info.segments), p.fft_size, int(p.info.kspec_bytes)) == (5, (16384,), int(c4.info.kspec_bytes))
     c1 = emul.plan_for((1, 8, 32768), (8, 8, 1025))
     assert int(c1.info.segments) == 1 and c1.fft_size == (32768,)
-    just_above = emul.plan_for((4, 8, 33000), (8, 8, 64))
+    just_above = emul.plan_for((4, 32, 33000), (32, 32, 64))
     assert int(just_above.info.segments) > 1 and just_above.fft_size[0] <= 8192
+    small = emul.plan_for((4, 8, 33000), (8, 8, 64))  # 8 channels: only windows that keep the fused-kernel program
+    assert int(small.info.segments) == 1 or small.fft_size[0] >= 16384

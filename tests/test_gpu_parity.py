@@ -767,12 +767,13 @@ def test_streaming_row_kernels_match_register_path_bitwise(xs, ws, kw):
 
 # ---- 1-d overlap-save with the segments as extra batch items (fc_plan.cpp "batch segments")
 _BSEG_GPU_CASES = [
-    ((2, 3, 9000), (4, 3, 33), dict(padding=16)),
-    ((1, 4, 9001), (2, 2, 40), dict(padding=7, stride=3, groups=2)),
+    ((2, 24, 9000), (4, 24, 33), dict(padding=16)),
+    ((1, 40, 9001), (4, 20, 40), dict(padding=7, stride=3, groups=2)),
     ((2, 8, 70001), (8, 8, 4100), dict(stride=2)),                 # 16384-point windows, fused axis kernel
+    ((1, 8, 70000), (8, 8, 1025), {}),                             # ... 5 windows per line
     ((3, 64, 40000), (128, 64, 1000), dict(padding=500)),          # tensor-core contraction over (batch, window) items
-    ((2, 128, 66000), (256, 128, 3000), {}),                       # ... with 256 output channels, several GEMM chunks
-    ((4, 8, 33000), (8, 8, 64), {}),                               # a line just above a power of two
+    ((2, 128, 66000), (256, 128, 3000), {}),                       # ... with 256 output channels
+    ((4, 32, 33000), (32, 32, 64), {}),                            # a line just above a power of two
 ]
 
 
@@ -818,14 +819,14 @@ def test_batch_segments_through_every_call_path():
     g = torch.Generator().manual_seed(31)
     # host buffers in and out: B = 1 goes through fc_conv_host, B = 7 through the chunked pipeline (chunk plans share the spectrum)
     for B in (1, 7):
-        x = torch.randn(B, 6, 34000, generator=g)
-        w = torch.randn(4, 3, 40, generator=g)
+        x = torch.randn(B, 40, 34000, generator=g)
+        w = torch.randn(4, 20, 40, generator=g)
         b = torch.randn(4, generator=g)
         with torch.no_grad():
             y = fcp.fft_conv(x, w, b, padding=20, groups=2)
             ref = F.conv1d(x.double(), w.double(), b.double(), padding=20, groups=2)
         assert not y.is_cuda and rel_err(y.numpy(), ref.numpy()) < TOL
-    e = Fn.get_plan(False, 7, 6, 4, 2, (34000,), (40,), (1,), (20,), (1,), (0,), "constant")
+    e = Fn.get_plan(False, 7, 40, 4, 2, (34000,), (40,), (1,), (20,), (1,), (0,), "constant")
     assert int(e.plan.info.segments) > 1
     # (batch, window) items beyond one tensor-core GEMM chunk of 80
     x = torch.randn(12, 64, 50000, generator=g).cuda()
@@ -839,16 +840,16 @@ def test_batch_segments_through_every_call_path():
         ref = F.conv1d(x[:, :, :20000], w, b)  # (cuDNN fp32, TF32 off: conftest) the first outputs of every line
     assert (y[:, :, : ref.shape[-1]].double() - ref.double()).abs().max().item() / ref.double().abs().max().item() < TOL
     # module under a captured graph
-    m = fcp.FFTConv1d(8, 8, 65, padding=32).cuda()
-    xs = torch.randn(3, 8, 33000, generator=g).cuda()
+    m = fcp.FFTConv1d(24, 8, 65, padding=32).cuda()
+    xs = torch.randn(3, 24, 33000, generator=g).cuda()
     gc = GraphedConv(m, xs)
     with torch.no_grad():
         y = gc().clone()
         ref = F.conv1d(xs.double(), m.weight.double(), m.bias.double(), padding=32)
     assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < TOL
     # backward (the adjoint convolutions plan themselves)
-    x0 = torch.randn(2, 4, 20000, generator=g).cuda().requires_grad_()
-    w0 = torch.randn(6, 4, 33, generator=g).cuda().requires_grad_()
+    x0 = torch.randn(2, 20, 20000, generator=g).cuda().requires_grad_()
+    w0 = torch.randn(6, 20, 33, generator=g).cuda().requires_grad_()
     b0 = torch.randn(6, generator=g).cuda().requires_grad_()
     x1, w1, b1 = (t.detach().clone().requires_grad_() for t in (x0, w0, b0))
     gy = torch.randn(2, 6, 19968, generator=g).cuda()
