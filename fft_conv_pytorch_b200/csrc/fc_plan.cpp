@@ -484,18 +484,24 @@ bool choose_batch_segments(const fc_problem& P, bseg_choice* c) {
   if (Lp < Kd) return false;
   const int64_t Lout = (Lp - Kd) / st + 1;
   const int64_t N0 = next_pow2(std::max<int64_t>(Lp, 2));
-  // Cost in bytes moved, from the geometry and the channel counts only (never the batch: the batch chunks of the host
-  // pipeline must agree with the full-batch plan whose kernel spectrum they share): the transform passes move ~24 bytes
+  // Cost in bytes moved, from the geometry and the channel counts only (the window length never depends on the batch, so
+  // plans of different batch sizes that are both segmented share one kernel spectrum): the transform passes move ~24 bytes
   // per point and channel for a nominal batch of 16, the contraction reads the kernel spectrum once.
   const double Ig = (double)(P.cin / P.groups);
   auto cost = [&](double Ns, double S) { return S * Ns * (P.cin + P.cout) * 24.0 * 16.0 + (double)P.cout * Ig * (Ns / 2) * 8.0; };
-  // a segmented plan has to be clearly cheaper (FC_FLAG_SEGMENT: take the cheapest window length whatever the gain; A/B timing)
-  double best = (P.flags & FC_FLAG_SEGMENT) ? 1e300 : 0.75 * cost((double)N0, 1.0);
-  bool found = false;
   // Channel groups the fused axis kernel serves (<= 16 per group) keep the four-step layout and its specialised kernels:
   // windows of at least 64 x 256 points. (Measured, profiles/r2b_batch_segments_probe.txt: 8 channels, 33000 points, K = 64
   // runs 0.042 ms on one 65536-point transform against 0.055 ms on 17 windows of 2048 points through the generic passes.)
   const bool fusable = P.cin / P.groups <= 16 && P.cout / P.groups <= 16;
+  // How much cheaper a segmented plan has to be. Wide channel groups (generic passes around the contraction): clearly, 25 %.
+  // Fusable groups: any gain — and small problems (<= 2^22 point-channels) even at 1.6 x the bytes, because 16384-point
+  // windows run the 64 x 256 kernels on S times as many CTAs and a small call is latency-bound (profiles/r2b_tiny_probe.txt:
+  // BASELINE c1 34.8 -> 24.6 us on 3 windows; (1,4,131072) K = 513: 65.5 -> 28.7 us on 9). This one rule looks at the batch:
+  // callers that need a batch-independent choice (the host pipeline's batch chunks) pin it with FC_FLAG_SEGMENT /
+  // FC_FLAG_NO_SEGMENT. FC_FLAG_SEGMENT: take the cheapest window length whatever the gain.
+  const bool small = fusable && (double)P.batch * (P.cin + P.cout) * (double)N0 <= (double)(1 << 22);
+  double best = (P.flags & FC_FLAG_SEGMENT) ? 1e300 : (small ? 1.6 : fusable ? 1.0 : 0.75) * cost((double)N0, 1.0);
+  bool found = false;
   for (int64_t Ns = fusable ? 16384 : 1024; Ns <= N0 / 2; Ns *= 2) {
     if (Ns < 2 * Kd) continue;  // at least half of a window is output
     const int64_t Vo = (Ns - Kd) / st + 1, S = (Lout + Vo - 1) / Vo;

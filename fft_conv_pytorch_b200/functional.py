@@ -337,6 +337,8 @@ def _run(transposed: bool, signal: Tensor, kernel: Tensor, bias: Optional[Tensor
             # a chunk runs on the kernel spectrum of the full-batch plan, so its plan must choose the same spectrum layout:
             # the tensor-core layout depends on the batch (<= 32), so a full batch on the SIMT path keeps its chunks there
             cflags = flags | (0 if int(plan.info.tensor_core) else L.FC_FLAG_NO_TC)
+            if signal.dim() == 3 and not transposed:  # 1-d batch segments: the (batch-dependent) choice of the full-batch plan
+                cflags |= L.FC_FLAG_SEGMENT if int(plan.info.segments) > 1 else L.FC_FLAG_NO_SEGMENT
             sub = entry if a1 - a0 == B else get_plan(transposed, a1 - a0, cin, cout, groups, tuple(int(v) for v in signal.shape[2:]),
                                                       tuple(int(v) for v in kernel.shape[2:]), stride_, padding_, dilation_, opad_, padding_mode, cflags)
             sp = sub.plan

@@ -93,8 +93,10 @@ def test_plan_shapes_follow_reference_formulas():
     assert p.fft_size == (256, 256) and p.info.segments == 25
     p = emul.plan_for((4, 64, 1024, 1024), (64, 16, 31, 31), transposed=True, stride=2, dilation=2, groups=4, flags=L.FC_FLAG_NO_SEGMENT)
     assert p.fft_size == (2048, 2048) and p.info.segments == 1
-    p = emul.plan_for((16, 256, 65536), (256, 256, 4097))
-    assert p.out_size == (61440,) and p.fft_size == (65536,)
+    p = emul.plan_for((16, 256, 65536), (256, 256, 4097))  # 5 windows of 16384 points as batch items (f3, 1-d)
+    assert p.out_size == (61440,) and p.fft_size == (16384,) and p.info.segments == 5
+    p = emul.plan_for((16, 256, 65536), (256, 256, 4097), flags=L.FC_FLAG_NO_SEGMENT)
+    assert p.out_size == (61440,) and p.fft_size == (65536,) and p.info.segments == 1
     p = emul.plan_for((1, 8, 32768), (8, 8, 1025))
     assert p.out_size == (31744,)
     # SURVEY §8d algorithmic bytes at the reference extents for c1/c2
@@ -459,8 +461,15 @@ def test_batch_segment_choice():
     for B in (1, 3, 40):
         p = emul.plan_for((B, 256, 65536), (256, 256, 4097))
         assert (int(p.info.segments), p.fft_size, int(p.info.kspec_bytes)) == (5, (16384,), int(c4.info.kspec_bytes))
+    # channel groups the fused axis kernel serves: windows of 16384 points only; a small call (BASELINE c1) takes them even at
+    # 1.5 x the points (more CTAs on a latency-bound problem), a large batch of the same lines only when they move fewer bytes
     c1 = emul.plan_for((1, 8, 32768), (8, 8, 1025))
-    assert int(c1.info.segments) == 1 and c1.fft_size == (32768,)
+    assert int(c1.info.segments) == 3 and c1.fft_size == (16384,) and c1.out_size == (31744,)
+    big = emul.plan_for((64, 8, 32768), (8, 8, 1025))
+    assert int(big.info.segments) == 1 and big.fft_size == (32768,)
+    for flags, segs in ((L.FC_FLAG_NO_SEGMENT, 1), (L.FC_FLAG_SEGMENT, 3)):  # what the host pipeline pins for its batch chunks
+        for B in (1, 64):
+            assert int(emul.plan_for((B, 8, 32768), (8, 8, 1025), flags=flags).info.segments) == segs
     just_above = emul.plan_for((4, 32, 33000), (32, 32, 64))
     assert int(just_above.info.segments) > 1 and just_above.fft_size[0] <= 8192
     small = emul.plan_for((4, 8, 33000), (8, 8, 64))  # 8 channels: only windows that keep the fused-kernel program

@@ -828,6 +828,15 @@ def test_batch_segments_through_every_call_path():
         assert not y.is_cuda and rel_err(y.numpy(), ref.numpy()) < TOL
     e = Fn.get_plan(False, 7, 40, 4, 2, (34000,), (40,), (1,), (20,), (1,), (0,), "constant")
     assert int(e.plan.info.segments) > 1
+    # 8 channels: the small-call rule depends on the batch, so the host pipeline pins the full-batch choice for its chunks
+    for B, segs in ((6, 3), (16, 1)):
+        x = torch.randn(B, 8, 32768, generator=g)
+        w = torch.randn(8, 8, 1025, generator=g)
+        with torch.no_grad():
+            y = fcp.fft_conv(x, w, None)
+            ref = F.conv1d(x.cuda(), w.cuda())  # (cuDNN fp32, TF32 off)
+        assert int(Fn.get_plan(False, B, 8, 8, 1, (32768,), (1025,), (1,), (0,), (1,), (0,), "constant").plan.info.segments) == segs
+        assert rel_err(y.numpy(), ref.cpu().numpy()) < TOL
     # (batch, window) items beyond one tensor-core GEMM chunk of 80
     x = torch.randn(12, 64, 50000, generator=g).cuda()
     w = torch.randn(128, 64, 1500, generator=g).cuda()
