@@ -26,6 +26,7 @@ FC_FLAG_NO_ROW_FILL = 2048
 FC_FLAG_NO_STREAM = 4096
 FC_FLAG_STREAM_R2C = 8192
 FC_FLAG_SEGMENT = 16384
+FC_FLAG_NO_SHORT_SPLIT = 32768
 
 _I3 = ctypes.c_int32 * FC_MAX_ND
 

@@ -502,7 +502,7 @@ bool choose_batch_segments(const fc_problem& P, bseg_choice* c) {
   const bool small = fusable && (double)P.batch * (P.cin + P.cout) * (double)N0 <= (double)(1 << 22);
   double best = (P.flags & FC_FLAG_SEGMENT) ? 1e300 : (small ? 1.6 : fusable ? 1.0 : 0.75) * cost((double)N0, 1.0);
   bool found = false;
-  for (int64_t Ns = fusable ? 16384 : 1024; Ns <= N0 / 2; Ns *= 2) {
+  for (int64_t Ns = fusable ? 16384 : 2048; Ns <= N0 / 2; Ns *= 2) {  // (from 2048 points a window runs on the four-step kernels)
     if (Ns < 2 * Kd) continue;  // at least half of a window is output
     const int64_t Vo = (Ns - Kd) / st + 1, S = (Lout + Vo - 1) / Vo;
     if (S < 2 || (int64_t)P.batch * S > (1 << 20)) continue;
@@ -750,7 +750,13 @@ int plan_build_core(fc_plan* pl, const fc_problem* prob, std::string* msg) {
   // ---- structure
   pl->N1 = pl->N2 = 0;
   if (nd == 1) {
-    if (pl->ax[0].N <= kMaxRealLine) {
+    // Lines of 2048 ... 8192 points take the four-step layout too (64 x 32 ... 128): its column and warp-engine passes run at
+    // 4 - 5 TB/s where the generic block-level pass reaches ~1 TB/s on such lines, and the five specialised launches beat the
+    // three generic ones even on small calls (profiles/r2b_short_split_probe.txt: faster in all twelve probed shapes, 16 - 47 %).
+    const int64_t N0 = pl->ax[0].N;
+    const bool short_split = !(P.flags & (FC_FLAG_NO_SHORT_SPLIT | FC_FLAG_NO_FUSED | FC_FLAG_NO_FAST_C2C | FC_FLAG_NO_FAST_R2C | FC_FLAG_NO_FAST_C2R)) &&
+                             N0 >= 2048;
+    if (N0 <= kMaxRealLine && !short_split) {
       pl->structure = FC_S_1D;
     } else {
       pl->structure = FC_S_1D_SPLIT;
@@ -758,7 +764,7 @@ int plan_build_core(fc_plan* pl, const fc_problem* prob, std::string* msg) {
       // per column entirely in registers (fc_column.cuh) and the contiguous pass on the warp engine (N2 = 256..2048).
       // Longer lines fall back to a balanced split on the generic kernels.
       const int N = pl->ax[0].N, l2 = ilog2(N);
-      pl->N1 = (N / 64 >= 256 && N / 64 <= 2048) ? 64 : 1 << ((l2 + 1) / 2);
+      pl->N1 = (N / 64 >= (short_split ? 32 : 256) && N / 64 <= 2048) ? 64 : 1 << ((l2 + 1) / 2);
       pl->N2 = N / pl->N1;
       pl->ax[0].Nk = 0;  // bins are (N1/2+1) x N2 for the split layout
     }

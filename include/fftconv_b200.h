@@ -86,6 +86,7 @@ enum {
   FC_FLAG_NO_ROW_FILL = 2048, /* transposed row lattices: leave the bias-only rows to the last kernel (A/B timing) */
   FC_FLAG_NO_STREAM = 4096,  /* keep K4 on the register-path kernel (no tensor-map streaming, fc_stream.cuh; tests, A/B timing) */
   FC_FLAG_SEGMENT = 16384,   /* 1-d fft_conv: run as batch segments (windows of the line) whenever a window length applies, even if the cost model sees no gain; with FC_FLAG_NO_SEGMENT the two pin the (batch-dependent) choice for plans that share a kernel spectrum */
+  FC_FLAG_NO_SHORT_SPLIT = 32768, /* 1-d lines of 2048 ... 8192 points: keep the one-pass layout on the generic kernels (default: four-step 64 x N2 on the column / warp-engine kernels) */
   FC_FLAG_STREAM_R2C = 8192  /* run K1 on the bulk-copy / tensor-map-store kernel too (measured equal to the register path at BASELINE c2) */
 };
 

@@ -474,3 +474,38 @@ def test_batch_segment_choice():
     assert int(just_above.info.segments) > 1 and just_above.fft_size[0] <= 8192
     small = emul.plan_for((4, 8, 33000), (8, 8, 64))  # 8 channels: only windows that keep the fused-kernel program
     assert int(small.info.segments) == 1 or small.fft_size[0] >= 16384
+
+
+# ---- 1-d lines of 2048 ... 8192 points on the four-step layout (64 x 32 ... 128: column + warp-engine kernels)
+_SHORT_SPLIT_CASES = [
+    ((2, 64, 4000), (64, 64, 33), dict(padding=16)),
+    ((1, 40, 8000), (24, 20, 100), dict(groups=2, stride=2)),
+    ((3, 7, 2048), (6, 7, 7), {}),
+    ((1, 12, 2000), (8, 12, 9), dict(padding=4, dilation=3)),
+    ((2, 4, 3000), (4, 4, 40), dict(padding=20, padding_mode="reflect")),
+]
+
+
+@pytest.mark.parametrize("xs,ws,kw", _SHORT_SPLIT_CASES)
+def test_short_lines_on_the_four_step_layout(xs, ws, kw):
+    import torch
+    import torch.nn.functional as F
+
+    rng = np.random.RandomState(2)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = rng.standard_normal(ws).astype(np.float32)
+    b = rng.standard_normal(ws[0]).astype(np.float32)
+    y, plan = emul.conv(x, w, b, **kw)
+    d = plan.describe()
+    assert "structure=2" in d and "col_r2c_N64" in d and "col_c2r_N64" in d, d
+    y1, plan1 = emul.conv(x, w, b, flags=L.FC_FLAG_NO_SHORT_SPLIT, **kw)
+    assert "structure=1" in plan1.describe()
+    kw2 = dict(kw)
+    mode = kw2.pop("padding_mode", "constant")
+    xt = torch.from_numpy(x).double()
+    if mode != "constant":
+        p = kw2.pop("padding")
+        xt = F.pad(xt, (p, p), mode=mode)
+    ref = F.conv1d(xt, torch.from_numpy(w).double(), torch.from_numpy(b).double(), **kw2).numpy()
+    assert y.shape == ref.shape and not np.isnan(y).any()
+    assert rel_err(y, ref) < 1e-5 and rel_err(y, y1) < 1e-5

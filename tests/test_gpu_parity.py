@@ -866,3 +866,38 @@ def test_batch_segments_through_every_call_path():
     (F.conv1d(x1, w1, bias=b1) * gy).sum().backward()
     for a, r in ((w0.grad, w1.grad), (b0.grad, b1.grad), (x0.grad, x1.grad)):
         assert rel_err(a.detach().cpu().numpy(), r.detach().cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("xs,ws,kw", [((32, 32, 8192), (64, 32, 129), {}), ((8, 8, 4000), (8, 8, 65), dict(padding=32)),
+                                      ((5, 16, 2048), (16, 8, 33), dict(groups=2, stride=2)), ((3, 128, 4096), (128, 128, 100), {}),
+                                      ((2, 6, 3000), (4, 6, 40), dict(padding=20, padding_mode="circular"))])
+def test_short_1d_lines_on_the_four_step_layout(xs, ws, kw):
+    """1-d lines of 2048 ... 8192 points: column + warp-engine kernels (default) against the generic one-pass kernels."""
+    from fft_conv_pytorch_b200 import _lib as L
+
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(*xs, generator=g).cuda()
+    w = torch.randn(*ws, generator=g).cuda()
+    b = torch.randn(ws[0], generator=g).cuda()
+    out = {}
+    try:
+        for name, flags in (("split", 0), ("one", L.FC_FLAG_NO_SHORT_SPLIT)):
+            Fn.set_default_flags(flags)
+            Fn.clear_caches()
+            with torch.no_grad():
+                out[name] = fcp.fft_conv(x, w, b, **kw).clone()
+            d = Fn._plans[next(reversed(Fn._plans))].plan.describe()
+            assert ("structure=2" in d) == (name == "split"), d
+    finally:
+        Fn.set_default_flags(0)
+        Fn.clear_caches()
+    kw2 = dict(kw)
+    mode = kw2.pop("padding_mode", "constant")
+    xt = x.double()
+    if mode != "constant":
+        p = kw2.pop("padding")
+        xt = F.pad(xt, (p, p), mode=mode)
+    with torch.no_grad():
+        ref = F.conv1d(xt, w.double(), b.double(), **kw2)
+    assert (out["split"].double() - ref).abs().max().item() / ref.abs().max().item() < TOL
+    assert (out["split"] - out["one"]).abs().max().item() / ref.abs().max().item() < 2e-5
