@@ -104,7 +104,7 @@ thread_local int g_num_sms = 148;  // SM count of the calling thread's current d
 #define FC_FAST_C2C_ALL(X) X(32, 2, 8, 4) X(64, 2, 8, 4) X(128, 2, 8, 4) X(256, 2, 8, 3) X(512, 2, 8, 2) X(1024, 1, 8, 2) X(2048, 1, 8, 1)
 
 // ... and of the two-axis plane kernels: X(NY, NZ).
-#define FC_PLANE_ALL(X) X(32, 32) X(32, 64) X(64, 32) X(64, 64)
+#define FC_PLANE_ALL(X) X(32, 32) X(32, 64) X(64, 32) X(64, 64) X(32, 128) X(64, 128) X(128, 32) X(128, 64) X(128, 128)
 
 // ... of the pair pipeline (fc_pair.cuh). K1p / K4p: X(M, pair lines per warp group, warps, CTAs per SM);
 // KBp: X(N, channels per group, pair items per CTA, warps, plain, CTAs per SM).
@@ -928,7 +928,7 @@ int launch_pair_fused64(const fc_plan* pl, const fc_fused_desc& f, const void* i
 int tc_padded_batch(int batch) { return batch <= 8 ? 8 : (batch + 7) / 8 * 8; }
 bool tc_supported(int batch, int cin, int cout, int groups) {
   const int I = cin / groups, O = cout / groups;
-  return I >= 32 && (2 * I) % 32 == 0 && O % 128 == 0 && tc_padded_batch(batch) <= FC_TC_MAX_BATCH;
+  return I >= 32 && (2 * I) % 32 == 0 && O % 64 == 0 && tc_padded_batch(batch) <= FC_TC_MAX_BATCH;
 }
 
 int launch_tc_relayout(int mode, const void* in, void* out, int64_t bins, int batch, int cin, int cout, int groups, cudaStream_t st) {
@@ -969,6 +969,7 @@ int launch_tc_gemm(const float* A, const float* Bt, float* D, int64_t bins, int 
   // 3 * (2*MT*16 KB + 2*N*128 B) <= 223 KB and 2*MT*N <= 512 TMEM columns -> N <= 32 for MT = 2, N <= 160 for MT = 1
   // ... and with N >= 96 two tiles per pass on two stages and one accumulator set (fc_tc.cuh, variants)
   static const int wide2 = fc_tune_int("TC_WIDE2", 1);
+  a.tile_rows = a.O % 128 == 0 ? 128 : 64;
   const bool two = a.O % 256 == 0 && (N <= 32 || (N >= 96 && wide2));
   const int MT = two ? 2 : 1, stages = (two && N > 32) ? 2 : 3;
   if (N > 2 * FC_TC_MAX_BATCH) return set_err(FC_EUNSUPPORTED, "tensor-core contraction: batch chunk too wide");

@@ -868,7 +868,11 @@ int plan_build_core(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     // multiple of 8
     const int bc = fc_tc_chunk(P.batch);
     const int bp = bc <= 8 ? 8 : (bc + 7) / 8 * 8;
-    pl->use_tc = !(P.flags & (FC_FLAG_NO_TC | FC_FLAG_NO_FUSED)) && Ig >= 32 && (2 * Ig) % 32 == 0 && Og % 128 == 0;
+    // (output groups that are multiples of 64 only run on 64-row A tiles at ~2.2 TB/s against 3.5 - 3.9 TB/s on full tiles: that
+    // beats the SIMT contraction (0.8 - 1.3 TB/s at 64 channels) once there are enough bins to fill the pipeline,
+    // profiles/r2b_tc_64row_tiles.txt)
+    pl->use_tc = !(P.flags & (FC_FLAG_NO_TC | FC_FLAG_NO_FUSED)) && Ig >= 32 && (2 * Ig) % 32 == 0 &&
+                 (Og % 128 == 0 || (Og % 64 == 0 && bins >= 2048));
 #ifdef FC_CPU_EMUL
     pl->use_tc = 0;  // tcgen05 cannot run in the host emulation
 #endif
@@ -980,7 +984,7 @@ bool column_pass_ok(const fc_pass& p) {
   return p.kind == FC_C2R && p.in_rs == 1 && p.out_rs == 0 && p.out_es == 1;
 }
 
-bool plane_len(int n) { return n == 32 || n == 64; }
+bool plane_len(int n) { return n == 32 || n == 64 || n == 128; }
 bool plain_gather(const fc_imap& m) { return m.mode == FC_PAD_CONSTANT && m.up == 1 && m.sub == 1; }
 bool plain_crop(const fc_omap& m) { return m.og == 1 && m.os == 1 && m.ob >= 0; }
 

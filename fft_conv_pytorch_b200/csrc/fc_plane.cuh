@@ -1,10 +1,10 @@
 // fc_plane.cuh — two axis passes of a 3-d transform in one kernel: a CTA holds the (z, y) plane of one (item, kx) in
-// shared memory (at most 64 x 64 points = 32 KB), transforms its rows and then its columns with the group FFT engine
+// shared memory (at most 128 x 128 points = 129 KB), transforms its rows and then its columns with the group FFT engine
 // (fc_fused.cuh: 8 points per lane, 32/G lines per warp) and writes the result in the layout the next step expects.
 // The spectrum between the two passes never reaches HBM, and neither side needs a transposing tile:
 //   fc_plane_fwd_kernel  [kx][z][y] (rows contiguous) -> y transform -> z transform -> [ky][kx][kz] (512-byte runs)
 //   fc_plane_inv_kernel  [ky][kx][kz] -> z inverse -> y inverse -> crop -> [kx][jz][jy] (rows contiguous)
-// They replace the C2C passes sig[1]+sig[2] / inv[0]+inv[1] of the 3-d program when both extents are 32 or 64 and the
+// They replace the C2C passes sig[1]+sig[2] / inv[0]+inv[1] of the 3-d program when both extents are 32, 64 or 128 and the
 // maps are plain (constant padding, no zero-stuffing / subsampling; unit-stride crop).
 #pragma once
 #include "fc_fused.cuh"

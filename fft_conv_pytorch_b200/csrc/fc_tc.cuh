@@ -23,7 +23,8 @@
 // ("blobs"): a chunk is 32 consecutive fp32 of the K dimension (one 128-byte row per matrix row), rows in groups of 8
 // (1024 bytes), the eight 16-byte pieces of a row XOR-swizzled with the row index (UMMA SWIZZLE_128B, K-major). A
 // blob is contiguous, so one bulk async copy (cp.async.bulk) moves it into its pipeline stage at full DRAM efficiency.
-//   A blobs : [bin][group][tile][chunk] x (128 rows x 32 fp32)             kernel spectrum, rows = output channels (128 per tile)
+//   A blobs : [bin][group][tile][chunk] x (128 rows x 32 fp32)             kernel spectrum, rows = output channels (128 per tile;
+//             64 per tile when Cout/g is a multiple of 64 only: the GEMM then zero-fills the upper half of its 128-row operand)
 //   Bt blobs: [bin][group][chunk] x (N rows x 32 fp32)                     signal spectrum, rows = (batch, re/im); the
 //             raw values (the tensor core ignores the low 13 mantissa bits = the "hi" operand); like A's, the "lo" operand
 //             (value - truncated value) is derived in shared memory by the GEMM kernel, so it never crosses HBM
@@ -70,7 +71,7 @@ __global__ void fc_tc_relayout_kernel(fc_tc_relayout_args a) {
       if (a.mode == 0) {
         const int o = r / a.I, i = r - o * a.I;  // o over all groups
         const int g = o / a.Og, og = o - g * a.Og;
-        const int G = a.O / a.Og, prow = 128, passes = a.Og / prow;  // one blob per 128-row tile, whatever the GEMM's tiles per pass
+        const int G = a.O / a.Og, prow = a.Og % 128 == 0 ? 128 : 64, passes = a.Og / prow;  // one blob per tile of 128 (or 64) output rows
         const int pass = og / prow, row = og - pass * prow;
         const int64_t blob = (((f * G + g) * passes + pass) * n_chunks);
         // K column i holds re, column I + i holds im
@@ -343,7 +344,8 @@ struct fc_tc_args {
   const float* Bt;  // Bt blobs [item][chunk][N x 32]
   float* D;         // [item][O][N]   product (complex Y[f][g][o][b])
   int64_t n_items;  // bins * G
-  int32_t O, I, B;  // per group; O % 128 == 0, (2I) % 32 == 0, B = padded batch (multiple of 8): N = 2B <= 160 (MT = 1) or <= 32 (MT = 2)
+  int32_t O, I, B;  // per group; O % 64 == 0, (2I) % 32 == 0, B = padded batch (multiple of 8): N = 2B <= 160 (MT = 1) or <= 32 (MT = 2)
+  int32_t tile_rows;  // output rows per A tile: 128, or 64 (O % 128 != 0; MT = 1): the MMA still runs M = 128 on a zero upper half
 };
 
 // One CTA per SM, persistent over (bin, group) items; warp-specialised:
@@ -399,7 +401,18 @@ __global__ void __launch_bounds__(FC_TC_THREADS, 1) fc_tc_gemm_kernel(fc_tc_args
   const uint32_t tmem_base = tmem_slot;
   const uint32_t idesc = idesc_tf32(128, N);
 
-  const int passes = a.O / (MT * 128);
+  const int TR = a.tile_rows;  // 128, or 64 with MT == 1
+  const uint32_t a_load = (uint32_t)TR * 128u;  // bytes of one A tile in HBM
+  if (TR < 128) {  // rows TR..127 of every stage's A operand (raw and low part) stay zero: they are never written again
+    for (int s = 0; s < FC_TC_STAGES; ++s)
+      for (int e = tid; e < (128 - TR) * 8 * 2; e += FC_TC_THREADS) {
+        unsigned char* half = sbase + (size_t)s * stage_bytes + (e >= (128 - TR) * 8 ? A_BYTES : 0) + (size_t)TR * 128;
+        *reinterpret_cast<float4*>(half + ((e % ((128 - TR) * 8)) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    fence_proxy_async();
+    __syncthreads();
+  }
+  const int passes = a.O / (MT * TR);
   const int64_t my_items = (a.n_items > (int64_t)blockIdx.x) ? (a.n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int64_t n_acc = my_items * passes;       // accumulator uses (item, pass) of this CTA
   const int64_t total = n_acc * n_chunks;        // flat chunk sequence q = acc_use * n_chunks + c
@@ -416,10 +429,10 @@ __global__ void __launch_bounds__(FC_TC_THREADS, 1) fc_tc_gemm_kernel(fc_tc_args
         const int pass = (int)(ip % passes);
         const int64_t item = blockIdx.x + (ip / passes) * gridDim.x;
         unsigned char* st = sbase + (size_t)s * stage_bytes;
-        mbar_expect_tx(&bar_full[s], (uint32_t)(A_BYTES + B_BYTES));
+        mbar_expect_tx(&bar_full[s], (uint32_t)(MT * a_load + B_BYTES));
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)  // the 128-row tiles of this pass are n_chunks blobs apart
-          bulk_g2s(st + mt * 16384, a.A + ((((item * passes + pass) * MT + mt) * n_chunks + c) * (int64_t)4096), 16384, &bar_full[s]);
+        for (int mt = 0; mt < MT; ++mt)  // the tiles of this pass are n_chunks blobs apart
+          bulk_g2s(st + mt * 16384, a.A + ((((item * passes + pass) * MT + mt) * n_chunks + c) * (int64_t)(a_load / 4)), a_load, &bar_full[s]);
         bulk_g2s(st + 2 * A_BYTES, a.Bt + ((item * n_chunks + c) * (int64_t)(B_BYTES / 4)), B_BYTES, &bar_full[s]);
       }
     }
@@ -466,6 +479,7 @@ __global__ void __launch_bounds__(FC_TC_THREADS, 1) fc_tc_gemm_kernel(fc_tc_args
       // low part keeps the same positions)
 #pragma unroll
       for (int j = 0; j < MT * 4; ++j) {
+        if (TR < 128 && j >= TR / 32) break;  // (the zero upper half keeps its zero low part)
         const int row = (tid >> 3) + 32 * j;
         const uint32_t off = (uint32_t)row * 128 + (uint32_t)(piece << 4);
         const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
@@ -490,9 +504,9 @@ __global__ void __launch_bounds__(FC_TC_THREADS, 1) fc_tc_gemm_kernel(fc_tc_args
         mbar_wait(&bar_acc_full[buf], (uint32_t)((ip / NBUF) & 1));
         tc_fence_after();
         const int mt = warp >> 2;  // warps 0-3: tile 0, warps 4-7: tile 1
-        if (mt < MT) {
-          const int row = (warp & 3) * 32 + lane;  // TMEM lane = accumulator row
-          float* drow = a.D + (item * (int64_t)a.O + (int64_t)pass * MT * 128 + mt * 128 + row) * N;
+        const int row = (warp & 3) * 32 + lane;  // TMEM lane = accumulator row
+        if (mt < MT && row < TR) {
+          float* drow = a.D + (item * (int64_t)a.O + (int64_t)pass * MT * TR + mt * TR + row) * N;
           for (int c0 = 0; c0 < N; c0 += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)(mt * N + c0), v);

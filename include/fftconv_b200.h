@@ -161,7 +161,7 @@ int fc_complex_matmul(const float* d_a, const float* d_b, float* d_y, int64_t ba
 
 /* Tensor-core variant of the contraction for wide channel counts (tcgen05 kind::tf32 with a 3xTF32 split):
  * fc_tc_supported says whether the shape qualifies (Cin/groups >= 32 and a multiple of 16, Cout/groups a multiple of
- * 128, batch <= 32). The kernel spectrum is converted once by fc_tc_prepare_kernel into the bin-outermost planar
+ * 64, batch <= 80; fc_conv runs larger batches in chunks). The kernel spectrum is converted once by fc_tc_prepare_kernel into the bin-outermost planar
  * layout (same byte size as the input); d_scratch needs fc_tc_scratch_bytes. */
 int fc_tc_supported(int64_t batch, int64_t cin, int64_t cout, int64_t groups);
 int64_t fc_tc_scratch_bytes(int64_t batch, int64_t cin, int64_t cout, int64_t groups, int64_t bins);

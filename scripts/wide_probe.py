@@ -14,14 +14,19 @@ from fft_conv_pytorch_b200 import functional as Fn
 
 dev = torch.device("cuda", 0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-CASES = [((16, 64, 65536), (64, 64, 4097)), ((16, 64, 65536), (128, 64, 4097)), ((16, 128, 65536), (64, 128, 4097)), ((16, 96, 65536), (96, 96, 4097)),
-         ((8, 64, 16384), (64, 64, 257)), ((32, 32, 8192), (64, 32, 129))]
+CASES = [((64, 16, 1024), (16, 16, 33)), ((256, 64, 512), (64, 64, 9)), ((32, 3, 224, 224), (64, 3, 7, 7)), ((32, 64, 56, 56), (64, 64, 3, 3)),
+         ((16, 64, 128, 128), (64, 64, 5, 5)), ((8, 32, 256, 256), (32, 32, 9, 9)), ((4, 16, 512, 512), (16, 16, 31, 31)), ((16, 8, 100, 100), (8, 8, 11, 11)),
+         ((8, 4, 32, 32, 32), (8, 4, 5, 5, 5)), ((2, 16, 64, 64, 64), (16, 16, 7, 7, 7)), ((4, 1, 128, 128, 128), (4, 1, 9, 9, 9)), ((8, 128, 64, 64), (128, 128, 7, 7)),
+         ((2, 8, 1024, 1024), (8, 8, 33, 33)), ((1, 3, 2048, 2048), (3, 3, 65, 65))]
+if len(sys.argv) > 1:
+    CASES = eval(sys.argv[1])
 P = lambda t_: ctypes.c_void_p(t_.data_ptr())
 for xs, ws in CASES:
     x = torch.randn(*xs, device=dev)
     w = torch.randn(*ws, device=dev)
     b = torch.randn(ws[0], device=dev)
-    entry = Fn.get_plan(False, xs[0], xs[1], ws[0], 1, tuple(xs[2:]), tuple(ws[2:]), (1,), (0,), (1,), (0,), "constant")
+    nd = len(xs) - 2
+    entry = Fn.get_plan(False, xs[0], xs[1], ws[0], 1, tuple(xs[2:]), tuple(ws[2:]), (1,) * nd, (0,) * nd, (1,) * nd, (0,) * nd, "constant")
     plan = entry.plan
     lib = plan.lib
     kspec = Fn.kernel_spectrum(entry, w, dev)
@@ -46,7 +51,8 @@ for xs, ws in CASES:
         lib.fc_plan_launch_info(plan.handle, j, nm, 64, ctypes.byref(ab))
         names.append((nm.value.decode(), ab.value))
     tot = sum(statistics.median(a) for a in acc)
-    print(xs, ws, f"fft {plan.fft_size[0]} x {int(plan.info.segments)} total {tot:.0f} us:",
+    abytes = sum(ab for _, ab in names)
+    print(xs, ws, f"fft {plan.fft_size} x {int(plan.info.segments)} total {tot:.0f} us = {abytes / tot / 1e3:.0f} GB/s:",
           " ".join(f"{n}={statistics.median(a):.0f}us({ab / statistics.median(a) / 1e3:.0f}GB/s)" for (n, ab), a in zip(names, acc)), flush=True)
     del x, w, y, wsb, kspec
     Fn.clear_caches()

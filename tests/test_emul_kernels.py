@@ -509,3 +509,22 @@ def test_short_lines_on_the_four_step_layout(xs, ws, kw):
     ref = F.conv1d(xt, torch.from_numpy(w).double(), torch.from_numpy(b).double(), **kw2).numpy()
     assert y.shape == ref.shape and not np.isnan(y).any()
     assert rel_err(y, ref) < 1e-5 and rel_err(y, y1) < 1e-5
+
+
+@pytest.mark.parametrize("xs,ws,kw", [((1, 2, 70, 100, 40), (2, 2, 3, 5, 3), {}), ((1, 1, 100, 40, 66), (2, 1, 5, 3, 3), dict(padding=(2, 1, 1))),
+                                      ((1, 2, 128, 128, 30), (1, 2, 2, 2, 2), {})])
+def test_plane_kernels_with_128_point_axes(xs, ws, kw):
+    """3-d programs whose middle axes are 128 points long run on the plane kernels (a 128 x 128 plane is 129 KB of shared memory)."""
+    import torch
+    import torch.nn.functional as F
+
+    rng = np.random.RandomState(3)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = rng.standard_normal(ws).astype(np.float32)
+    b = rng.standard_normal(ws[0]).astype(np.float32)
+    y, plan = emul.conv(x, w, b, **kw)
+    d = plan.describe()
+    assert "plane_fwd_" in d and "plane_inv_" in d and "128" in d, d
+    ref = F.conv3d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), **kw).numpy()
+    assert y.shape == ref.shape and not np.isnan(y).any()
+    assert rel_err(y, ref) < 1e-5

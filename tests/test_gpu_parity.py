@@ -901,3 +901,19 @@ def test_short_1d_lines_on_the_four_step_layout(xs, ws, kw):
         ref = F.conv1d(xt, w.double(), b.double(), **kw2)
     assert (out["split"].double() - ref).abs().max().item() / ref.abs().max().item() < TOL
     assert (out["split"] - out["one"]).abs().max().item() / ref.abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("xs,ws,kw,tr", [((2, 2, 100, 100, 70), (3, 2, 5, 3, 9), {}, False), ((1, 4, 128, 128, 128), (4, 4, 9, 9, 9), {}, False),
+                                         ((1, 3, 40, 100, 90), (2, 3, 3, 3, 5), dict(padding=(1, 2, 2)), False),
+                                         ((1, 2, 60, 60, 30), (2, 2, 3, 3, 3), dict(stride=2, padding=1, output_padding=1), True)])
+def test_3d_programs_with_128_point_plane_axes(xs, ws, kw, tr):
+    g = torch.Generator().manual_seed(43)
+    x = torch.randn(*xs, generator=g).cuda()
+    w = torch.randn(*ws, generator=g).cuda()
+    b = torch.randn(ws[1] if tr else ws[0], generator=g).cuda()
+    with torch.no_grad():
+        y = (fcp.fft_conv_transpose if tr else fcp.fft_conv)(x, w, b, **kw)
+        ref = (F.conv_transpose3d if tr else F.conv3d)(x.double(), w.double(), b.double(), **kw)
+    d = Fn._plans[next(reversed(Fn._plans))].plan.describe()
+    assert ("plane_inv_128" in d if tr else "plane_fwd_" in d and "128" in d), d  # (a zero-stuffing gather keeps the forward passes apart)
+    assert (y.double() - ref).abs().max().item() / ref.abs().max().item() < TOL

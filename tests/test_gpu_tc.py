@@ -32,7 +32,9 @@ def _tc_matmul(a, b, groups):
 
 @pytest.mark.parametrize("B,cin,cout,groups,bins", [(16, 256, 256, 1, 300), (4, 64, 128, 1, 77), (16, 128, 256, 2, 130), (9, 96, 128, 1, 65),
                                                      # wide batch chunks: one 128-row tile per pass, up to 160 accumulator columns
-                                                     (80, 64, 128, 1, 40), (40, 256, 256, 1, 33), (33, 96, 256, 2, 17), (24, 128, 256, 1, 50)])
+                                                     (80, 64, 128, 1, 40), (40, 256, 256, 1, 33), (33, 96, 256, 2, 17), (24, 128, 256, 1, 50),
+                                                     # output-channel groups that are multiples of 64 only: 64-row A tiles
+                                                     (16, 64, 64, 1, 70), (48, 128, 192, 1, 21), (5, 64, 128, 2, 33), (80, 32, 320, 1, 9)])
 def test_tc_contraction_matches_fp32(B, cin, cout, groups, bins):
     torch.manual_seed(0)
     a = torch.randn(B, cin, bins, dtype=torch.complex64, device="cuda")
