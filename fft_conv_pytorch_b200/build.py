@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfftconv_b200.so")
 SOURCES = ["fc_api.cu", "fc_plan.cpp"]
-DEPS = ["fc_api.cu", "fc_plan.cpp", "fc_plan.h", "fc_types.h", "fc_kernels.cuh", "fc_fused.cuh", "fc_pair.cuh", "fc_column.cuh", "fc_plane.cuh", "fc_tune.h", "fc_tc.cuh", "fc_stream.cuh", os.path.join("..", "..", "include", "fftconv_b200.h")]
+DEPS = ["fc_api.cu", "fc_plan.cpp", "fc_plan.h", "fc_types.h", "fc_kernels.cuh", "fc_fused.cuh", "fc_pair.cuh", "fc_column.cuh", "fc_plane.cuh", "fc_line.cuh", "fc_tune.h", "fc_tc.cuh", "fc_stream.cuh", os.path.join("..", "..", "include", "fftconv_b200.h")]
 
 
 def _nvcc() -> str:

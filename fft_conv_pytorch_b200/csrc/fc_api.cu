@@ -13,6 +13,7 @@
 #include "fc_pair.cuh"
 #include "fc_column.cuh"
 #include "fc_plane.cuh"
+#include "fc_line.cuh"
 #include "fc_tc.cuh"
 #include "fc_stream.cuh"
 #include "fc_plan.h"
@@ -189,6 +190,10 @@ void init_once() {
   cudaFuncSetAttribute(fc_tc_gemm_kernel<1, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   cudaFuncSetAttribute(fc_tc_gemm_kernel<2, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   cudaFuncSetAttribute(fc_tc_gemm_kernel<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+#ifndef FC_CPU_EMUL
+  cudaFuncSetAttribute(fc_line_r2c_kernel<512, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  cudaFuncSetAttribute(fc_line_c2r_kernel<512, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+#endif
   cudaFuncSetAttribute(fc_tc_c2c_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   cudaFuncSetAttribute(fc_tc_c2c_inv_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   cudaFuncSetAttribute(fc_tc_c2c_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -568,6 +573,30 @@ int launch_plane(bool inverse, const fc_plane_desc& d, const void* in, void* out
   if (!done) return set_err(FC_EUNSUPPORTED, "no plane kernel for these extents");
   rec_mark();
   return check_cuda("plane pass launch");
+}
+
+// The real pass of a one-pass 1-d program on the warp engine (fc_line.cuh): 8 warps x 2 lines per CTA.
+int launch_line(const fc_pass& p, const void* in, void* out, const float2* tw, const float* bias, cudaStream_t st) {
+  fc_line_args a;
+  a.p = p;
+  a.p.has_bias = bias ? 1 : 0;
+  a.in = in;
+  a.out = out;
+  a.tw = tw;
+  a.bias = bias;
+  if (p.n_outer < 1) return FC_OK;
+  const size_t smem = (size_t)8 * 2 * p.M * sizeof(float2);
+  const int occ = p.M == 256 ? 4 : 3;
+  int64_t grid = (p.n_outer + 15) / 16;
+  if (grid > (int64_t)g_num_sms * occ) grid = (int64_t)g_num_sms * occ;
+  dim3 g((unsigned)grid), b(256);
+  if (p.kind == FC_R2C && p.M == 256) { auto k = fc_line_r2c_kernel<256, 8, 4>; FC_LAUNCH(k, g, b, smem, st, a); }
+  else if (p.kind == FC_R2C && p.M == 512) { auto k = fc_line_r2c_kernel<512, 8, 3>; FC_LAUNCH(k, g, b, smem, st, a); }
+  else if (p.kind == FC_C2R && p.M == 256) { auto k = fc_line_c2r_kernel<256, 8, 4>; FC_LAUNCH(k, g, b, smem, st, a); }
+  else if (p.kind == FC_C2R && p.M == 512) { auto k = fc_line_c2r_kernel<512, 8, 3>; FC_LAUNCH(k, g, b, smem, st, a); }
+  else return set_err(FC_EUNSUPPORTED, "no line kernel for this pass");
+  rec_mark();
+  return check_cuda("line pass launch");
 }
 
 int launch_fast_c2c(const fc_pass& p, const void* in, void* out, const float2* tw, cudaStream_t st) {
@@ -1213,6 +1242,10 @@ int fc_conv(const fc_plan* plan, const void* d_const, const float* d_x, const fl
       case FC_L_COL_R2C:
       case FC_L_COL_C2R:
         rc = launch_column(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, d_bias, st);
+        break;
+      case FC_L_LINE_R2C:
+      case FC_L_LINE_C2R:
+        rc = launch_line(L.pass, buf_ptr(b, L.src), buf_ptr(b, L.dst), tw, d_bias, st);
         break;
       case FC_L_CONTRACT: {
         const fc_contract_desc& c = plan->contract;

@@ -531,8 +531,10 @@ int fc_plan_build(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     P2.padding_mode = FC_PAD_CONSTANT;
     std::string m2;
     if (plan_build_core(pl, &P2, &m2) == FC_OK && !pl->prog.empty() &&
-        (pl->prog.front().type == FC_L_PASS || pl->prog.front().type == FC_L_COL_R2C) && pl->prog.front().pass.kind == FC_R2C &&
-        (pl->prog.back().type == FC_L_PASS || pl->prog.back().type == FC_L_COL_C2R) && pl->prog.back().pass.kind == FC_C2R &&
+        (pl->prog.front().type == FC_L_PASS || pl->prog.front().type == FC_L_COL_R2C || pl->prog.front().type == FC_L_LINE_R2C) &&
+        pl->prog.front().pass.kind == FC_R2C &&
+        (pl->prog.back().type == FC_L_PASS || pl->prog.back().type == FC_L_COL_C2R || pl->prog.back().type == FC_L_LINE_C2R) &&
+        pl->prog.back().pass.kind == FC_C2R &&
         pl->ax[0].Lout == c.Vo && pl->ax[0].N == c.Ns) {
       const int64_t Kd = (int64_t)(P.kernel_size[0] - 1) * P.dilation[0] + 1;
       const int Lout = (int)(((int64_t)P.in_size[0] + 2 * P.padding[0] - Kd) / P.stride[0] + 1);
@@ -984,6 +986,12 @@ bool column_pass_ok(const fc_pass& p) {
   return p.kind == FC_C2R && p.in_rs == 1 && p.out_rs == 0 && p.out_es == 1;
 }
 
+// The real pass of a one-pass 1-d program (contiguous lines of 512 or 1024 real points on both sides): fc_line.cuh.
+bool line_pass_ok(const fc_pass& p) {
+  return (p.M == 256 || p.M == 512) && p.R == 1 && p.flat && p.in_es == 1 && p.out_es == 1 && !p.in_rfast && !p.out_rfast && !p.twiddle &&
+         p.pos_n == 1 && p.pos_r == 0 && p.out_oq == 0 && p.seg_n <= 1;
+}
+
 bool plane_len(int n) { return n == 32 || n == 64 || n == 128; }
 bool plain_gather(const fc_imap& m) { return m.mode == FC_PAD_CONSTANT && m.up == 1 && m.sub == 1; }
 bool plain_crop(const fc_omap& m) { return m.og == 1 && m.os == 1 && m.ob >= 0; }
@@ -1099,8 +1107,11 @@ void fc_plan_build_program(fc_plan* pl) {
       L.type = FC_L_FAST_C2C;
     } else if (allow && !(flags & FC_FLAG_NO_FAST_R2C) && p.kind == FC_R2C && column_pass_ok(p)) {
       L.type = FC_L_COL_R2C;
+    } else if (allow && !(flags & FC_FLAG_NO_FAST_R2C) && p.kind == FC_R2C && line_pass_ok(p) && plain_gather(p.imap)) {
+      L.type = FC_L_LINE_R2C;
     }
     L.name = L.type == FC_L_FAST_R2C   ? "fast_r2c_N" + std::to_string(p.N)
+             : L.type == FC_L_LINE_R2C ? "line_r2c_N" + std::to_string(p.N)
              : L.type == FC_L_COL_R2C  ? "col_r2c_N" + std::to_string(p.N)
              : L.type == FC_L_FAST_C2C ? "fast_c2c_fwd_N" + std::to_string(p.N)
                                        : std::string("fwd_") + kKindName[p.kind] + "_N" + std::to_string(p.N);
@@ -1222,8 +1233,11 @@ void fc_plan_build_program(fc_plan* pl) {
       L.type = FC_L_FAST_C2C;
     } else if (allow && !(flags & FC_FLAG_NO_FAST_C2R) && p.kind == FC_C2R && column_pass_ok(p)) {
       L.type = FC_L_COL_C2R;
+    } else if (allow && !(flags & FC_FLAG_NO_FAST_C2R) && p.kind == FC_C2R && line_pass_ok(p) && p.omap.og == 1 && p.omap.os == 1 && p.row_og <= 1) {
+      L.type = FC_L_LINE_C2R;
     }
     L.name = L.type == FC_L_FAST_C2R   ? "fast_c2r_N" + std::to_string(p.N)
+             : L.type == FC_L_LINE_C2R ? "line_c2r_N" + std::to_string(p.N)
              : L.type == FC_L_COL_C2R  ? "col_c2r_N" + std::to_string(p.N)
              : L.type == FC_L_FAST_C2C ? "fast_c2c_inv_N" + std::to_string(p.N)
                                        : std::string("inv_") + kKindName[p.kind] + "_N" + std::to_string(p.N);

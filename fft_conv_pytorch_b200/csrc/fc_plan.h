@@ -42,7 +42,8 @@ struct fc_step {
 enum { FC_L_PASS = 0, FC_L_FAST_R2C = 1, FC_L_FAST_C2R = 2, FC_L_CONTRACT = 3, FC_L_FUSED = 4, FC_L_TC_X = 5, FC_L_TC_GEMM = 6, FC_L_TC_Y = 7, FC_L_FAST_C2C = 8, FC_L_COL_R2C = 9, FC_L_COL_C2R = 10, FC_L_PLANE_FWD = 11, FC_L_PLANE_INV = 12,
        FC_L_PAIR_R2C = 13, FC_L_PAIR_FUSED = 14, FC_L_PAIR_C2R = 15, FC_L_PAIR_FUSED64 = 16,
        FC_L_TC_FWD = 17,    // last forward pass writing the GEMM's Bt blobs itself (fc_tc_c2c_fwd_kernel)
-       FC_L_TC_INV = 18 };  // first inverse pass gathering from the GEMM's product (fc_tc_c2c_inv_kernel)
+       FC_L_TC_INV = 18,    // first inverse pass gathering from the GEMM's product (fc_tc_c2c_inv_kernel)
+       FC_L_LINE_R2C = 19, FC_L_LINE_C2R = 20 };  // the real passes of a one-pass 1-d program on the warp engine (fc_line.cuh)
 
 // Geometry of the fused "last forward axis -> contraction -> first inverse axis" kernel (fc_fused.cuh).
 struct fc_fused_desc {

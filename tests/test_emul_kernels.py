@@ -528,3 +528,25 @@ def test_plane_kernels_with_128_point_axes(xs, ws, kw):
     ref = F.conv3d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), **kw).numpy()
     assert y.shape == ref.shape and not np.isnan(y).any()
     assert rel_err(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("xs,ws,kw,line_out", [((5, 6, 1000), (4, 6, 33), dict(padding=7), True), ((3, 4, 512), (4, 2, 9), dict(groups=2), True),
+                                               ((1, 3, 700), (5, 3, 100), dict(padding=50, dilation=2), True), ((7, 2, 1024), (2, 2, 5), {}, True),
+                                               ((2, 2, 900), (2, 2, 5), dict(stride=2), False)])
+def test_short_1d_lines_on_the_warp_engine(xs, ws, kw, line_out):
+    """One-pass 1-d programs of 512 / 1024 points: fc_line.cuh (a strided output keeps the generic last pass)."""
+    import torch
+    import torch.nn.functional as F
+
+    rng = np.random.RandomState(4)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = rng.standard_normal(ws).astype(np.float32)
+    b = rng.standard_normal(ws[0]).astype(np.float32)
+    y, plan = emul.conv(x, w, b, **kw)
+    d = plan.describe()
+    assert "line_r2c_N" in d and ("line_c2r_N" in d) == line_out, d
+    y1, plan1 = emul.conv(x, w, b, flags=L.FC_FLAG_NO_FAST_R2C | L.FC_FLAG_NO_FAST_C2R, **kw)
+    assert "line_" not in plan1.describe()
+    ref = F.conv1d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), **kw).numpy()
+    assert y.shape == ref.shape and not np.isnan(y).any()
+    assert rel_err(y, ref) < 1e-5 and rel_err(y, y1) < 2e-6
