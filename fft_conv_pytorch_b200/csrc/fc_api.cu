@@ -191,6 +191,7 @@ void init_once() {
   cudaFuncSetAttribute(fc_tc_gemm_kernel<2, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   cudaFuncSetAttribute(fc_tc_gemm_kernel<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
 #ifndef FC_CPU_EMUL
+  cudaFuncSetAttribute(fc_contract_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   cudaFuncSetAttribute(fc_line_r2c_kernel<512, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   cudaFuncSetAttribute(fc_line_c2r_kernel<512, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
 #endif
@@ -285,6 +286,17 @@ int launch_contract(const float2* X, const float2* K, float2* Y, int64_t bins, i
       auto k = fc_contract_kernel<4, 4>;
       FC_LAUNCH(k, g, b, 0, st, a);
     }
+  } else if (batch >= 8 && Og >= 12 && cin / groups >= 48 && bins >= 4096 && !fc_tune_int("NO_CTILED", 0)) {
+    // wide channel groups on long spectra: 16 x 16 tiles fed through shared memory (fc_contract_tiled_kernel). Measured against
+    // the register tiles below (profiles/r2b_contraction_paths.txt): 64 channels, 33792 bins: 1278 -> 973 us; 96 channels: 2757 ->
+    // 2101 us; 64 channels, 8320 bins: 346 -> 285 us; but 32 channels, 33024 bins: 186 -> 251 us and 64 channels, 257 bins
+    // (batch 256): 143 -> 162 us, hence the bounds.
+    a.btiles = (batch + FC_CT_TB - 1) / FC_CT_TB;
+    a.otiles = (Og + FC_CT_TO - 1) / FC_CT_TO;
+    dim3 b(256), g((unsigned)((bins + 31) / 32), (unsigned)(a.btiles * a.otiles), (unsigned)groups);
+    const size_t smem = (size_t)FC_CT_KC * (FC_CT_TB + FC_CT_TO) * 32 * sizeof(float2);
+    auto k = fc_contract_tiled_kernel;
+    FC_LAUNCH(k, g, b, smem, st, a);
   } else if (batch >= 5 && Og >= 32) {
     // wide channels (BASELINE c4): 4 output tiles per CTA read the same signal spectrum (L1 hits for 3 of them)
     a.btiles = (batch + 7) / 8;

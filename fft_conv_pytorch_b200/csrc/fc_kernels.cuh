@@ -598,6 +598,75 @@ struct fc_contract_args {
   int32_t btiles, otiles;
 };
 
+// Contraction for channel groups too wide for register tiles alone (17 ... channels per group off the tensor-core path):
+// a CTA computes a 16-item x 16-output tile for 32 adjacent bins. The input channels go through shared memory eight at a
+// time (Xs / Ks: [8][16][32] complex, bins innermost, so both the coalesced global loads and the LDS of a warp are
+// contiguous 256-byte rows), and thread (bin lane, sub-tile) accumulates 4 items x 8 outputs in registers: 12 LDS.64 feed
+// 32 complex multiply-accumulates, and every signal / kernel value crosses L2 once per 16 outputs / 16 items instead of
+// once per 8 (the register-tile kernel below is L2-bound there: 0.8 - 1.3 TB/s at 64 channels, profiles/r2b_shape_probe.txt).
+#define FC_CT_TB 16
+#define FC_CT_TO 16
+#define FC_CT_KC 8
+__global__ void __launch_bounds__(256, 3) fc_contract_tiled_kernel(fc_contract_args a) {
+  fc_grid_dep_sync();
+  FC_DYN_SMEM(smem);
+  float2* Xs = smem;                                // [KC][TB][32]
+  float2* Ks = smem + FC_CT_KC * FC_CT_TB * 32;     // [KC][TO][32]
+  const int tid = threadIdx.x, lane = tid & 31, sub = tid >> 5;
+  const int bsub = (sub & 3) * 4, osub = (sub >> 2) * 8;  // this thread's 4 items and 8 outputs inside the tile
+  const int Ig = a.cin / a.groups, Og = a.cout / a.groups;
+  const int g = blockIdx.z;
+  const int bt = blockIdx.y / a.otiles, ot = blockIdx.y - bt * a.otiles;
+  const int b0 = bt * FC_CT_TB, o0 = ot * FC_CT_TO;
+  const int64_t f0 = (int64_t)blockIdx.x * 32;
+  const bool f_ok = f0 + lane < a.bins;
+  float2 acc[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[j][o] = make_float2(0.f, 0.f);
+  for (int i0 = 0; i0 < Ig; i0 += FC_CT_KC) {
+    // stage the next eight input channels: row r = (kk, j) of Xs / Ks is 32 bins of one (item, channel) / (output, channel)
+    for (int r = sub; r < FC_CT_KC * FC_CT_TB; r += 8) {
+      const int kk = r / FC_CT_TB, j = r - kk * FC_CT_TB;
+      const int i = i0 + kk, b = b0 + j, o = o0 + j;
+      const bool iv = i < Ig && f_ok;
+      Xs[r * 32 + lane] = (iv && b < a.batch) ? __ldg(a.X + ((int64_t)b * a.cin + g * Ig + i) * a.bins + f0 + lane) : make_float2(0.f, 0.f);
+      Ks[r * 32 + lane] = (iv && o < Og) ? __ldg(a.K + ((int64_t)(g * Og + o) * Ig + i) * a.bins + f0 + lane) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < FC_CT_KC; ++kk) {
+      float2 xv[4], kv[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xv[j] = Xs[(kk * FC_CT_TB + bsub + j) * 32 + lane];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) kv[o] = Ks[(kk * FC_CT_TO + osub + o) * 32 + lane];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          acc[j][o].x = fmaf(xv[j].x, kv[o].x, acc[j][o].x);
+          acc[j][o].y = fmaf(xv[j].x, kv[o].y, acc[j][o].y);
+          acc[j][o].x = fmaf(-xv[j].y, kv[o].y, acc[j][o].x);
+          acc[j][o].y = fmaf(xv[j].y, kv[o].x, acc[j][o].y);
+        }
+    }
+    __syncthreads();
+  }
+  if (!f_ok) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int b = b0 + bsub + j;
+    if (b >= a.batch) continue;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int oc = o0 + osub + o;
+      if (oc < Og) a.Y[((int64_t)b * a.cout + g * Og + oc) * a.bins + f0 + lane] = acc[j][o];
+    }
+  }
+}
+
 template <int TB, int TO>
 __global__ void fc_contract_kernel(fc_contract_args a) {
   fc_grid_dep_sync();

@@ -873,8 +873,9 @@ int plan_build_core(fc_plan* pl, const fc_problem* prob, std::string* msg) {
     // (output groups that are multiples of 64 only run on 64-row A tiles at ~2.2 TB/s against 3.5 - 3.9 TB/s on full tiles: that
     // beats the SIMT contraction (0.8 - 1.3 TB/s at 64 channels) once there are enough bins to fill the pipeline,
     // profiles/r2b_tc_64row_tiles.txt)
+    // With more bins the shared-memory-tiled SIMT contraction (fc_contract_tiled_kernel) is ahead again (profiles/r2b_contraction_paths.txt).
     pl->use_tc = !(P.flags & (FC_FLAG_NO_TC | FC_FLAG_NO_FUSED)) && Ig >= 32 && (2 * Ig) % 32 == 0 &&
-                 (Og % 128 == 0 || (Og % 64 == 0 && bins >= 2048));
+                 (Og % 128 == 0 || (Og % 64 == 0 && bins >= 2048 && bins < 8192));
 #ifdef FC_CPU_EMUL
     pl->use_tc = 0;  // tcgen05 cannot run in the host emulation
 #endif

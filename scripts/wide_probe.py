@@ -20,13 +20,14 @@ CASES = [((64, 16, 1024), (16, 16, 33)), ((256, 64, 512), (64, 64, 9)), ((32, 3,
          ((2, 8, 1024, 1024), (8, 8, 33, 33)), ((1, 3, 2048, 2048), (3, 3, 65, 65))]
 if len(sys.argv) > 1:
     CASES = eval(sys.argv[1])
+FLAGS = int(sys.argv[2]) if len(sys.argv) > 2 else 0  # FC_FLAG_* for every plan (32: no tensor cores)
 P = lambda t_: ctypes.c_void_p(t_.data_ptr())
 for xs, ws in CASES:
     x = torch.randn(*xs, device=dev)
     w = torch.randn(*ws, device=dev)
     b = torch.randn(ws[0], device=dev)
     nd = len(xs) - 2
-    entry = Fn.get_plan(False, xs[0], xs[1], ws[0], 1, tuple(xs[2:]), tuple(ws[2:]), (1,) * nd, (0,) * nd, (1,) * nd, (0,) * nd, "constant")
+    entry = Fn.get_plan(False, xs[0], xs[1], ws[0], 1, tuple(xs[2:]), tuple(ws[2:]), (1,) * nd, (0,) * nd, (1,) * nd, (0,) * nd, "constant", FLAGS)
     plan = entry.plan
     lib = plan.lib
     kspec = Fn.kernel_spectrum(entry, w, dev)

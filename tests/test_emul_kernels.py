@@ -254,8 +254,8 @@ _C2C_SHAPES = [
     ((2, 3, 50, 36), (3, 3, 5, 3), dict(padding=(2, 1), padding_mode="circular"), False),
     ((1, 2, 100, 20), (2, 1, 4, 3), dict(groups=2, stride=(3, 1), padding=(5, 0)), False),
     ((1, 2, 40, 20), (2, 2, 3, 3), dict(stride=2, padding=1, output_padding=1), True),
-    ((2, 2, 20, 70, 12), (2, 2, 3, 3, 3), {}, False),  # 3-d: the z passes (y extent 128, so no plane kernel)
-    ((1, 2, 40, 66, 10), (2, 2, 5, 3, 3), dict(stride=(2, 1, 1), dilation=(2, 1, 1)), True),
+    ((2, 2, 20, 140, 12), (2, 2, 3, 3, 3), {}, False),  # 3-d: the z passes (y extent 256, so no plane kernel)
+    ((1, 2, 40, 130, 10), (2, 2, 5, 3, 3), dict(stride=(2, 1, 1), dilation=(2, 1, 1)), True),  # (y extent 256 again)
 ]
 
 
@@ -550,3 +550,21 @@ def test_short_1d_lines_on_the_warp_engine(xs, ws, kw, line_out):
     ref = F.conv1d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), **kw).numpy()
     assert y.shape == ref.shape and not np.isnan(y).any()
     assert rel_err(y, ref) < 1e-5 and rel_err(y, y1) < 2e-6
+
+
+@pytest.mark.parametrize("xs,ws,kw", [((8, 48, 8100), (12, 48, 5), {}), ((9, 100, 120, 60), (26, 50, 3, 3), dict(groups=2, padding=1))])
+def test_shared_memory_tiled_contraction(xs, ws, kw):
+    """Wide channel groups on >= 4096 bins off the tensor-core path: fc_contract_tiled_kernel (ragged batch / channel tiles)."""
+    import torch
+    import torch.nn.functional as F
+
+    rng = np.random.RandomState(5)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = rng.standard_normal(ws).astype(np.float32)
+    b = rng.standard_normal(ws[0]).astype(np.float32)
+    y, plan = emul.conv(x, w, b, **kw)
+    assert int(plan.info.bins) >= 4096 and "launch contract" in plan.describe()
+    conv = F.conv1d if len(xs) == 3 else F.conv2d
+    ref = conv(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), **kw).numpy()
+    assert y.shape == ref.shape and not np.isnan(y).any()
+    assert rel_err(y, ref) < 1e-5
