@@ -254,8 +254,8 @@ _C2C_SHAPES = [
     ((2, 3, 50, 36), (3, 3, 5, 3), dict(padding=(2, 1), padding_mode="circular"), False),
     ((1, 2, 100, 20), (2, 1, 4, 3), dict(groups=2, stride=(3, 1), padding=(5, 0)), False),
     ((1, 2, 40, 20), (2, 2, 3, 3), dict(stride=2, padding=1, output_padding=1), True),
-    ((2, 2, 20, 140, 12), (2, 2, 3, 3, 3), {}, False),  # 3-d: the z passes (y extent 256, so no plane kernel)
-    ((1, 2, 40, 130, 10), (2, 2, 5, 3, 3), dict(stride=(2, 1, 1), dilation=(2, 1, 1)), True),  # (y extent 256 again)
+    ((1, 2, 20, 130, 12), (2, 2, 3, 3, 3), {}, False),  # 3-d: the z passes (y extent 256, so no plane kernel)
+    ((1, 1, 20, 130, 10), (1, 2, 5, 3, 3), dict(stride=(2, 1, 1), dilation=(2, 1, 1)), True),  # (y extent 256 again)
 ]
 
 
@@ -511,8 +511,7 @@ def test_short_lines_on_the_four_step_layout(xs, ws, kw):
     assert rel_err(y, ref) < 1e-5 and rel_err(y, y1) < 1e-5
 
 
-@pytest.mark.parametrize("xs,ws,kw", [((1, 2, 70, 100, 40), (2, 2, 3, 5, 3), {}), ((1, 1, 100, 40, 66), (2, 1, 5, 3, 3), dict(padding=(2, 1, 1))),
-                                      ((1, 2, 128, 128, 30), (1, 2, 2, 2, 2), {})])
+@pytest.mark.parametrize("xs,ws,kw", [((1, 1, 70, 100, 12), (2, 1, 3, 5, 3), {}), ((1, 1, 100, 40, 10), (1, 1, 5, 3, 3), dict(padding=(2, 1, 1)))])
 def test_plane_kernels_with_128_point_axes(xs, ws, kw):
     """3-d programs whose middle axes are 128 points long run on the plane kernels (a 128 x 128 plane is 129 KB of shared memory)."""
     import torch
@@ -552,7 +551,7 @@ def test_short_1d_lines_on_the_warp_engine(xs, ws, kw, line_out):
     assert rel_err(y, ref) < 1e-5 and rel_err(y, y1) < 2e-6
 
 
-@pytest.mark.parametrize("xs,ws,kw", [((8, 48, 8100), (12, 48, 5), {}), ((9, 100, 120, 60), (26, 50, 3, 3), dict(groups=2, padding=1))])
+@pytest.mark.parametrize("xs,ws,kw", [((9, 48, 8100), (13, 48, 5), {}), ((8, 100, 120, 60), (26, 50, 3, 3), dict(groups=2, padding=1))])
 def test_shared_memory_tiled_contraction(xs, ws, kw):
     """Wide channel groups on >= 4096 bins off the tensor-core path: fc_contract_tiled_kernel (ragged batch / channel tiles)."""
     import torch
