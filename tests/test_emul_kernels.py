@@ -337,16 +337,13 @@ _SEGMENT_SHAPES = [
     ((1, 2, 330, 40), (2, 2, 3, 3), dict(stride=2, padding=1, output_padding=1), True),  # zero-stuffed signal
     ((1, 2, 5000, 34), (2, 2, 31, 3), {}, False),  # longer than any single-line transform of this axis
     ((3, 2, 600, 34), (2, 2, 17, 3), dict(padding=(40, 0)), True),  # crop larger than the segment overlap
-    # ... and segments on the last axis as well: the row kernels K1 / K4 treat a (row, segment) pair as a line
-    ((2, 2, 300, 600), (3, 2, 9, 5), {}, False),
-    ((1, 9, 130, 600), (9, 9, 3, 7), dict(stride=(2, 2), dilation=(2, 2)), True),  # BASELINE c5 in small
+    # ... and segments on the last axis as well: the row kernels K1 / K4 treat a (row, segment) pair as a line (the strided /
+    # dilated / 2500-point variants of these run on the device only: tests/test_gpu_parity.py _SEGMENT_CASES)
+    ((1, 1, 300, 600), (2, 1, 9, 5), {}, False),
+    ((1, 3, 130, 600), (3, 3, 3, 7), dict(stride=(2, 2), dilation=(2, 2)), True),  # BASELINE c5 in small
     ((1, 2, 130, 700), (2, 2, 3, 4), {}, False),  # even kernel extent: segment stride rounded down to even
-    ((1, 2, 270, 640), (2, 1, 4, 6), dict(groups=2, stride=(1, 3)), False),  # strided scatter across segments
-    ((1, 2, 280, 660), (2, 2, 3, 4), dict(padding=(1, 3), dilation=(1, 2), output_padding=(0, 1)), True),
-    ((1, 2, 140, 2500), (2, 2, 3, 33), {}, False),
-    ((1, 3, 200, 1100), (3, 3, 3, 10), dict(padding=(0, 20)), True),  # crop across a segment boundary
+    ((1, 1, 130, 1100), (1, 1, 3, 10), dict(padding=(0, 20)), True),  # crop across a segment boundary
     ((1, 2, 130, 700), (2, 2, 3, 5), dict(padding=(1, 2)), False),  # zero padding inside the first / last row segment
-    ((1, 2, 280, 600), (2, 2, 3, 3), dict(dilation=(3, 2)), False),  # dilated kernel: longer segment overlap
 ]
 
 
