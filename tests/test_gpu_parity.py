@@ -917,3 +917,40 @@ def test_3d_programs_with_128_point_plane_axes(xs, ws, kw, tr):
     d = Fn._plans[next(reversed(Fn._plans))].plan.describe()
     assert ("plane_inv_128" in d if tr else "plane_fwd_" in d and "128" in d), d  # (a zero-stuffing gather keeps the forward passes apart)
     assert (y.double() - ref).abs().max().item() / ref.abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_1d_problems_across_the_round_2_paths(seed):
+    """Random 1-d forward problems over the ranges where the plan chooses between the line kernels (512 / 1024 points), the
+    four-step layout from 2048 points, batch segments (windows as batch items), the tiled / register-tile / tensor-core
+    contractions: lengths 300 ... 120000, 1 ... 96 channels per group, batches up to 40, every padding mode."""
+    rng = np.random.RandomState(5000 + seed)
+    groups = int(rng.choice([1, 1, 2, 3]))
+    ig = int(rng.choice([1, 3, 8, 16, 20, 48, 64, 96]))
+    og = int(rng.choice([1, 4, 8, 13, 32, 64, 128]))
+    cin, cout = ig * groups, og * groups
+    k = int(rng.choice([1, 2, 9, 33, 100, 513, 2049]))
+    dil = int(rng.choice([1, 1, 2, 3]))
+    stride = int(rng.choice([1, 1, 1, 2, 3]))
+    L_ = int(rng.choice([300, 500, 1000, 2000, 4000, 8100, 16500, 33000, 70000, 120000])) + int(rng.randint(0, 40))
+    L_ = max(L_, (k - 1) * dil + 1)
+    B = int(rng.choice([1, 2, 5, 9, 40]))
+    while B * (cin + cout) * L_ > 6e7:  # keep a case under ~0.25 GB
+        B = max(1, B // 2)
+        if B == 1:
+            break
+    if B * (cin + cout) * L_ > 6e7:
+        L_ = max(int(6e7 / (cin + cout)), (k - 1) * dil + 1)
+    mode = str(rng.choice(["constant", "constant", "reflect", "replicate", "circular"]))
+    pad = int(rng.randint(0, min(40, L_ - 1)))
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(B, cin, L_, device="cuda", generator=g)
+    w = torch.randn(cout, ig, k, device="cuda", generator=g)
+    b = torch.randn(cout, device="cuda", generator=g)
+    with torch.no_grad():
+        y = fcp.fft_conv(x, w, b, stride=stride, padding=pad, dilation=dil, groups=groups, padding_mode=mode)
+        xp = x.double() if mode == "constant" or pad == 0 else F.pad(x.double(), (pad, pad), mode=mode)
+        ref = F.conv1d(xp, w.double(), b.double(), stride=stride, padding=pad if mode == "constant" else 0, dilation=dil, groups=groups)
+    assert y.shape == ref.shape, (B, cin, cout, L_, k, stride, pad, dil, groups, mode)
+    err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < TOL, (err, B, cin, cout, L_, k, stride, pad, dil, groups, mode)
