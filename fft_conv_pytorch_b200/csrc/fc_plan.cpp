@@ -969,6 +969,8 @@ int64_t pass_bytes(const fc_pass& p) {
   // four-step 1-d layout: the real side of the R2C / C2R pass is one tensor of n_in / n_out elements per outer item
   const int64_t in_b = (p.kind == FC_R2C && p.pos_r) ? p.n_outer * (int64_t)p.imap.L * in_el : lines * (int64_t)p.n_in * in_el;
   const int64_t out_b = (p.kind == FC_C2R && p.pos_r) ? p.n_outer * (int64_t)p.omap.Lout * out_el : lines * (int64_t)p.n_out * out_el;
+  // overlap-save segments along the line (K1 / K4): the spectrum side holds seg_n half spectra per line
+  if (p.seg_n > 1) return p.kind == FC_R2C ? in_b + out_b * p.seg_n : p.kind == FC_C2R ? in_b * p.seg_n + out_b : in_b + out_b;
   return in_b + out_b;
 }
 
